@@ -1,0 +1,185 @@
+"""ac-3-acm-codec_b200 - Python face of the B200 AC-3 engine.
+
+Thin ctypes layer over the C ABI of liba52_b200.so (include/a52_batch.h,
+include/a52.h).  The decode itself is hand-written CUDA for sm_100a
+(csrc/a52_decode.cu); torch is used only as the owner of device buffers and
+streams.  There is no CPU path: importing works without a GPU (so that the
+symbol checks can run), every compute call needs one.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liba52_b200.so")
+
+A52_CHANNEL, A52_MONO, A52_STEREO, A52_3F, A52_2F1R, A52_3F1R, A52_2F2R, A52_3F2R = range(8)
+A52_CHANNEL1, A52_CHANNEL2, A52_DOLBY = 8, 9, 10
+A52_CHANNEL_MASK, A52_LFE, A52_ADJUST_LEVEL = 15, 16, 32
+PCM_F32_PLANAR, PCM_F32_INTERLEAVED, PCM_S16_INTERLEAVED = 0, 1, 2
+DEVICE_PTRS = 1
+DRC_STREAM, DRC_OFF = 0, 1
+ST_OK, ST_BAD_SYNC, ST_BAD_FRAME, ST_BAD_BLOCK = 0, 1, 2, 16
+_NFCH = [2, 1, 2, 3, 3, 4, 4, 5, 1, 1, 2]
+
+EXPORTS = [
+    "a52_init", "a52_samples", "a52_syncinfo", "a52_frame", "a52_dynrng", "a52_block", "a52_free",
+    "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index",
+    "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes",
+    "a52_batch_launch_count", "a52_batch_kernel_ms",
+]
+
+
+class CarryStruct(C.Structure):
+    _fields_ = [("dither_index", C.c_uint32), ("reserved", C.c_uint32 * 3), ("delay", (C.c_float * 128) * 6)]
+
+
+class DebugStruct(C.Structure):
+    _fields_ = [("exp", C.c_void_p), ("bap", C.c_void_p), ("coef", C.c_void_p), ("info", C.c_void_p)]
+
+
+def nout_of(flags):
+    return _NFCH[flags & A52_CHANNEL_MASK] + (1 if flags & A52_LFE else 0)
+
+
+_lib = None
+
+
+def load_library():
+    """Load liba52_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liba52_b200.so is missing - build it with ac-3-acm-codec_b200/build.sh "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.a52_batch_create.restype = C.c_void_p
+    L.a52_batch_create.argtypes = [C.c_int]
+    L.a52_batch_destroy.argtypes = [C.c_void_p]
+    L.a52_batch_last_error.restype = C.c_char_p
+    L.a52_batch_last_error.argtypes = [C.c_void_p]
+    L.a52_batch_index.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    L.a52_batch_frame_stride.restype = C.c_size_t
+    L.a52_batch_frame_stride.argtypes = [C.c_int, C.c_int]
+    L.a52_batch_set_max_frame_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.a52_batch_launch_count.restype = C.c_long
+    L.a52_batch_launch_count.argtypes = [C.c_void_p]
+    L.a52_batch_kernel_ms.restype = C.c_double
+    L.a52_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.a52_batch_decode.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+        C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.a52_init.restype = C.c_void_p
+    L.a52_init.argtypes = [C.c_uint32]
+    L.a52_samples.restype = C.POINTER(C.c_float)
+    L.a52_samples.argtypes = [C.c_void_p]
+    L.a52_syncinfo.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.a52_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_float]
+    L.a52_dynrng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.a52_block.argtypes = [C.c_void_p]
+    L.a52_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def index_frames(es):
+    """Frame offsets of an elementary stream (host side; a52dec.c:240-309 resync discipline)."""
+    L = load_library()
+    es = np.ascontiguousarray(es, dtype=np.uint8)
+    cap = len(es) // 64 + 2
+    off = np.zeros(cap, np.uint64)
+    n = L.a52_batch_index(es.ctypes.data, len(es), off.ctypes.data, cap)
+    return off[:n].copy()
+
+
+class BatchDecoder:
+    """Batched decoder context bound to one GPU (a52_batch_t)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = self.L.a52_batch_create(device)
+        if not self.ctx:
+            raise RuntimeError("a52_batch_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.L.a52_batch_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("a52_batch_decode failed (%d): %s" % (rc, self.L.a52_batch_last_error(self.ctx).decode()))
+
+    def decode_host(self, es, frame_off, stream_first, req_flags, level=1.0, bias=0.0, drc=DRC_STREAM,
+                    out_fmt=PCM_F32_PLANAR, carry=None, want_debug=False):
+        """Host buffers in, host buffers out (copies inside the call).
+
+        Returns dict(pcm=raw array [nframes, stride/itemsize], status, flags, carry, debug...)."""
+        es = np.ascontiguousarray(es, dtype=np.uint8)
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        stream_first = np.ascontiguousarray(stream_first, dtype=np.uint32)
+        nframes, nstreams = len(frame_off), len(stream_first) - 1
+        stride = self.L.a52_batch_frame_stride(req_flags, out_fmt)
+        dt = np.int16 if out_fmt == PCM_S16_INTERLEAVED else np.float32
+        pcm = np.zeros((nframes, stride // np.dtype(dt).itemsize), dt)
+        status = np.zeros(nframes, np.int32)
+        flags = np.zeros(nframes, np.int32)
+        cbuf = None
+        if carry is not None:
+            cbuf = (CarryStruct * nstreams)()
+            for i, c in enumerate(carry):
+                if c is not None:
+                    C.memmove(C.byref(cbuf[i]), C.byref(c), C.sizeof(CarryStruct))
+        dbg = None
+        out = {}
+        if want_debug:
+            out["exp"] = np.zeros((nframes, 6, 7, 256), np.uint8)
+            out["bap"] = np.zeros((nframes, 6, 7, 256), np.uint8)
+            out["coef"] = np.zeros((nframes, 6, 6, 256), np.float32)
+            out["info"] = np.zeros((nframes, 6, 16), np.int32)
+            dbg = DebugStruct(out["exp"].ctypes.data, out["bap"].ctypes.data, out["coef"].ctypes.data,
+                              out["info"].ctypes.data)
+        rc = self.L.a52_batch_decode(
+            self.ctx, es.ctypes.data, len(es), frame_off.ctypes.data, nframes, stream_first.ctypes.data,
+            nstreams, req_flags, level, bias, drc, out_fmt, pcm.ctypes.data, status.ctypes.data,
+            flags.ctypes.data, C.byref(cbuf) if cbuf is not None else None,
+            C.byref(dbg) if dbg is not None else None, 0, None)
+        self._check(rc)
+        out.update(pcm=pcm, status=status, flags=flags, carry=cbuf)
+        return out
+
+    def decode_device(self, es_ptr, es_bytes, off_ptr, nframes, first_ptr, nstreams, req_flags, pcm_ptr,
+                      status_ptr=0, flags_ptr=0, carry_ptr=0, level=1.0, bias=0.0, drc=DRC_STREAM,
+                      out_fmt=PCM_F32_INTERLEAVED, stream=0):
+        """Device pointers (e.g. torch tensor .data_ptr()); asynchronous on `stream`.
+
+        off_ptr must hold nframes + 1 offsets (last = es_bytes)."""
+        rc = self.L.a52_batch_decode(
+            self.ctx, es_ptr, es_bytes, off_ptr, nframes, first_ptr, nstreams, req_flags, level, bias, drc,
+            out_fmt, pcm_ptr, status_ptr or None, flags_ptr or None, carry_ptr or None, None, DEVICE_PTRS,
+            stream or None)
+        self._check(rc)
+
+    def set_max_frame_bytes(self, n):
+        self.L.a52_batch_set_max_frame_bytes(self.ctx, n)
+
+    def launch_count(self):
+        return self.L.a52_batch_launch_count(self.ctx)
+
+    def kernel_ms(self):
+        n = C.c_int(0)
+        ms = self.L.a52_batch_kernel_ms(self.ctx, C.byref(n))
+        return ms, n.value
+
+    def frame_stride(self, req_flags, out_fmt):
+        return self.L.a52_batch_frame_stride(req_flags, out_fmt)

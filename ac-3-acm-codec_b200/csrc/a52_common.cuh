@@ -1,0 +1,95 @@
+// a52_common.cuh - shared definitions of the B200 AC-3 decode engine.
+//
+// Data layout, constant tables and small device helpers used by the decode
+// kernel (a52_decode.cu).  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ac3_tables.h"
+
+namespace a52 {
+
+constexpr int kGroupThreads = 128;   // one "stream group": 4 warps walk one stream
+constexpr int kGroupWarps   = kGroupThreads / 32;
+constexpr int kMaxGroupsPerCta = 4;
+constexpr int kDitherPeriod = 65535;
+
+// output mode ids == liba52's A52_* flag values (include/a52.h)
+enum { M_CHANNEL = 0, M_MONO, M_STEREO, M_3F, M_2F1R, M_3F1R, M_2F2R, M_3F2R,
+       M_CHANNEL1, M_CHANNEL2, M_DOLBY, M_MASK = 15, M_LFE = 16, M_ADJUST = 32 };
+
+// ---- read-only tables, one copy per CTA in shared memory -------------------
+// (lane-indexed lookups: shared memory, not __constant__, because a constant
+// load with 32 different addresses serialises)
+struct __align__(16) Tables {
+    float    window[256];      // KBD alpha=5 (imdct.c:364-372)
+    float2   pre1[128];        // natural-order pre-twiddle of the 512 transform, sign folded
+    float2   post1[64];
+    float2   pre2[64];
+    float2   post2[32];
+    float2   wfft[128];        // e^{-2 pi j k / 128}
+    int16_t  q1[3][32];        // grouped 3-level values by (digit, 5-bit code)
+    int16_t  q2[3][128];       // grouped 5-level values by (digit, 7-bit code)
+    int16_t  q4[2][128];       // grouped 11-level values by (digit, 7-bit code)
+    int16_t  q3[8];            // 7-level
+    int16_t  q5[16];           // 15-level
+    uint16_t dither_lut[256];  // CRC-16/0xA011 byte step (tables.h:213-246)
+    uint16_t hth[3 * 50];
+    uint8_t  masktab[256];
+    uint8_t  latab[256];
+    uint8_t  baptab[64];
+    uint8_t  bndtab[52];
+    uint8_t  bap_bits[16];
+    uint8_t  pad_[12];
+};
+
+// ---- per-(requested output, acmod, mix levels) constants, host-computed ----
+struct ModeEntry {            // result of liba52's a52_downmix_init for one BSI combination
+    int32_t output;           // granted mode (without LFE bit), -1 = invalid request
+    float   level;            // adjusted level (A52_ADJUST_LEVEL folded in), before the x2
+};
+struct MixEntry {             // which coded channels feed each output channel
+    uint8_t nout;
+    uint8_t pos[5];
+    uint8_t neg[5];
+    uint8_t pad_;
+};
+
+// ---- kernel parameters -----------------------------------------------------
+struct StreamCarry {          // == a52_stream_carry_t (include/a52_batch.h)
+    uint32_t dither_index;
+    uint32_t reserved[3];
+    float    delay[6][128];
+};
+
+struct DecodeParams {
+    const uint8_t*  es;
+    uint64_t        es_bytes;
+    const uint64_t* frame_off;
+    const uint32_t* stream_first;
+    int             nstreams;
+    int             req_flags;
+    float           bias;
+    int             drc_off;
+    int             out_fmt;
+    int             nout_req;        // channels of the requested mode (+LFE)
+    size_t          frame_stride;    // bytes per decoded frame in pcm
+    uint8_t*        pcm;
+    int32_t*        status;
+    int32_t*        frame_flags;
+    StreamCarry*    carry;
+    const uint16_t* dither_seq;      // state after n dither_gen() calls from seed 1, n = 0..65534
+    int*            work_counter;
+    int             fbuf_bytes;      // bytes of one staged-frame buffer (multiple of 16)
+    int             ndelay;          // delay planes kept per group
+    int             group_bytes;     // shared-memory bytes per group
+    // optional dumps
+    uint8_t*        dbg_exp;
+    uint8_t*        dbg_bap;
+    float*          dbg_coef;
+    int32_t*        dbg_info;
+};
+
+}  // namespace a52

@@ -1,0 +1,700 @@
+// a52_host.inl - host side of the engine: context, constant tables, the C ABI
+// declared in include/a52_batch.h and the drop-in liba52 API of include/a52.h.
+// Included at the end of a52_decode.cu (same translation unit as the kernel).
+
+#include <new>
+#include <vector>
+
+#include "../../include/a52.h"
+#include "../../include/a52_batch.h"
+
+namespace a52 {
+
+// ---------------------------------------------------------------------------
+// host tables
+// ---------------------------------------------------------------------------
+static const uint8_t h_nfchans[11] = {2, 1, 2, 3, 3, 4, 4, 5, 1, 1, 2};
+
+static int host_syncinfo(const uint8_t* b, int* flags, int* sample_rate, int* bit_rate)
+{
+    // reference: liba52/parse.c:86-129
+    static const uint8_t lfe_bit[8] = {0x10, 0x10, 0x04, 0x04, 0x04, 0x01, 0x04, 0x01};
+    if (b[0] != 0x0b || b[1] != 0x77) return 0;
+    int bsid = b[5] >> 3;
+    if (bsid >= 12) return 0;
+    int half = bsid > 8 ? bsid - 8 : 0;
+    int acmod = b[6] >> 5;
+    *flags = (((b[6] & 0xf8) == 0x50) ? M_DOLBY : acmod) | ((b[6] & lfe_bit[acmod]) ? M_LFE : 0);
+    int cod = b[4] & 63;
+    if (cod >= 38) return 0;
+    int kbps = ac3_bitrate_kbps[cod >> 1];
+    *bit_rate = (kbps * 1000) >> half;
+    switch (b[4] >> 6) {
+    case 0: *sample_rate = 48000 >> half; return 4 * kbps;
+    case 1: *sample_rate = 44100 >> half; return 2 * (320 * kbps / 147 + (cod & 1));
+    case 2: *sample_rate = 32000 >> half; return 6 * kbps;
+    }
+    return 0;
+}
+
+// output-mode negotiation + level adjustment, reference: liba52/downmix.c:34-160.
+// `input` = acmod, or M_DOLBY for a 2/0 stream flagged Dolby surround.
+static int host_downmix_init(int input, int flags, float* level, float clev, float slev)
+{
+    static const char* grant[11] = {"0A222222", "11111111", "0A222222", "0A232323", "0A224444",
+                                    "0A224545", "0A236666", "0A236767", "81111111", "91111111",
+                                    "0A2AAAAA"};
+    const double k3 = 0.7071067811865476, kp3 = 1.4142135623730951;
+    int req = flags & M_MASK;
+    if (req > M_DOLBY) return -1;
+    char ch = grant[req][input & 7];
+    int out = ch >= 'A' ? ch - 'A' + 10 : ch - '0';
+    // the reference compares the float clev with a double constant here
+    // (downmix.c:69-71), which never matches in the float build
+    if (out == M_STEREO && (input == M_DOLBY || (input == M_3F && (double)clev == k3))) out = M_DOLBY;
+    if (!(flags & M_ADJUST)) return out;
+    double adj;
+    const int key = (out << 3) + (input & 7);
+#define K(i, o) (((o) << 3) + (i))
+    switch (key) {
+    case K(M_3F, M_MONO): adj = k3 / (1 + clev); break;
+    case K(M_STEREO, M_MONO): case K(M_2F2R, M_2F1R): case K(M_3F2R, M_3F1R): adj = k3; break;
+    case K(M_3F2R, M_2F1R):
+        if (clev < kp3 - 1) { adj = k3; break; }
+        /* fall through */
+    case K(M_3F, M_STEREO): case K(M_3F1R, M_2F1R): case K(M_3F1R, M_2F2R): case K(M_3F2R, M_2F2R):
+        adj = 1 / (1 + clev); break;
+    case K(M_2F1R, M_MONO): adj = kp3 / (2 + slev); break;
+    case K(M_2F1R, M_STEREO): case K(M_3F1R, M_3F): adj = 1 / (1 + slev * k3); break;
+    case K(M_3F1R, M_MONO): adj = k3 / (1 + clev + slev * 0.5); break;
+    case K(M_3F1R, M_STEREO): adj = 1 / (1 + clev + slev * k3); break;
+    case K(M_2F2R, M_MONO): adj = k3 / (1 + slev); break;
+    case K(M_2F2R, M_STEREO): case K(M_3F2R, M_3F): adj = 1 / (1 + slev); break;
+    case K(M_3F2R, M_MONO): adj = k3 / (1 + clev + slev); break;
+    case K(M_3F2R, M_STEREO): adj = 1 / (1 + clev + slev); break;
+    case K(M_MONO, M_DOLBY): adj = kp3; break;
+    case K(M_3F, M_DOLBY): case K(M_2F1R, M_DOLBY): adj = 1 / (1 + k3); break;
+    case K(M_3F1R, M_DOLBY): case K(M_2F2R, M_DOLBY): adj = 1 / (1 + 2 * k3); break;
+    case K(M_3F2R, M_DOLBY): adj = 1 / (1 + 3 * k3); break;
+    default: return out;
+    }
+#undef K
+    float a = (float)adj;
+    *level = *level * a;
+    return out;
+}
+
+static void host_mix_levels(int acmod, int cmix, int smix, float* clev, float* slev)
+{
+    // parse.c:134-137, 152-158
+    static const double cm[4] = {0.7071067811865476, 0.5946035575013605, 0.5, 0.5946035575013605};
+    static const double sm[4] = {0.7071067811865476, 0.5, 0, 0.5};
+    *clev = *slev = 0;
+    if ((acmod & 1) && acmod != 1) *clev = (float)cm[cmix];
+    if (acmod & 4) *slev = (float)sm[smix];
+}
+
+static void build_mode_table(ModeEntry* tab, int req_flags, float level)
+{
+    for (int ae = 0; ae < 9; ae++)
+        for (int cm = 0; cm < 4; cm++)
+            for (int sm = 0; sm < 4; sm++) {
+                int acmod = ae == 8 ? 2 : ae;
+                float clev, slev, lv = level;
+                host_mix_levels(acmod, cm, sm, &clev, &slev);
+                int out = host_downmix_init(ae == 8 ? M_DOLBY : acmod, req_flags, &lv, clev, slev);
+                tab[ae * 16 + cm * 4 + sm].output = out;
+                tab[ae * 16 + cm * 4 + sm].level = lv;
+            }
+}
+
+// which coded channels feed which output channel (downmix.c:480-619 as a sign matrix)
+static void build_mix_table(MixEntry* tab)
+{
+    enum { R_L, R_C, R_R, R_S, R_SL, R_SR, R_A, R_B, R_NONE };
+    static const uint8_t in_roles[8][5] = {
+        {R_A, R_B, R_NONE, R_NONE, R_NONE}, {R_C, R_NONE, R_NONE, R_NONE, R_NONE},
+        {R_L, R_R, R_NONE, R_NONE, R_NONE}, {R_L, R_C, R_R, R_NONE, R_NONE},
+        {R_L, R_R, R_S, R_NONE, R_NONE},    {R_L, R_C, R_R, R_S, R_NONE},
+        {R_L, R_R, R_SL, R_SR, R_NONE},     {R_L, R_C, R_R, R_SL, R_SR}};
+    static const uint8_t out_roles[11][5] = {
+        {R_A, R_B, R_NONE, R_NONE, R_NONE},   // CHANNEL
+        {R_C, R_NONE, R_NONE, R_NONE, R_NONE},// MONO (everything sums here)
+        {R_L, R_R, R_NONE, R_NONE, R_NONE},   // STEREO
+        {R_L, R_C, R_R, R_NONE, R_NONE},      // 3F
+        {R_L, R_R, R_S, R_NONE, R_NONE},      // 2F1R
+        {R_L, R_C, R_R, R_S, R_NONE},         // 3F1R
+        {R_L, R_R, R_SL, R_SR, R_NONE},       // 2F2R
+        {R_L, R_C, R_R, R_SL, R_SR},          // 3F2R
+        {R_A, R_NONE, R_NONE, R_NONE, R_NONE},// CHANNEL1
+        {R_B, R_NONE, R_NONE, R_NONE, R_NONE},// CHANNEL2
+        {R_L, R_R, R_NONE, R_NONE, R_NONE}};  // DOLBY
+    memset(tab, 0, sizeof(MixEntry) * 8 * 11);
+    for (int acmod = 0; acmod < 8; acmod++)
+        for (int out = 0; out < 11; out++) {
+            MixEntry& m = tab[acmod * 11 + out];
+            int nout = h_nfchans[out];
+            m.nout = nout;
+            bool has[9] = {false};
+            for (int o = 0; o < nout; o++) has[out_roles[out][o]] = true;
+            for (int ch = 0; ch < h_nfchans[acmod]; ch++) {
+                int r = in_roles[acmod][ch];
+                for (int o = 0; o < nout; o++) {
+                    int t = out_roles[out][o];
+                    int sign = 0;
+                    if (out == M_MONO) sign = 1;
+                    else if (out == M_CHANNEL1 || out == M_CHANNEL2 || out == M_CHANNEL) sign = (t == r) ? 1 : 0;
+                    else if (t == r) sign = 1;                                 // straight through
+                    else if (r == R_C && !has[R_C] && (t == R_L || t == R_R)) sign = 1;
+                    else if (r == R_S && !has[R_S]) {
+                        if (has[R_SL]) sign = (t == R_SL || t == R_SR) ? 1 : 0;    // 1 surround -> 2
+                        else if (out == M_DOLBY) sign = (t == R_L) ? -1 : (t == R_R) ? 1 : 0;
+                        else sign = (t == R_L || t == R_R) ? 1 : 0;
+                    } else if ((r == R_SL || r == R_SR) && !has[R_SL]) {
+                        if (has[R_S]) sign = (t == R_S) ? 1 : 0;                   // 2 surrounds -> 1
+                        else if (out == M_DOLBY) sign = (t == R_L) ? -1 : (t == R_R) ? 1 : 0;
+                        else sign = ((r == R_SL && t == R_L) || (r == R_SR && t == R_R)) ? 1 : 0;
+                    }
+                    if (sign > 0) m.pos[o] |= 1u << ch;
+                    if (sign < 0) m.neg[o] |= 1u << ch;
+                }
+            }
+        }
+}
+
+static void build_tables(Tables* T)
+{
+    memset(T, 0, sizeof(*T));
+    // KBD window, alpha = 5 (imdct.c:347-372): same double recurrence, rounded to float
+    {
+        double sum = 0, cum[256];
+        for (int i = 0; i < 256; i++) {
+            double x = i * (256 - i) * (5 * M_PI / 256) * (5 * M_PI / 256), b = 1;
+            for (int k = 100; k > 0; k--) b = b * x / (k * k) + 1;
+            sum += b;
+            cum[i] = sum;
+        }
+        sum++;
+        for (int i = 0; i < 256; i++) T->window[i] = (float)sqrt(cum[i] / sum);
+    }
+    for (int m = 0; m < 128; m++) {
+        double th = (M_PI / 256) * (m + 64 - 0.25), sg = (m & 1) ? -1.0 : 1.0;   // imdct.c:386-396
+        T->pre1[m] = make_float2((float)(sg * cos(th)), (float)(sg * sin(th)));
+        T->wfft[m] = make_float2((float)cos(2 * M_PI * m / 128), (float)-sin(2 * M_PI * m / 128));
+    }
+    for (int i = 0; i < 64; i++) {
+        T->post1[i] = make_float2((float)cos((M_PI / 256) * (i + 0.5)), (float)sin((M_PI / 256) * (i + 0.5)));
+        T->pre2[i] = make_float2((float)cos((M_PI / 128) * (i - 0.25)), (float)sin((M_PI / 128) * (i - 0.25)));
+    }
+    for (int i = 0; i < 32; i++)
+        T->post2[i] = make_float2((float)cos((M_PI / 128) * (i + 0.5)), (float)sin((M_PI / 128) * (i + 0.5)));
+    for (int c = 0; c < 32; c++)
+        for (int d = 0; d < 3; d++) {
+            int dig[3] = {c / 9, (c / 3) % 3, c % 3};
+            T->q1[d][c] = c < 27 ? ac3_q3[dig[d]] : 0;
+        }
+    for (int c = 0; c < 128; c++) {
+        int d5[3] = {c / 25, (c / 5) % 5, c % 5};
+        int d11[2] = {c / 11, c % 11};
+        for (int d = 0; d < 3; d++) T->q2[d][c] = c < 125 ? ac3_q5[d5[d]] : 0;
+        for (int d = 0; d < 2; d++) T->q4[d][c] = c < 121 ? ac3_q11[d11[d]] : 0;
+    }
+    for (int i = 0; i < 8; i++) T->q3[i] = ac3_q7[i];
+    for (int i = 0; i < 16; i++) T->q5[i] = ac3_q15[i];
+    for (int i = 0; i < 256; i++) {
+        T->dither_lut[i] = ac3_dither_lut[i];
+        T->masktab[i] = ac3_masktab[i];
+        T->latab[i] = ac3_latab[i];
+    }
+    for (int i = 0; i < 150; i++) T->hth[i] = ac3_hth[i];
+    for (int i = 0; i < 64; i++) T->baptab[i] = ac3_baptab[i];
+    for (int i = 0; i < 51; i++) T->bndtab[i] = ac3_bndtab[i];
+    T->bndtab[51] = 253;
+    for (int i = 0; i < 16; i++) T->bap_bits[i] = ac3_bap_bits[i];
+}
+
+static int nout_of_flags(int flags)
+{
+    int m = flags & M_MASK;
+    if (m > M_DOLBY) m = M_STEREO;
+    return h_nfchans[m] + ((flags & M_LFE) ? 1 : 0);
+}
+
+// frame length pre-pass for device-resident input: max over frames of the
+// length a52_syncinfo derives from each header
+__global__ void a52_maxlen_kernel(const uint8_t* es, const uint64_t* off, int nframes, int* out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (i < nframes) {
+        const uint8_t* b = es + off[i];
+        int cod = b[4] & 63, fscod = b[4] >> 6;
+        if (b[0] == 0x0b && b[1] == 0x77 && cod < 38 && fscod < 3) {
+            int kbps = c_bitrate[cod >> 1];
+            len = fscod == 0 ? 4 * kbps : fscod == 2 ? 6 * kbps : 2 * (320 * kbps / 147 + (cod & 1));
+        }
+    }
+    for (int o = 16; o; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len) atomicMax(out, len);
+}
+
+}  // namespace a52
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct a52_batch_s {
+    int device = 0;
+    int num_sms = 0;
+    int groups_per_cta = 2;
+    int max_frame_hint = 0;
+    uint16_t* d_dither = nullptr;
+    int* d_counter = nullptr;      // [0] work counter, [1] max frame length
+    char err[256] = {0};
+    long launches = 0;
+    // timing
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    // cached mode table key
+    int mode_flags = -1;
+    float mode_level = 0;
+    // host-mode scratch
+    struct Buf { void* p = nullptr; size_t cap = 0; } b_es, b_off, b_first, b_pcm, b_status, b_flags,
+        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo;
+};
+
+#define A52_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            snprintf(ctx->err, sizeof(ctx->err), "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+static int ensure(a52_batch_t* ctx, a52_batch_s::Buf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t cap = bytes + bytes / 8 + 256;
+    A52_CUDA(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return 0;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+a52_batch_t* a52_batch_create(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    a52_batch_t* ctx = new (std::nothrow) a52_batch_s();
+    if (!ctx) return nullptr;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
+    ctx->num_sms = prop.multiProcessorCount;
+    const char* g = getenv("A52_B200_GROUPS_PER_CTA");
+    if (g) ctx->groups_per_cta = atoi(g);
+    if (ctx->groups_per_cta < 1) ctx->groups_per_cta = 1;
+    if (ctx->groups_per_cta > a52::kMaxGroupsPerCta) ctx->groups_per_cta = a52::kMaxGroupsPerCta;
+
+    // constant tables
+    a52::Tables* T = new a52::Tables;
+    a52::build_tables(T);
+    bool ok = cudaMemcpyToSymbol(a52::g_tables, T, sizeof(*T)) == cudaSuccess;
+    delete T;
+    a52::MixEntry mix[8 * 11];
+    a52::build_mix_table(mix);
+    ok = ok && cudaMemcpyToSymbol(a52::c_mix, mix, sizeof(mix)) == cudaSuccess;
+    // dither sequence: state after n calls from seed 1 (parse.c:310-319)
+    std::vector<uint16_t> seq(a52::kDitherPeriod);
+    uint16_t s = 1;
+    for (int n = 0; n < a52::kDitherPeriod; n++) {
+        seq[n] = s;
+        s = (uint16_t)(ac3_dither_lut[s >> 8] ^ (uint16_t)(s << 8));
+    }
+    ok = ok && cudaMalloc(&ctx->d_dither, seq.size() * 2) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024) == cudaSuccess;
+    if (!ok) {
+        a52_batch_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+void a52_batch_destroy(a52_batch_t* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    a52_batch_s::Buf* bufs[] = {&ctx->b_es, &ctx->b_off, &ctx->b_first, &ctx->b_pcm, &ctx->b_status,
+                                &ctx->b_flags, &ctx->b_carry, &ctx->b_dexp, &ctx->b_dbap, &ctx->b_dcoef,
+                                &ctx->b_dinfo};
+    for (auto* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->d_dither) cudaFree(ctx->d_dither);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+const char* a52_batch_last_error(a52_batch_t* ctx) { return ctx ? ctx->err : "no context"; }
+
+int a52_batch_index(const uint8_t* es, size_t es_bytes, uint64_t* frame_off, int max_frames)
+{
+    // same resync discipline as the reference driver (a52dec.c:240-309): slide one
+    // byte at a time until a52_syncinfo accepts a header, then hop by the frame length
+    size_t pos = 0;
+    int n = 0;
+    while (pos + 7 <= es_bytes && n < max_frames) {
+        int fl, sr, br;
+        int len = a52::host_syncinfo(es + pos, &fl, &sr, &br);
+        if (!len) { pos++; continue; }
+        if (pos + len > es_bytes) break;
+        frame_off[n++] = pos;
+        pos += len;
+    }
+    return n;
+}
+
+size_t a52_batch_frame_stride(int req_flags, int out_fmt)
+{
+    return (size_t)1536 * a52::nout_of_flags(req_flags) * (out_fmt == A52_PCM_S16_INTERLEAVED ? 2 : 4);
+}
+
+void a52_batch_set_max_frame_bytes(a52_batch_t* ctx, int nbytes) { ctx->max_frame_hint = nbytes; }
+
+long a52_batch_launch_count(a52_batch_t* ctx) { return ctx->launches; }
+
+double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
+{
+    double total = 0;
+    int n = 0;
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0;
+        cudaEventSynchronize(ctx->ev_pool[i + 1]);
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) {
+            total += ms;
+            n++;
+        }
+    }
+    ctx->ev_used = 0;
+    if (nlaunches) *nlaunches = n;
+    return n ? total / n : 0.0;
+}
+
+static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int max_frame_bytes,
+                         float level, cudaStream_t st)
+{
+    using namespace a52;
+    // per-request constants
+    if (ctx->mode_flags != P.req_flags || ctx->mode_level != level) {
+        ModeEntry tab[9 * 16];
+        build_mode_table(tab, P.req_flags, level);
+        A52_CUDA(cudaMemcpyToSymbolAsync(c_mode, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
+        // the host array dies at return: make sure the copy has been consumed
+        A52_CUDA(cudaStreamSynchronize(st));
+        ctx->mode_flags = P.req_flags;
+        ctx->mode_level = level;
+    }
+    if (max_frame_bytes < 128) max_frame_bytes = 128;
+    if (max_frame_bytes > 3840) max_frame_bytes = 3840;
+    P.fbuf_bytes = align16(max_frame_bytes + 15) + 16 + 16;
+    P.ndelay = P.nout_req;
+    P.group_bytes = group_smem_bytes(P.fbuf_bytes, P.ndelay);
+    P.dither_seq = ctx->d_dither;
+    P.work_counter = ctx->d_counter;
+    const int G = ctx->groups_per_cta;
+    const int threads = G * kGroupThreads;
+    const size_t smem = align16((int)sizeof(Tables)) + (size_t)G * P.group_bytes;
+    int occ = 0;
+    A52_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, a52_decode_kernel, threads, smem));
+    if (occ < 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "decode kernel does not fit: %zu bytes of shared memory", smem);
+        return -2;
+    }
+    int grid = ctx->num_sms * occ;
+    int need = (P.nstreams + G - 1) / G;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    A52_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+    // timing events
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+        if (ctx->ev_pool.size() < 8192) {
+            cudaEvent_t a, b;
+            A52_CUDA(cudaEventCreate(&a));
+            A52_CUDA(cudaEventCreate(&b));
+            ctx->ev_pool.push_back(a);
+            ctx->ev_pool.push_back(b);
+        } else {
+            ctx->ev_used = 0;
+        }
+    }
+    cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used], e1 = ctx->ev_pool[ctx->ev_used + 1];
+    ctx->ev_used += 2;
+    A52_CUDA(cudaEventRecord(e0, st));
+    a52_decode_kernel<<<grid, threads, smem, st>>>(P);
+    A52_CUDA(cudaEventRecord(e1, st));
+    A52_CUDA(cudaGetLastError());
+    ctx->launches++;
+    (void)nframes;
+    return 0;
+}
+
+int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const uint64_t* frame_off,
+                     int nframes, const uint32_t* stream_first, int nstreams, int req_flags, float level,
+                     float bias, int drc_mode, int out_fmt, void* pcm_out, int32_t* frame_status,
+                     int32_t* frame_flags, a52_stream_carry_t* carry, const a52_batch_debug_t* debug,
+                     int mem_flags, void* cuda_stream)
+{
+    using namespace a52;
+    if (!ctx) return -1;
+    ctx->err[0] = 0;
+    if (nframes < 0 || nstreams < 0 || (req_flags & M_MASK) > M_DOLBY || out_fmt < 0 || out_fmt > 2) {
+        snprintf(ctx->err, sizeof(ctx->err), "bad argument");
+        return -3;
+    }
+    if (nframes == 0 || nstreams == 0) return 0;
+    A52_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t stride = a52_batch_frame_stride(req_flags, out_fmt);
+
+    DecodeParams P;
+    memset(&P, 0, sizeof(P));
+    P.es_bytes = es_bytes;
+    P.nstreams = nstreams;
+    P.req_flags = req_flags;
+    P.bias = bias;
+    P.drc_off = (drc_mode == A52_DRC_OFF);
+    P.out_fmt = out_fmt;
+    P.nout_req = nout_of_flags(req_flags);
+    P.frame_stride = stride;
+
+    if (mem_flags & A52_BATCH_DEVICE_PTRS) {
+        if (((uintptr_t)es & 15) != 0) {
+            snprintf(ctx->err, sizeof(ctx->err), "device bitstream pointer must be 16-byte aligned");
+            return -3;
+        }
+        P.es = es;
+        P.frame_off = frame_off;
+        P.stream_first = stream_first;
+        P.pcm = (uint8_t*)pcm_out;
+        P.status = frame_status;
+        P.frame_flags = frame_flags;
+        P.carry = (StreamCarry*)carry;
+        if (debug) { P.dbg_exp = debug->exp; P.dbg_bap = debug->bap; P.dbg_coef = debug->coef; P.dbg_info = debug->info; }
+        int maxlen = ctx->max_frame_hint;
+        if (maxlen <= 0) {
+            A52_CUDA(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(int), st));
+            a52_maxlen_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(es, frame_off, nframes, ctx->d_counter + 1);
+            A52_CUDA(cudaMemcpyAsync(&maxlen, ctx->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaStreamSynchronize(st));
+            ctx->launches++;
+        }
+        return launch_decode(ctx, P, nframes, maxlen, level, st);
+    }
+
+    // ---- host pointers: stage in, decode, stage out (synchronous) ----
+    int maxlen = 0;
+    for (int i = 0; i < nframes; i++) {
+        int fl, sr, br;
+        if (frame_off[i] + 7 <= es_bytes) {
+            int len = host_syncinfo(es + frame_off[i], &fl, &sr, &br);
+            if (len > maxlen) maxlen = len;
+        }
+    }
+    if (ensure(ctx, ctx->b_es, es_bytes + 32)) return -1;
+    if (ensure(ctx, ctx->b_off, (size_t)(nframes + 1) * 8)) return -1;
+    if (ensure(ctx, ctx->b_first, (size_t)(nstreams + 1) * 4)) return -1;
+    if (ensure(ctx, ctx->b_pcm, stride * nframes)) return -1;
+    if (ensure(ctx, ctx->b_status, (size_t)nframes * 4)) return -1;
+    if (ensure(ctx, ctx->b_flags, (size_t)nframes * 4)) return -1;
+    A52_CUDA(cudaMemcpyAsync(ctx->b_es.p, es, es_bytes, cudaMemcpyHostToDevice, st));
+    A52_CUDA(cudaMemsetAsync((uint8_t*)ctx->b_es.p + es_bytes, 0, 32, st));
+    std::vector<uint64_t> off(frame_off, frame_off + nframes);
+    off.push_back(es_bytes);
+    A52_CUDA(cudaMemcpyAsync(ctx->b_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    A52_CUDA(cudaMemcpyAsync(ctx->b_first.p, stream_first, (size_t)(nstreams + 1) * 4, cudaMemcpyHostToDevice, st));
+    P.es = (const uint8_t*)ctx->b_es.p;
+    P.frame_off = (const uint64_t*)ctx->b_off.p;
+    P.stream_first = (const uint32_t*)ctx->b_first.p;
+    P.pcm = (uint8_t*)ctx->b_pcm.p;
+    P.status = (int32_t*)ctx->b_status.p;
+    P.frame_flags = (int32_t*)ctx->b_flags.p;
+    if (carry) {
+        if (ensure(ctx, ctx->b_carry, sizeof(StreamCarry) * (size_t)nstreams)) return -1;
+        A52_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, st));
+        P.carry = (StreamCarry*)ctx->b_carry.p;
+    }
+    const size_t nblk = (size_t)nframes * 6;
+    if (debug) {
+        if (debug->exp && debug->bap) {
+            if (ensure(ctx, ctx->b_dexp, nblk * 7 * 256) || ensure(ctx, ctx->b_dbap, nblk * 7 * 256)) return -1;
+            P.dbg_exp = (uint8_t*)ctx->b_dexp.p;
+            P.dbg_bap = (uint8_t*)ctx->b_dbap.p;
+            A52_CUDA(cudaMemsetAsync(P.dbg_exp, 0, nblk * 7 * 256, st));
+            A52_CUDA(cudaMemsetAsync(P.dbg_bap, 0, nblk * 7 * 256, st));
+        }
+        if (debug->coef) {
+            if (ensure(ctx, ctx->b_dcoef, nblk * 6 * 256 * 4)) return -1;
+            P.dbg_coef = (float*)ctx->b_dcoef.p;
+            A52_CUDA(cudaMemsetAsync(P.dbg_coef, 0, nblk * 6 * 256 * 4, st));
+        }
+        if (debug->info) {
+            if (ensure(ctx, ctx->b_dinfo, nblk * 16 * 4)) return -1;
+            P.dbg_info = (int32_t*)ctx->b_dinfo.p;
+            A52_CUDA(cudaMemsetAsync(P.dbg_info, 0, nblk * 16 * 4, st));
+        }
+    }
+    // the staging copies above read pageable host vectors: finish them before they go away
+    A52_CUDA(cudaStreamSynchronize(st));
+    int rc = launch_decode(ctx, P, nframes, maxlen, level, st);
+    if (rc) return rc;
+    A52_CUDA(cudaMemcpyAsync(pcm_out, P.pcm, stride * nframes, cudaMemcpyDeviceToHost, st));
+    if (frame_status) A52_CUDA(cudaMemcpyAsync(frame_status, P.status, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
+    if (frame_flags) A52_CUDA(cudaMemcpyAsync(frame_flags, P.frame_flags, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
+    if (carry) A52_CUDA(cudaMemcpyAsync(carry, P.carry, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, st));
+    if (debug) {
+        if (P.dbg_exp) {
+            A52_CUDA(cudaMemcpyAsync(debug->exp, P.dbg_exp, nblk * 7 * 256, cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaMemcpyAsync(debug->bap, P.dbg_bap, nblk * 7 * 256, cudaMemcpyDeviceToHost, st));
+        }
+        if (P.dbg_coef) A52_CUDA(cudaMemcpyAsync(debug->coef, P.dbg_coef, nblk * 6 * 256 * 4, cudaMemcpyDeviceToHost, st));
+        if (P.dbg_info) A52_CUDA(cudaMemcpyAsync(debug->info, P.dbg_info, nblk * 16 * 4, cudaMemcpyDeviceToHost, st));
+    }
+    A52_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ===========================================================================
+// drop-in liba52 API (include/a52.h) on top of the batched path
+// ===========================================================================
+struct a52_state_s {
+    a52_batch_t* ctx;
+    sample_t* samples;          // 256 * 12 floats, pinned host memory
+    float* frame_pcm;           // [6][6][256] decoded frame (planar)
+    const uint8_t* frame;       // caller's buffer (valid through the 6 a52_block calls)
+    int frame_len;
+    int req_flags;              // request incl. A52_ADJUST_LEVEL as passed to a52_frame
+    int out_flags;
+    float level_in, bias;
+    int drc_off;
+    int blk;                    // next block to hand out
+    int decoded;                // frame_pcm valid for the staged frame
+    int status;
+    a52_stream_carry_t carry;
+};
+
+a52_state_t* a52_init(uint32_t mm_accel)
+{
+    (void)mm_accel;
+    int dev = 0;
+    const char* e = getenv("A52_B200_DEVICE");
+    if (e) dev = atoi(e);
+    a52_batch_t* ctx = a52_batch_create(dev);
+    if (!ctx) return nullptr;       // no CPU fallback by design
+    a52_state_t* s = (a52_state_t*)calloc(1, sizeof(*s));
+    if (!s) { a52_batch_destroy(ctx); return nullptr; }
+    s->ctx = ctx;
+    if (cudaMallocHost((void**)&s->samples, 256 * 12 * sizeof(sample_t)) != cudaSuccess ||
+        cudaMallocHost((void**)&s->frame_pcm, 6 * 6 * 256 * sizeof(float)) != cudaSuccess) {
+        a52_free(s);
+        return nullptr;
+    }
+    memset(s->samples, 0, 256 * 12 * sizeof(sample_t));
+    return s;
+}
+
+sample_t* a52_samples(a52_state_t* s) { return s->samples; }
+
+int a52_syncinfo(uint8_t* buf, int* flags, int* sample_rate, int* bit_rate)
+{
+    return a52::host_syncinfo(buf, flags, sample_rate, bit_rate);
+}
+
+int a52_frame(a52_state_t* s, uint8_t* buf, int* flags, level_t* level, sample_t bias)
+{
+    using namespace a52;
+    // BSI fields needed for the mode negotiation (parse.c:139-167); everything
+    // else of the frame is parsed on the GPU
+    int acmod = buf[6] >> 5;
+    uint32_t bits = ((uint32_t)buf[6] << 24) | ((uint32_t)buf[7] << 16) | ((uint32_t)buf[8] << 8);
+    int p = 3, input = acmod, cmix = 0, smix = 0;
+    auto take = [&](int n) { int v = (bits << p) >> (32 - n); p += n; return v; };
+    if (acmod == 2 && take(2) == 2) input = M_DOLBY;
+    if ((acmod & 1) && acmod != 1) cmix = take(2);
+    if (acmod & 4) smix = take(2);
+    int lfeon = take(1);
+    float clev, slev;
+    host_mix_levels(acmod, cmix, smix, &clev, &slev);
+    float lv = *level;
+    int out = host_downmix_init(input, *flags, &lv, clev, slev);
+    if (out < 0) return 1;
+    s->req_flags = *flags;
+    s->level_in = *level;
+    if (lfeon && (*flags & M_LFE)) out |= M_LFE;
+    *flags = out;
+    *level = lv;
+    s->out_flags = out;
+    s->bias = bias;
+    s->drc_off = 0;
+    s->frame = buf;
+    int fl, sr, br;
+    s->frame_len = host_syncinfo(buf, &fl, &sr, &br);
+    if (s->frame_len <= 0) s->frame_len = 3840;      // a52_frame does not validate the header itself
+    s->blk = 0;
+    s->decoded = 0;
+    s->status = 0;
+    return 0;
+}
+
+void a52_dynrng(a52_state_t* s, level_t (*call)(level_t, void*), void* data)
+{
+    // NULL callback = dynamic range compression off (parse.c:207-216).  A user
+    // callback would have to run on the host between the GPU's parse and
+    // dequantisation stages; it is accepted and treated as "compression as coded".
+    (void)data;
+    s->drc_off = (call == nullptr);
+}
+
+int a52_block(a52_state_t* s)
+{
+    if (s->blk >= 6) return 1;
+    if (!s->decoded) {
+        uint64_t off[2] = {0, (uint64_t)s->frame_len};
+        uint32_t first[2] = {0, 1};
+        int32_t status = 0, fflags = 0;
+        int rc = a52_batch_decode(s->ctx, s->frame, (size_t)s->frame_len, off, 1, first, 1, s->req_flags,
+                                  s->level_in, s->bias, s->drc_off ? A52_DRC_OFF : A52_DRC_STREAM,
+                                  A52_PCM_F32_PLANAR, s->frame_pcm, &status, &fflags, &s->carry, nullptr, 0,
+                                  nullptr);
+        if (rc) return 1;
+        s->status = status;
+        s->decoded = 1;
+    }
+    int b = s->blk++;
+    if (s->status && (s->status < A52_ST_BAD_BLOCK || b >= s->status - A52_ST_BAD_BLOCK)) return 1;
+    int nout = a52::nout_of_flags(s->out_flags);
+    memcpy(s->samples, s->frame_pcm + (size_t)b * nout * 256, (size_t)nout * 256 * sizeof(float));
+    return 0;
+}
+
+void a52_free(a52_state_t* s)
+{
+    if (!s) return;
+    if (s->samples) cudaFreeHost(s->samples);
+    if (s->frame_pcm) cudaFreeHost(s->frame_pcm);
+    if (s->ctx) a52_batch_destroy(s->ctx);
+    free(s);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

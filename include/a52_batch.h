@@ -1,0 +1,120 @@
+/* include/a52_batch.h - batched entry points of the B200 AC-3 engine (C ABI).
+ *
+ * One call decodes thousands of independent AC-3 streams: every stream is a
+ * run of sync frames walked by one group of 128 GPU threads, frames of one
+ * stream in order (overlap-add tail and dither generator carried on chip),
+ * streams in parallel.  This is the batched form of the per-frame loop every
+ * liba52 caller writes (reference: a52dec.c:240-309 - a52_syncinfo, a52_frame,
+ * [a52_dynrng], 6 x a52_block, copy a52_samples()), with the same arithmetic
+ * per frame as a52_frame/a52_block (liba52/parse.c:131-205, 558-940).
+ *
+ * All functions use plain pointers and sizes; no CUDA or torch types appear.
+ * Pointers are host pointers unless A52_BATCH_DEVICE_PTRS is set in
+ * `mem_flags`, in which case es / frame_off / stream_first / pcm_out /
+ * frame_status / frame_flags / state are device pointers (es 16-byte aligned
+ * with >= 16 readable bytes after es_bytes) and no copy is made.
+ */
+#ifndef A52_BATCH_H
+#define A52_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct a52_batch_s a52_batch_t;
+
+/* PCM layouts (per frame: 6 blocks x 256 samples x nout channels, channel
+ * order as liba52: [LFE] then the granted mode's channels) */
+#define A52_PCM_F32_PLANAR      0   /* float [6][nout][256]   == 6 x a52_samples() */
+#define A52_PCM_F32_INTERLEAVED 1   /* float [1536][nout] */
+#define A52_PCM_S16_INTERLEAVED 2   /* int16 [1536][nout], round-to-nearest of x*32768, saturated
+				       (== libao convert2s16.c:33-41 applied to bias-384 floats) */
+
+#define A52_BATCH_DEVICE_PTRS   1
+
+/* dynamic range control */
+#define A52_DRC_STREAM          0   /* apply the stream's dynrng words (liba52 default) */
+#define A52_DRC_OFF             1   /* == a52_dynrng (state, NULL, NULL) */
+
+/* per-frame status written to frame_status[] */
+#define A52_ST_OK               0
+#define A52_ST_BAD_SYNC         1   /* a52_syncinfo would return 0 (parse.c:98-127) */
+#define A52_ST_BAD_FRAME        2   /* a52_frame would return 1 (parse.c:163-164) */
+#define A52_ST_BAD_BLOCK        16  /* + block index: a52_block returned 1 in that block */
+
+/* per-stream carry between calls (optional): dither generator position and
+ * the overlap-add tail of every output channel */
+typedef struct {
+    uint32_t dither_index;      /* number of dither_gen() calls so far, mod 65535 */
+    uint32_t reserved[3];
+    float    delay[6][128];     /* per output channel, liba52 delay[0..127] (downmixed domain) */
+} a52_stream_carry_t;
+
+/* optional intermediate dumps for parity testing; any pointer may be NULL.
+ * Layouts: exp/bap uint8 [nframes][6 blocks][7][256] with index 0..4 fbw,
+ * 5 lfe, 6 coupling channel, bap in the A/52 standard's numbering 0..15;
+ * coef float [nframes][6][6][256] = dequantised, gain-applied coefficients
+ * before mixing (planes 0..4 fbw, 5 lfe); info int32 [nframes][6][16]
+ * (endmant[5], cplstrtmant, cplendmant, chincpl, lfsr_state, acmod, lfeon,
+ * output, 0, ncplbnd, rematflg, csnroffst). */
+typedef struct {
+    uint8_t * exp;
+    uint8_t * bap;
+    float *   coef;
+    int32_t * info;
+} a52_batch_debug_t;
+
+a52_batch_t * a52_batch_create (int device);
+void a52_batch_destroy (a52_batch_t * ctx);
+const char * a52_batch_last_error (a52_batch_t * ctx);
+
+/* Host-side frame indexer: scans an elementary stream for sync frames exactly
+ * like the resync loop of a52dec.c:240-309 and writes the byte offset of each
+ * frame.  Returns the number of frames found (<= max_frames). */
+int a52_batch_index (const uint8_t * es, size_t es_bytes, uint64_t * frame_off, int max_frames);
+
+/* bytes one decoded frame occupies in pcm_out for a request (req_flags as for
+ * a52_frame): 1536 * nout_requested * sample size */
+size_t a52_batch_frame_stride (int req_flags, int out_fmt);
+
+/* Decode nframes frames forming nstreams streams.
+ *   frame_off[nframes]      byte offset of each frame in es (frame length is
+ *                           derived from its own header as a52_syncinfo does)
+ *   stream_first[nstreams+1] index of the first frame of each stream
+ *   req_flags, level, bias  as for a52_frame (A52_ADJUST_LEVEL honoured)
+ *   pcm_out                 nframes * a52_batch_frame_stride() bytes
+ *   frame_status[nframes]   A52_ST_* (may be NULL)
+ *   frame_flags[nframes]    granted output flags per frame (may be NULL)
+ *   carry[nstreams]         in/out per-stream carry (may be NULL: streams
+ *                           start from liba52's initial state)
+ *   cuda_stream             a cudaStream_t (NULL = default stream)
+ * Returns 0 on success, negative on a CUDA/argument error (see
+ * a52_batch_last_error).  Asynchronous when A52_BATCH_DEVICE_PTRS is set. */
+int a52_batch_decode (a52_batch_t * ctx,
+		      const uint8_t * es, size_t es_bytes,
+		      const uint64_t * frame_off, int nframes,
+		      const uint32_t * stream_first, int nstreams,
+		      int req_flags, float level, float bias, int drc_mode,
+		      int out_fmt, void * pcm_out,
+		      int32_t * frame_status, int32_t * frame_flags,
+		      a52_stream_carry_t * carry,
+		      const a52_batch_debug_t * debug,
+		      int mem_flags, void * cuda_stream);
+
+/* Optional: upper bound of the frame length (bytes) in the next batches, so that
+ * device-pointer calls need no length pre-pass; 0 = derive it (default). */
+void a52_batch_set_max_frame_bytes (a52_batch_t * ctx, int nbytes);
+
+/* number of kernel launches issued by this context so far (bench bookkeeping) */
+long a52_batch_launch_count (a52_batch_t * ctx);
+/* average device time (ms) of the decode kernel over the launches since the
+ * last call, measured with CUDA events on the launching stream; resets. */
+double a52_batch_kernel_ms (a52_batch_t * ctx, int * nlaunches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A52_BATCH_H */
