@@ -158,6 +158,18 @@ class BatchDecoder:
         out.update(pcm=pcm, status=status, flags=flags, carry=cbuf)
         return out
 
+    def decode_host_into(self, es_ptr, es_bytes, frame_off, stream_first, req_flags, pcm_ptr, status_ptr=0,
+                         flags_ptr=0, level=1.0, bias=0.0, drc=DRC_STREAM, out_fmt=PCM_F32_INTERLEAVED):
+        """Host pointers (ideally pinned) in and out, no allocation here: the host form of
+        a52_batch_decode with caller-owned buffers.  Synchronous."""
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        stream_first = np.ascontiguousarray(stream_first, dtype=np.uint32)
+        rc = self.L.a52_batch_decode(
+            self.ctx, es_ptr, es_bytes, frame_off.ctypes.data, len(frame_off), stream_first.ctypes.data,
+            len(stream_first) - 1, req_flags, level, bias, drc, out_fmt, pcm_ptr, status_ptr or None,
+            flags_ptr or None, None, None, 0, None)
+        self._check(rc)
+
     def decode_device(self, es_ptr, es_bytes, off_ptr, nframes, first_ptr, nstreams, req_flags, pcm_ptr,
                       status_ptr=0, flags_ptr=0, carry_ptr=0, level=1.0, bias=0.0, drc=DRC_STREAM,
                       out_fmt=PCM_F32_INTERLEAVED, stream=0):

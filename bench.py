@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py - decoded audio-seconds per second, batched 5.1 448 kb/s AC-3 decode on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # liba52 on the host cores
+
+Workload (BASELINE.json configs[1]): 4096 independent 10 s streams (313 frames each) of
+5.1 / 48 kHz / 448 kb/s AC-3 per GPU, full path (exponents, bit allocation, dequantisation,
+IMDCT-512, stereo downmix), float32 stereo PCM out.  The bitstreams are the committed
+reference-encoded fixture (tests/golden/c2_fixture.npz: 4 unique streams x 64 frames of synthetic
+multitone + noise) tiled to the batch shape with per-stream frame rotation.
+A "step" is one pass of the decode over the whole batch.  One line of JSON is printed by rank 0.
+
+  value      : audio-s/s, bitstream already resident in HBM, PCM left in HBM (CUDA events, max over ranks)
+  e2e        : the same through the C ABI with HOST buffers (pinned): H2D of the bitstream and
+               D2H of the PCM inside the timed region
+  roofline   : decode kernel vs the HBM roofline - algorithmic bytes (1792 B read + 12288 B
+               written per frame) / mean kernel time measured live with CUDA events
+  cpu_baseline: the unmodified reference (oracle/_ref, liba52 compiled from /root/reference) or the
+               oracle port, one process per host core, on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_BYTES = 1792                  # 5.1 @ 448 kb/s, 48 kHz (parse.c:119)
+FRAME_SECONDS = 1536 / 48000.0
+PCM_BYTES = 1536 * 2 * 4            # float32 stereo per frame
+ALGO_BYTES_PER_FRAME = FRAME_BYTES + PCM_BYTES      # 14080
+A52_STEREO, A52_ADJUST_LEVEL = 2, 32
+REQ_FLAGS = A52_STEREO | A52_ADJUST_LEVEL
+METRIC = "decoded audio-sec/sec, 5.1 448k AC-3, batched streams"
+UNIT = "audio-s/s"
+
+
+def build_corpus(nstreams, nframes):
+    """[nstreams, nframes, 1792] uint8: fixture streams tiled, stream s starts at frame 7*s of base s%4."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "c2_fixture.npz"))["frames"]
+    nb, nf = fx.shape[0], fx.shape[1]
+    idx = (np.arange(nframes)[None, :] + 7 * np.arange(nstreams)[:, None]) % nf
+    base = np.arange(nstreams) % nb
+    return fx[base[:, None], idx]
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference decoder on the host cores (checker code: the only use of oracle/ here)
+# ---------------------------------------------------------------------------
+_cpu = {}
+
+
+def _cpu_init(kind):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refbind
+    _cpu["lib"] = refbind.RefA52() if kind == "reference" else refbind.Oracle()
+    _cpu["es"] = build_corpus(4, 313).reshape(4, -1)
+    _cpu["out"] = np.zeros((313 * 6 + 8, 2, 256), np.float32)
+
+
+def _cpu_work(nstreams):
+    import ctypes as C
+    lib = _cpu["lib"]
+    fn = lib.lib.ref_decode_stream if hasattr(lib.lib, "ref_decode_stream") else lib.lib.ora_decode_stream
+    t0 = time.perf_counter()
+    frames = 0
+    out = _cpu["out"]
+    for s in range(nstreams):
+        es = _cpu["es"][s % 4]
+        nf = fn(None, es.ctypes.data_as(C.POINTER(C.c_uint8)), len(es), REQ_FLAGS, 1.0, 0.0,
+                out.ctypes.data_as(C.POINTER(C.c_float)), 2, 0)
+        assert nf == 313, nf
+        frames += nf
+    return frames, time.perf_counter() - t0
+
+
+class CpuArm:
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refbind
+        self.kind = "reference" if refbind.have_ref() else "port"
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            self.cores = os.cpu_count() or 1
+        import multiprocessing as mp
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
+        self.pool.map(_cpu_work, [1] * self.cores)               # warm: page in, tables
+
+    def run(self, streams_per_core):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_work, [streams_per_core] * self.cores, chunksize=1)
+        wall = time.perf_counter() - t0
+        frames = sum(r[0] for r in res)
+        return frames * FRAME_SECONDS, wall
+
+    def calibrate(self, target_s):
+        self.run(2)                                  # every worker initialised and warm
+        secs, wall = self.run(8)
+        per_stream = wall / 8.0
+        return max(1, int(target_s / max(per_stream, 1e-4)))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    arm = CpuArm()
+    k = arm.calibrate(2.0)                                   # ~2 s of CPU work per core per step
+    for _ in range(args.warmup):
+        arm.run(k)
+    t_total, a_total = 0.0, 0.0
+    for _ in range(args.steps):
+        a, w = arm.run(k)
+        a_total += a
+        t_total += w
+    arm.close()
+    v = a_total / t_total
+    sample = "%d streams x 313 frames per core per step (%d cores), in memory, stereo float out" % (k, arm.cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": "5.1 48 kHz 448 kbps decode, %d independent %.1f s streams per GPU, stereo downmix, "
+                        "float32 PCM (BASELINE.json configs[1])" % (args.streams, args.frames * FRAME_SECONDS),
+            "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "frame_bytes": FRAME_BYTES,
+            "out": "f32 stereo interleaved", "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2"
+            % (args.streams * args.frames * ALGO_BYTES_PER_FRAME / 1e9)}
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, ln in self.rows:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            p = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx = max(mx, float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (fork-based pool: must happen before CUDA is initialised in this process)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        arm = CpuArm()
+        k = arm.calibrate(args.cpu_seconds)
+        a, w = arm.run(k)
+        arm.close()
+        cpu_baseline = {"value": a / w, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                        "sample": "%d streams x 313 frames per core (%d cores, %.1f s wall), in memory, stereo float out"
+                                  % (k, arm.cores, w)}
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    eng = ge.load_engine()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the decode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import importlib
+    shard = importlib.import_module("ac3_acm_codec_b200.shard")
+
+    S, F = args.streams, args.frames
+    nframes = S * F
+    corpus = build_corpus(S, F)                                # weak scaling: every rank decodes S streams
+    es_host = torch.from_numpy(corpus.reshape(-1))
+    es_bytes = es_host.numel()
+    dev = torch.device("cuda", local)
+    es = torch.zeros(es_bytes + 64, dtype=torch.uint8, device=dev)
+    es[:es_bytes].copy_(es_host)
+    off = torch.arange(nframes + 1, dtype=torch.int64, device=dev) * FRAME_BYTES
+    first = (torch.arange(S + 1, dtype=torch.int64, device=dev) * F).to(torch.int32)
+    pcm = torch.empty(nframes * 1536 * 2, dtype=torch.float32, device=dev)
+    status = torch.zeros(nframes, dtype=torch.int32, device=dev)
+
+    dec = eng.BatchDecoder(local)
+    dec.set_max_frame_bytes(FRAME_BYTES)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        dec.decode_device(es.data_ptr(), es_bytes, off.data_ptr(), nframes, first.data_ptr(), S, REQ_FLAGS,
+                          pcm.data_ptr(), status_ptr=status.data_ptr(), out_fmt=eng.PCM_F32_INTERLEAVED,
+                          stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    assert int((status != 0).sum().item()) == 0, "decode reported frame errors"
+    dec.kernel_ms()                                            # reset the kernel-time accumulator
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.25)
+    l0 = dec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    ms = shard.max_over_ranks(ms)
+    launches = dec.launch_count() - l0
+    kms, kn = dec.kernel_ms()
+    clocks = sampler.window(t0, t1) if sampler else None
+    audio_s_per_step = nframes * FRAME_SECONDS * world
+    value = audio_s_per_step * args.steps / (ms / 1e3)
+
+    # checksum of the device result against the fixture digest (cheap sanity: sum of squares of stream 0)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "c2_fixture.npz"))
+    if F >= 64:
+        got = float((pcm[: 64 * 3072].double() ** 2).sum().item())
+        want = float(fx["digest"][0][1])
+        assert abs(got - want) / want < 1e-5, ("stream 0 energy differs from the reference digest", got, want)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, eng, dec, corpus, shard, barrier, world)
+
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        peaks, peak_src = None, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks["hbm_gbs"]) if peaks and peaks.get("hbm_gbs") else 6650.0
+        if peaks and peaks.get("hbm_gbs"):
+            peak_src = "measured"
+        achieved = nframes * ALGO_BYTES_PER_FRAME / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "a52_decode_kernel", "kernel_ms": kms, "kernel_launches_timed": kn,
+                         "algorithmic_bytes_per_launch": nframes * ALGO_BYTES_PER_FRAME},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, eng, dec, corpus, shard, barrier, world):
+    import torch
+    S, F = args.streams, args.frames
+    # bound the pinned allocation by what the host can spare
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except ImportError:
+        avail = 64 << 30
+    per_stream = F * (FRAME_BYTES + PCM_BYTES)
+    s_e2e = S
+    budget = avail // (3 * max(world, 1))
+    while s_e2e > 64 and s_e2e * per_stream > budget:
+        s_e2e //= 2
+    nframes = s_e2e * F
+    es_h = torch.from_numpy(corpus[:s_e2e].reshape(-1).copy()).pin_memory()
+    pcm_h = torch.empty(nframes * 1536 * 2, dtype=torch.float32).pin_memory()
+    status_h = torch.zeros(nframes, dtype=torch.int32).pin_memory()
+    off_h = (np.arange(nframes, dtype=np.uint64) * FRAME_BYTES)
+    first_h = (np.arange(s_e2e + 1, dtype=np.uint32) * F).astype(np.uint32)
+
+    def step():
+        dec.decode_host_into(es_h.data_ptr(), es_h.numel(), off_h, first_h, REQ_FLAGS, pcm_h.data_ptr(),
+                             status_h.data_ptr(), out_fmt=eng.PCM_F32_INTERLEAVED)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    barrier()
+    n = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    barrier()
+    wall = time.perf_counter() - t0
+    wall = shard.max_over_ranks(wall)
+    assert int((status_h != 0).sum().item()) == 0
+    return {"value": nframes * FRAME_SECONDS * world * n / wall, "unit": UNIT,
+            "h2d_bytes_per_step": int(es_h.numel() + off_h.nbytes + first_h.nbytes),
+            "d2h_bytes_per_step": int(pcm_h.numel() * 4 + status_h.numel() * 4),
+            "streams_per_gpu": s_e2e, "steps": n, "ms_per_step": 1e3 * wall / n,
+            "api": "a52_batch_decode (host pointers, pinned)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=4096)
+    ap.add_argument("--frames", type=int, default=313)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,357 @@
+"""GPU parity tests: the CUDA decode path, called through the C ABI (include/a52_batch.h,
+include/a52.h), against the oracle on the same inputs.
+
+Bars (BASELINE.json north_star): exponents, baps and mantissa integers bit-exact; float PCM
+within 1e-5 relative RMS; int16 output within +-1 LSB.  TOL_PCM below is that tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from refbind import (A52_3F2R, A52_LFE, A52_STEREO, A52_ADJUST_LEVEL, A52_MONO, A52_DOLBY, A52_2F2R, A52_3F,
+                     A52_CHANNEL, A52_CHANNEL1, A52_CHANNEL2, A52_2F1R, A52_3F1R, nout_of)
+from bitstream_writer import make_stream
+from util import LIBA52_BAP, NFCHANS, relrms, s16_of, frame_offsets
+
+pytestmark = pytest.mark.gpu
+
+TOL_PCM = 1e-5          # relative RMS, float PCM (north_star)
+
+
+def gpu_decode(decoder, engine, es, oracle, flags, bias=0.0, fmt=None, debug=False, drc=0, level=1.0):
+    off = frame_offsets(es, oracle)
+    first = np.array([0, len(off)], np.uint32)
+    fmt = engine.PCM_F32_PLANAR if fmt is None else fmt
+    out = decoder.decode_host(es, off, first, flags, level, bias, drc=drc, out_fmt=fmt, want_debug=debug)
+    return off, out
+
+
+def planar(out, nframes, nout):
+    return out["pcm"][:, : 6 * nout * 256].reshape(nframes * 6, nout, 256)
+
+
+# ---------------------------------------------------------------------------
+# golden vectors generated from the unmodified reference
+# ---------------------------------------------------------------------------
+def test_golden_vectors(decoder, engine, oracle, golden):
+    for name in golden["names"]:
+        name = str(name)
+        es = golden[name + ".es"]
+        flags, bias = [int(x) for x in golden[name + ".req"]]
+        off, out = gpu_decode(decoder, engine, es, oracle, flags, float(bias), debug=True)
+        assert len(off) == 4 and (out["status"] == 0).all(), (name, out["status"])
+        ref = golden[name + ".pcm"]
+        nout = ref.shape[1]
+        got = planar(out, 4, nout)
+        if bias:
+            assert np.abs(got - ref).max() <= 2.0 ** -15 + 1e-9, name      # float add at 384 quantises to 2^-15
+            assert np.abs(s16_of(got).astype(int) - s16_of(ref).astype(int)).max() <= 1, name
+        else:
+            assert relrms(got, ref) < TOL_PCM, (name, relrms(got, ref))
+        # integers: exponents, baps (frame 0), dither generator state after the last block
+        ginfo = golden[name + ".info"]
+        assert out["info"][-1, -1, 8] == int(golden[name + ".lfsr"][0]), name
+        for b in range(6):
+            gi = ginfo[b]
+            for ch in range(NFCHANS[gi[9]]):
+                end = gi[ch]
+                assert (out["exp"][0, b, ch, :end] == golden[name + ".exp"][b, ch, :end]).all(), (name, b, ch)
+                assert (LIBA52_BAP[out["bap"][0, b, ch, :end]] == golden[name + ".bap"][b, ch, :end]).all(), (name, b, ch)
+            if gi[10]:
+                assert (out["exp"][0, b, 5, :7] == golden[name + ".exp"][b, 5, :7]).all()
+                assert (LIBA52_BAP[out["bap"][0, b, 5, :7]] == golden[name + ".bap"][b, 5, :7]).all()
+            if gi[7]:
+                s, e = gi[5], gi[6]
+                assert (out["exp"][0, b, 6, s:e] == golden[name + ".exp"][b, 6, s:e]).all()
+                assert (LIBA52_BAP[out["bap"][0, b, 6, s:e]] == golden[name + ".bap"][b, 6, s:e]).all()
+
+
+def test_c2_fixture_all_stages(decoder, engine, oracle, c2):
+    """Config 2 (5.1 448 kb/s -> stereo): exp / bap / coefficient bits / PCM against the oracle."""
+    nfr = 16
+    for s in range(4):
+        es = c2["frames"][s, :nfr].reshape(-1)
+        # 5.1 -> 5.1: neither decoder mixes, so coefficients are comparable plane by plane
+        off, out = gpu_decode(decoder, engine, es, oracle, A52_3F2R | A52_LFE, debug=True)
+        dump = oracle.decode_dump(es, req_flags=A52_3F2R | A52_LFE)
+        assert (out["status"] == 0).all()
+        for f in range(nfr):
+            for b in range(6):
+                blk = dump[f]["blocks"][b]
+                for ch in range(5):
+                    end = blk["info"][ch]
+                    assert (out["exp"][f, b, ch, :end] == blk["exp"][ch, :end]).all()
+                    assert (LIBA52_BAP[out["bap"][f, b, ch, :end]] == blk["bap"][ch, :end]).all()
+                assert (out["exp"][f, b, 5, :7] == blk["exp"][5, :7]).all()
+                assert (LIBA52_BAP[out["bap"][f, b, 5, :7]] == blk["bap"][5, :7]).all()
+                # dequantised coefficients: bit-exact (=> mantissa integers bit-exact: level is 2^k)
+                assert (out["coef"][f, b].view(np.uint32) == blk["coef"].view(np.uint32)).all(), (s, f, b)
+                assert out["info"][f, b, 8] == blk["info"][8]                  # lfsr_state
+        got = planar(out, nfr, 6)
+        want = np.stack([blk["pcm"] for fr in dump for blk in fr["blocks"]])
+        assert relrms(got, want) < TOL_PCM
+        # the benchmark request: stereo downmix with level adjustment
+        off, out = gpu_decode(decoder, engine, es, oracle, A52_STEREO | A52_ADJUST_LEVEL)
+        nf, want = oracle.decode_stream(es, A52_STEREO | A52_ADJUST_LEVEL, 1.0, 0.0)
+        assert nf == nfr and relrms(planar(out, nfr, 2), want) < TOL_PCM
+
+
+# ---------------------------------------------------------------------------
+# config 3: block switching, coupling, rematrixing, dynrng, delta bit allocation, skip fields
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("acmod,lfe,flags,fscod,cod", [
+    (7, 1, A52_STEREO | A52_ADJUST_LEVEL, 0, 36), (7, 1, A52_3F2R | A52_LFE, 0, 36),
+    (7, 0, A52_MONO, 0, 30), (7, 1, A52_DOLBY, 0, 34), (7, 1, A52_2F1R | A52_LFE | A52_ADJUST_LEVEL, 0, 36),
+    (7, 1, A52_3F1R, 0, 36), (7, 1, A52_2F2R | A52_ADJUST_LEVEL, 0, 36), (7, 1, A52_3F | A52_LFE, 0, 36),
+    (2, 0, A52_STEREO, 0, 24), (2, 0, A52_MONO | A52_ADJUST_LEVEL, 1, 22), (2, 0, A52_DOLBY, 0, 24),
+    (0, 0, A52_CHANNEL, 0, 24), (0, 0, A52_CHANNEL1, 0, 24), (0, 1, A52_CHANNEL2, 0, 24), (0, 0, A52_MONO, 0, 24),
+    (0, 0, A52_STEREO, 0, 24),
+    (1, 0, A52_STEREO, 2, 14), (1, 1, A52_MONO | A52_LFE, 0, 14), (1, 0, A52_DOLBY | A52_ADJUST_LEVEL, 0, 14),
+    (3, 0, A52_STEREO | A52_ADJUST_LEVEL, 0, 28), (3, 0, A52_MONO | A52_ADJUST_LEVEL, 0, 28), (3, 0, A52_3F, 0, 28),
+    (4, 1, A52_3F1R | A52_LFE, 0, 28), (4, 0, A52_STEREO | A52_ADJUST_LEVEL, 0, 28), (4, 0, A52_DOLBY, 0, 28),
+    (4, 0, A52_2F2R, 0, 28),
+    (5, 1, A52_2F2R | A52_LFE, 1, 33), (5, 0, A52_STEREO, 0, 33), (5, 0, A52_2F1R | A52_ADJUST_LEVEL, 0, 33),
+    (6, 0, A52_DOLBY | A52_ADJUST_LEVEL, 2, 30), (6, 0, A52_3F, 0, 30), (6, 0, A52_2F1R, 0, 30),
+    (6, 1, A52_MONO | A52_ADJUST_LEVEL | A52_LFE, 0, 30),
+])
+def test_feature_streams(decoder, engine, oracle, acmod, lfe, flags, fscod, cod):
+    es, fb = make_stream(2000 + acmod * 16 + (flags & 15), acmod, lfe, 4, oracle.bit_allocate, fscod=fscod,
+                         frmsizecod=cod)
+    nf, want = oracle.decode_stream(es, flags, 1.0, 0.0)
+    assert nf == 4
+    off, out = gpu_decode(decoder, engine, es, oracle, flags, debug=True)
+    assert (out["status"] == 0).all(), out["status"]
+    dump = oracle.decode_dump(es, req_flags=flags)
+    nout = want.shape[1]
+    assert out["flags"][0] == dump[0]["out_flags"]
+    for f in range(4):
+        for b in range(6):
+            blk = dump[f]["blocks"][b]
+            info = blk["info"]
+            for ch in range(NFCHANS[acmod]):
+                end = info[ch]
+                assert (out["exp"][f, b, ch, :end] == blk["exp"][ch, :end]).all(), (f, b, ch)
+                assert (LIBA52_BAP[out["bap"][f, b, ch, :end]] == blk["bap"][ch, :end]).all(), (f, b, ch)
+            if info[7]:
+                s, e = info[5], info[6]
+                assert (out["exp"][f, b, 6, s:e] == blk["exp"][6, s:e]).all()
+                assert (LIBA52_BAP[out["bap"][f, b, 6, s:e]] == blk["bap"][6, s:e]).all()
+            assert out["info"][f, b, 8] == info[8], (f, b)          # dither generator in step
+    assert relrms(planar(out, 4, nout), want) < TOL_PCM
+    # dynamic range compression switched off (a52_dynrng (state, NULL, NULL))
+    nf, want = oracle.decode_stream(es, flags, 1.0, 0.0, dynrng_off=True)
+    off, out = gpu_decode(decoder, engine, es, oracle, flags, drc=engine.DRC_OFF)
+    assert relrms(planar(out, 4, nout), want) < TOL_PCM
+
+
+def test_transient_640k_stream(decoder, engine, oracle):
+    """Config 3 proper: 5.1 640 kb/s, heavy block switching + coupling, longer run."""
+    es, fb = make_stream(31337, 7, 1, 12, oracle.bit_allocate, frmsizecod=36,
+                         features=dict(blksw=0.5, cpl=0.9, dynrng=0.5, deltba=0.1))
+    assert fb == 2560
+    for flags in (A52_STEREO | A52_ADJUST_LEVEL, A52_3F2R | A52_LFE):
+        nf, want = oracle.decode_stream(es, flags, 1.0, 0.0)
+        off, out = gpu_decode(decoder, engine, es, oracle, flags)
+        assert nf == 12 and (out["status"] == 0).all()
+        assert relrms(planar(out, 12, want.shape[1]), want) < TOL_PCM
+
+
+def test_halfrate_and_level(decoder, engine, oracle, golden):
+    es = golden["enc20_halfrate.es"]
+    for level, bias in ((0.5, 0.0), (2.0, 1.0)):
+        nf, want = oracle.decode_stream(es, A52_STEREO, level, bias)
+        off, out = gpu_decode(decoder, engine, es, oracle, A52_STEREO, bias=bias, level=level)
+        d = planar(out, 4, 2).astype(np.float64) - want
+        assert np.sqrt((d * d).mean()) / np.sqrt(((want - bias) ** 2).mean()) < TOL_PCM
+
+
+# ---------------------------------------------------------------------------
+# output formats
+# ---------------------------------------------------------------------------
+def test_s16_and_interleaved_output(decoder, engine, oracle, c2):
+    es = c2["frames"][1, :8].reshape(-1)
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    nf, want384 = oracle.decode_stream(es, flags, 1.0, 384.0)       # the -o wav semantic
+    want_s16 = s16_of(want384)                                        # [blocks, 2, 256]
+    want_s16 = want_s16.reshape(8, 6, 2, 256).transpose(0, 1, 3, 2).reshape(8, 1536, 2)
+    off, out = gpu_decode(decoder, engine, es, oracle, flags, fmt=engine.PCM_S16_INTERLEAVED)
+    got = out["pcm"].reshape(8, 1536, 2)
+    assert np.abs(got.astype(int) - want_s16.astype(int)).max() <= 1
+    assert (got == want_s16).mean() > 0.999
+    nf, want = oracle.decode_stream(es, flags, 1.0, 0.0)
+    off, out = gpu_decode(decoder, engine, es, oracle, flags, fmt=engine.PCM_F32_INTERLEAVED)
+    got = out["pcm"].reshape(8, 6, 256, 2).transpose(0, 1, 3, 2).reshape(48, 2, 256)
+    assert relrms(got, want) < TOL_PCM
+
+
+# ---------------------------------------------------------------------------
+# batch semantics: ragged / empty streams, mixed formats, carry, errors
+# ---------------------------------------------------------------------------
+def test_ragged_and_empty_streams(decoder, engine, oracle, c2):
+    counts = [5, 0, 1, 8, 0, 3]
+    chunks, off, first = [], [], [0]
+    pos = 0
+    for s, n in enumerate(counts):
+        fr = c2["frames"][s % 4, :n].reshape(-1)
+        chunks.append(fr)
+        off += [pos + 1792 * k for k in range(n)]
+        pos += len(fr)
+        first.append(first[-1] + n)
+    es = np.concatenate(chunks)
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    out = decoder.decode_host(es, np.array(off, np.uint64), np.array(first, np.uint32), flags)
+    assert (out["status"] == 0).all()
+    for s, n in enumerate(counts):
+        if n == 0:
+            continue
+        nf, want = oracle.decode_stream(chunks[s], flags, 1.0, 0.0)
+        got = out["pcm"][first[s]:first[s + 1]].reshape(n * 6, 2, 256)
+        assert relrms(got, want) < TOL_PCM, s
+    # nothing to do
+    out = decoder.decode_host(np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.array([0], np.uint32), flags)
+    assert out["pcm"].shape[0] == 0
+
+
+def test_mixed_formats_one_batch(decoder, engine, oracle, golden):
+    """Streams of different channel modes, sample rates and frame sizes (unaligned 44.1 kHz frames)
+    in one launch."""
+    names = ["enc51_stereo", "enc10_stereo", "enc50_dolby_441", "syn20_remat", "enc30_mono_32k", "syn31_2f2r_441"]
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    chunks, off, first = [], [], [0]
+    pos = 0
+    for n in names:
+        es = golden[n + ".es"]
+        o = frame_offsets(es, oracle)
+        off += [pos + int(x) for x in o]
+        first.append(first[-1] + len(o))
+        chunks.append(es)
+        pos += len(es)
+    out = decoder.decode_host(np.concatenate(chunks), np.array(off, np.uint64), np.array(first, np.uint32), flags)
+    assert (out["status"] == 0).all()
+    for k, n in enumerate(names):
+        nf, want = oracle.decode_stream(chunks[k], flags, 1.0, 0.0)
+        assert want.shape[1] == 2
+        got = out["pcm"][first[k]:first[k + 1]].reshape(-1, 2, 256)
+        assert relrms(got, want) < TOL_PCM, n
+
+
+def test_carry_split_equals_one_call(decoder, engine, oracle, c2):
+    """Decoding a stream in two calls with the carry record == one call (overlap tail + dither)."""
+    es = c2["frames"][2, :10].reshape(-1)
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    off = np.arange(10, dtype=np.uint64) * 1792
+    whole = decoder.decode_host(es, off, np.array([0, 10], np.uint32), flags)
+    c0 = engine.CarryStruct()
+    a = decoder.decode_host(es[: 4 * 1792], off[:4], np.array([0, 4], np.uint32), flags, carry=[c0])
+    b = decoder.decode_host(es[4 * 1792:], off[:6], np.array([0, 6], np.uint32), flags, carry=[a["carry"][0]])
+    got = np.concatenate([a["pcm"], b["pcm"]])
+    assert (got.view(np.uint32) == whole["pcm"].view(np.uint32)).all()
+
+
+def test_corrupted_frames_status_and_isolation(decoder, engine, oracle):
+    """Same per-frame error returns as liba52; a bad frame does not poison other streams."""
+    rng = np.random.RandomState(11)
+    es0, fb = make_stream(77, 7, 1, 3, oracle.bit_allocate)
+    flags = A52_STEREO
+    nerr = 0
+    for it in range(120):
+        es = es0.copy()
+        for _ in range(int(rng.randint(1, 4))):
+            p = fb + int(rng.randint(6, 500))
+            es[p] ^= 1 << int(rng.randint(8))
+        dump = oracle.decode_dump(es, req_flags=flags)
+        want_status = [0 if f["status"] == 0 else (2 if f["status"] == 1 else 16 + f["status"] - 2) for f in dump]
+        # two streams in the batch: the damaged one and the clean one
+        both = np.concatenate([es, es0])
+        off = np.arange(6, dtype=np.uint64) * fb
+        out = decoder.decode_host(both, off, np.array([0, 3, 6], np.uint32), flags)
+        assert out["status"][:3].tolist() == want_status, (it, out["status"], want_status)
+        assert (out["status"][3:] == 0).all()
+        nerr += any(want_status)
+        if it == 0:
+            clean = out["pcm"][3:].copy()
+        assert (out["pcm"][3:].view(np.uint32) == clean.view(np.uint32)).all()
+        # frames before the first error match the oracle
+        for f in range(3):
+            if want_status[f]:
+                break
+            want = np.stack([blk["pcm"] for blk in dump[f]["blocks"]])
+            assert relrms(out["pcm"][f].reshape(6, 2, 256), want) < TOL_PCM, (it, f)
+    assert nerr > 5
+    # bad sync word and truncated last frame
+    es = es0.copy()
+    es[fb] = 0
+    out = decoder.decode_host(es, np.arange(3, dtype=np.uint64) * fb, np.array([0, 3], np.uint32), flags)
+    assert out["status"].tolist()[1] == engine.ST_BAD_SYNC and out["status"][0] == 0
+    assert not out["pcm"][1].any()
+
+
+# ---------------------------------------------------------------------------
+# the drop-in liba52 API (include/a52.h) used the way a52dec.c:240-309 uses it
+# ---------------------------------------------------------------------------
+def test_dropin_api_decodes_like_liba52(engine, oracle, c2, golden):
+    L = engine.load_library()
+    for es, flags, bias in [(c2["frames"][3, :5].reshape(-1), A52_STEREO | A52_ADJUST_LEVEL, 384.0),
+                            (golden["syn51_51.es"], A52_3F2R | A52_LFE, 0.0)]:
+        es = np.ascontiguousarray(es)
+        nf, want = oracle.decode_stream(es, flags, 1.0, bias)
+        st = L.a52_init(0)
+        assert st
+        pos, blocks = 0, []
+        fl, sr, br = C.c_int(0), C.c_int(0), C.c_int(0)
+        while pos + 7 <= len(es):
+            n = L.a52_syncinfo(es[pos:].ctypes.data, C.byref(fl), C.byref(sr), C.byref(br))
+            assert n > 0
+            f, lv = C.c_int(flags), C.c_float(1.0)
+            frame = np.ascontiguousarray(es[pos:pos + n])
+            assert L.a52_frame(st, frame.ctypes.data, C.byref(f), C.byref(lv), C.c_float(bias)) == 0
+            nout = nout_of(f.value)
+            for b in range(6):
+                assert L.a52_block(st) == 0
+                sp = L.a52_samples(st)
+                blocks.append(np.ctypeslib.as_array(sp, shape=(nout * 256,)).copy().reshape(nout, 256))
+            pos += n
+        L.a52_free(st)
+        got = np.stack(blocks)
+        assert got.shape == want.shape
+        d = got.astype(np.float64) - want
+        assert np.sqrt((d * d).mean()) / np.sqrt(((want - bias) ** 2).mean()) < TOL_PCM
+
+
+# ---------------------------------------------------------------------------
+# full-size property checks (BASELINE.json config 2 shape: thousands of streams in one launch)
+# ---------------------------------------------------------------------------
+def test_large_batch_properties(decoder, engine, oracle, c2):
+    """2048 streams x 64 frames through the device-pointer entry: every copy of a base stream must
+    produce bit-identical PCM regardless of which thread group decoded it (checksum of checksums),
+    and each base stream matches the oracle."""
+    import torch
+    ns, nfr = 2048, 64
+    base = c2["frames"]                                     # [4, 64, 1792]
+    rng = np.random.RandomState(3)
+    pick = rng.randint(0, 4, ns)
+    es = torch.from_numpy(np.ascontiguousarray(base[pick]).reshape(-1)).cuda()
+    es = torch.cat([es, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    nframes = ns * nfr
+    off = (torch.arange(nframes + 1, dtype=torch.int64, device="cuda") * 1792)
+    first = (torch.arange(ns + 1, dtype=torch.int32, device="cuda") * nfr)
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    pcm = torch.empty(nframes * 1536 * 2, dtype=torch.float32, device="cuda")
+    status = torch.full((nframes,), -1, dtype=torch.int32, device="cuda")
+    decoder.decode_device(es.data_ptr(), nframes * 1792, off.data_ptr(), nframes, first.data_ptr(), ns, flags,
+                          pcm.data_ptr(), status_ptr=status.data_ptr(), out_fmt=engine.PCM_F32_PLANAR)
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0
+    per_stream = pcm.view(ns, -1)
+    pick_t = torch.from_numpy(pick).cuda()
+    for b in range(4):
+        sel = per_stream[pick_t == b]
+        assert sel.shape[0] > 0
+        assert bool((sel.view(torch.int32) == sel[0:1].view(torch.int32)).all()), b
+        nf, want = oracle.decode_stream(base[b].reshape(-1), flags, 1.0, 0.0)
+        got = sel[0].cpu().numpy().reshape(nfr * 6, 2, 256)
+        assert relrms(got, want) < TOL_PCM
+        d = c2["digest"][b]
+        p = got.astype(np.float64)
+        assert abs((p * p).sum() - d[1]) / d[1] < 1e-5
