@@ -32,7 +32,8 @@ EXPORTS = [
 
 
 class CarryStruct(C.Structure):
-    _fields_ = [("dither_index", C.c_uint32), ("reserved", C.c_uint32 * 3), ("delay", (C.c_float * 128) * 6)]
+    _fields_ = [("dither_index", C.c_uint32), ("per_channel", C.c_uint32), ("reserved", C.c_uint32 * 2),
+                ("delay", (C.c_float * 128) * 6)]
 
 
 class DebugStruct(C.Structure):

@@ -54,13 +54,14 @@ struct MixEntry {             // which coded channels feed each output channel
     uint8_t nout;
     uint8_t pos[5];
     uint8_t neg[5];
-    uint8_t pad_;
+    uint8_t up[5];            // a52_upmix: output plane that moves to coded channel ch (0xff = zeroed)
 };
 
 // ---- kernel parameters -----------------------------------------------------
 struct StreamCarry {          // == a52_stream_carry_t (include/a52_batch.h)
     uint32_t dither_index;
-    uint32_t reserved[3];
+    uint32_t per_channel;
+    uint32_t reserved[2];
     float    delay[6][128];
 };
 

@@ -69,6 +69,7 @@ struct __align__(16) GroupCtl {
     uint32_t limit_bit;        // end of frame (bits) inside the staged buffer
     uint32_t bitpos;           // cursor (bits), advanced block by block
     uint32_t dither_index;     // dither_gen() calls so far in this stream, mod 65535
+    uint32_t per_channel;      // delay planes hold per-coded-channel tails (liba52: downmixed == 0)
     // BSI
     uint8_t  fscod, halfrate, acmod, lfeon, nfchans, nout, out_lfe, pad0;
     int      output;           // granted mode incl. LFE bit
@@ -1042,7 +1043,10 @@ a52_decode_kernel(const DecodeParams P)
         // carry in
         for (int i = gt; i < P.ndelay * 128; i += kGroupThreads)
             G.delay[i] = P.carry ? P.carry[s].delay[i >> 7][i & 127] : 0.f;
-        if (gt == 0) c->dither_index = P.carry ? P.carry[s].dither_index % kDitherPeriod : 0;
+        if (gt == 0) {
+            c->dither_index = P.carry ? P.carry[s].dither_index % kDitherPeriod : 0;
+            c->per_channel = P.carry ? (P.carry[s].per_channel != 0) : 0;
+        }
 
         // prefetch the first frame
         int cur = 0;
@@ -1357,7 +1361,7 @@ a52_decode_kernel(const DecodeParams P)
                     for (int i = 0; i < 5; i++) o[i] = c->endmant[i];
                     o[5] = c->cplstrtmant; o[6] = c->cplendmant; o[7] = c->chincpl;
                     o[8] = P.dither_seq[c->dither_index]; o[9] = c->acmod; o[10] = c->lfeon;
-                    o[11] = c->output; o[12] = 0; o[13] = c->ncplbnd; o[14] = c->rematflg;
+                    o[11] = c->output; o[12] = c->blksw | (c->uniform_path << 8) | ((c->clev == 0.f) << 9) | ((c->slev == 0.f) << 10); o[13] = c->ncplbnd; o[14] = c->rematflg;
                     o[15] = c->csnroffst;
                 }
 
@@ -1402,49 +1406,114 @@ a52_decode_kernel(const DecodeParams P)
                 }
                 group_sync(gid);
 
-                // ================= O: (time-domain mix) + window + overlap-add + store ========
+                // ================= O: window + overlap-add (+ time-domain mix) + store ========
+                // The delay planes follow liba52's state machine (parse.c:881-937): after a block that
+                // mixed coefficients they hold the downmixed tail (planes 0..nout-1); after a block that
+                // transformed every coded channel they hold per-channel tails (planes 0..nfchans-1).
+                // Switching representation = a52_downmix / a52_upmix on the delay (downmix.c:480-685);
+                // a channel whose gain is zero keeps its tail untouched and unheard (parse.c:897-909).
                 {
-                    const int nout = nmain + (c->out_lfe ? 1 : 0);
+                    const int lfe_on = c->out_lfe;
+                    const int nout = nmain + lfe_on;
                     const float bias = P.bias;
-                    // output channel oc: 0 = LFE when present, then the main channels
-                    for (int idx = gt; idx < nout * 128; idx += kGroupThreads) {
-                        int oc = idx >> 7, p = idx & 127;
-                        int o = oc - (c->out_lfe ? 1 : 0);
-                        float U, V;
-                        if (o < 0) { U = G.plane[5 * 256 + p]; V = G.plane[5 * 256 + 128 + p]; }
-                        else if (uniform) { U = G.plane[o * 256 + p]; V = G.plane[o * 256 + 128 + p]; }
-                        else {
-                            U = 0.f; V = 0.f;
-                            for (int ch = 0; ch < nfchans; ch++) {
-                                float su = G.plane[ch * 256 + p], sv = G.plane[ch * 256 + 128 + p];
-                                if ((mx.pos[o] >> ch) & 1) { U += su; V += sv; }
-                                else if ((mx.neg[o] >> ch) & 1) { U -= su; V -= sv; }
+                    float* D = G.delay;
+                    const int p = gt;                              // kGroupThreads == 128 positions
+                    const float w0 = T.window[p], w1 = T.window[255 - p];
+                    float y0[6], y1[6];                            // by output channel (0 = LFE when present)
+#pragma unroll
+                    for (int o = 0; o < 6; o++) { y0[o] = 0.f; y1[o] = 0.f; }
+                    if (lfe_on) {
+                        float U = G.plane[5 * 256 + p], V = G.plane[5 * 256 + 128 + p], Dv = D[5 * 128 + p];
+                        y0[0] = Dv * w1 - U * w0;
+                        y1[0] = Dv * w0 + U * w1;
+                        D[5 * 128 + p] = V;
+                    }
+                    if (uniform) {
+                        if (c->per_channel) {
+                            float d[5], m[5];
+#pragma unroll
+                            for (int ch = 0; ch < 5; ch++)
+                                d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? D[ch * 128 + p] : 0.f;
+#pragma unroll
+                            for (int o = 0; o < 5; o++) {
+                                float acc = 0.f;
+#pragma unroll
+                                for (int ch = 0; ch < 5; ch++) {
+                                    if ((mx.pos[o] >> ch) & 1) acc += d[ch];
+                                    else if ((mx.neg[o] >> ch) & 1) acc -= d[ch];
+                                }
+                                m[o] = acc;
+                            }
+#pragma unroll
+                            for (int o = 0; o < 5; o++)
+                                if (o < nmain) D[o * 128 + p] = m[o];
+                        }
+#pragma unroll
+                        for (int o = 0; o < 5; o++) {
+                            if (o < nmain) {
+                                float U = G.plane[o * 256 + p], V = G.plane[o * 256 + 128 + p], Dv = D[o * 128 + p];
+                                float a = Dv * w1 - U * w0, b = Dv * w0 + U * w1;
+                                D[o * 128 + p] = V;
+                                if (lfe_on) { y0[o + 1 > 5 ? 5 : o + 1] = a; y1[o + 1 > 5 ? 5 : o + 1] = b; }
+                                else { y0[o] = a; y1[o] = b; }
                             }
                         }
-                        float D = G.delay[oc * 128 + p];
-                        float w0 = T.window[p], w1 = T.window[255 - p];
-                        float y0 = (D * w1 - U * w0) + bias;       // sample p
-                        float y1 = (D * w0 + U * w1) + bias;       // sample 255 - p
-                        G.delay[oc * 128 + p] = V;
-                        if (P.out_fmt == 0) {
-                            float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
-                            dst[p] = y0;
-                            dst[255 - p] = y1;
-                        } else if (P.out_fmt == 1) {
-                            float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
-                            dst[p * nout + oc] = y0;
-                            dst[(255 - p) * nout + oc] = y1;
-                        } else {
-                            int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
-                            int a = __float2int_rn((y0 - bias) * 32768.f), b2 = __float2int_rn((y1 - bias) * 32768.f);
-                            a = min(max(a, -32768), 32767);
-                            b2 = min(max(b2, -32768), 32767);
-                            dst[p * nout + oc] = (int16_t)a;
-                            dst[(255 - p) * nout + oc] = (int16_t)b2;
+                    } else {
+                        if (!c->per_channel) {
+                            float m[5];
+#pragma unroll
+                            for (int o = 0; o < 5; o++) m[o] = D[o * 128 + p];
+#pragma unroll
+                            for (int ch = 0; ch < 5; ch++) {
+                                if (ch < nfchans) {
+                                    float v = 0.f;
+#pragma unroll
+                                    for (int o = 0; o < 5; o++)
+                                        if (mx.up[ch] == o) v = m[o];
+                                    D[ch * 128 + p] = v;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 5; ch++) {
+                            if (ch < nfchans && c->gain[ch] != 0.f) {
+                                float U = G.plane[ch * 256 + p], V = G.plane[ch * 256 + 128 + p], Dv = D[ch * 128 + p];
+                                float a = Dv * w1 - U * w0, b = Dv * w0 + U * w1;
+                                D[ch * 128 + p] = V;
+#pragma unroll
+                                for (int o = 0; o < 5; o++) {
+                                    const int oo = lfe_on ? (o + 1 > 5 ? 5 : o + 1) : o;
+                                    if ((mx.pos[o] >> ch) & 1) { y0[oo] += a; y1[oo] += b; }
+                                    else if ((mx.neg[o] >> ch) & 1) { y0[oo] -= a; y1[oo] -= b; }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int oc = 0; oc < 6; oc++) {
+                        if (oc < nout) {
+                            float a = y0[oc] + bias, b = y1[oc] + bias;
+                            if (P.out_fmt == 0) {
+                                float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
+                                dst[p] = a;
+                                dst[255 - p] = b;
+                            } else if (P.out_fmt == 1) {
+                                float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
+                                dst[p * nout + oc] = a;
+                                dst[(255 - p) * nout + oc] = b;
+                            } else {
+                                int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
+                                int ia = __float2int_rn(y0[oc] * 32768.f), ib = __float2int_rn(y1[oc] * 32768.f);
+                                ia = min(max(ia, -32768), 32767);
+                                ib = min(max(ib, -32768), 32767);
+                                dst[p * nout + oc] = (int16_t)ia;
+                                dst[(255 - p) * nout + oc] = (int16_t)ib;
+                            }
                         }
                     }
                 }
                 group_sync(gid);
+                if (gt == 0) c->per_channel = uniform ? 0 : 1;
             }   // blocks
 
             if (c->frame_ok && blk < 6) frame_status = 16 + blk;     // A52_ST_BAD_BLOCK + block
@@ -1465,7 +1534,10 @@ a52_decode_kernel(const DecodeParams P)
         if (P.carry) {
             for (int i = gt; i < P.ndelay * 128; i += kGroupThreads)
                 P.carry[s].delay[i >> 7][i & 127] = G.delay[i];
-            if (gt == 0) P.carry[s].dither_index = c->dither_index;
+            if (gt == 0) {
+                P.carry[s].dither_index = c->dither_index;
+                P.carry[s].per_channel = c->per_channel;
+            }
         }
         group_sync(gid);
     }

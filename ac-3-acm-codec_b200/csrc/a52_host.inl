@@ -159,6 +159,19 @@ static void build_mix_table(MixEntry* tab)
                     if (sign < 0) m.neg[o] |= 1u << ch;
                 }
             }
+            // a52_upmix (downmix.c:621-685): where each downmixed delay plane goes when the decoder
+            // falls back to per-channel transforms; the remaining channels' planes are zeroed
+            for (int ch = 0; ch < 5; ch++) m.up[ch] = 0xff;
+            for (int o = 0; o < nout; o++) {
+                int t = out_roles[out][o], dst = -1;
+                for (int ch = 0; ch < h_nfchans[acmod] && dst < 0; ch++)
+                    if (in_roles[acmod][ch] == t) dst = ch;
+                if (dst < 0 && out == M_MONO) dst = 0;
+                if (dst < 0 && t == R_S)
+                    for (int ch = 0; ch < h_nfchans[acmod] && dst < 0; ch++)
+                        if (in_roles[acmod][ch] == R_SL) dst = ch;
+                if (dst >= 0 && m.up[dst] == 0xff) m.up[dst] = (uint8_t)o;
+            }
         }
 }
 
@@ -408,7 +421,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     if (max_frame_bytes < 128) max_frame_bytes = 128;
     if (max_frame_bytes > 3840) max_frame_bytes = 3840;
     P.fbuf_bytes = align16(max_frame_bytes + 15) + 16 + 16;
-    P.ndelay = P.nout_req;
+    P.ndelay = 6;
     P.group_bytes = group_smem_bytes(P.fbuf_bytes, P.ndelay);
     P.dither_seq = ctx->d_dither;
     P.work_counter = ctx->d_counter;

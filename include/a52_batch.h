@@ -49,8 +49,10 @@ typedef struct a52_batch_s a52_batch_t;
  * the overlap-add tail of every output channel */
 typedef struct {
     uint32_t dither_index;      /* number of dither_gen() calls so far, mod 65535 */
-    uint32_t reserved[3];
-    float    delay[6][128];     /* per output channel, liba52 delay[0..127] (downmixed domain) */
+    uint32_t per_channel;       /* 0: delay planes 0..nout-1 hold the downmixed tail (liba52 downmixed=1,
+				   the initial state); 1: planes 0..nfchans-1 hold per-coded-channel tails */
+    uint32_t reserved[2];
+    float    delay[6][128];     /* overlap-add tails: planes 0..4 main channels, plane 5 LFE */
 } a52_stream_carry_t;
 
 /* optional intermediate dumps for parity testing; any pointer may be NULL.
