@@ -11,9 +11,7 @@
 
 namespace a52 {
 
-constexpr int kGroupThreads = 128;   // one "stream group": 4 warps walk one stream
-constexpr int kGroupWarps   = kGroupThreads / 32;
-constexpr int kMaxGroupsPerCta = 4;
+constexpr int kMaxWarpsPerCta = 16;  // one warp walks one stream; a CTA is just a bag of warps
 constexpr int kDitherPeriod = 65535;
 
 // output mode ids == liba52's A52_* flag values (include/a52.h)
@@ -33,9 +31,14 @@ struct __align__(16) Tables {
     int16_t  q1[3][32];        // grouped 3-level values by (digit, 5-bit code)
     int16_t  q2[3][128];       // grouped 5-level values by (digit, 7-bit code)
     int16_t  q4[2][128];       // grouped 11-level values by (digit, 7-bit code)
-    int16_t  q3[8];            // 7-level
-    int16_t  q5[16];           // 15-level
+    int16_t  q35[24];          // 7-level at [0..7], 15-level at [8..23]
     uint16_t dither_lut[256];  // CRC-16/0xA011 byte step (tables.h:213-246)
+    uint16_t jump_hi[256];     // dither generator advanced 32 steps: contribution of the high byte
+    uint16_t jump_lo[256];     //                                      and of the low byte
+    uint2    cnt_lut[16];      // per bap: x = n1 | n2 << 8 | n4 << 16 | nplain << 24, y = plain field bits | zero << 16
+    uint4    emit_lut[16];     // per bap: x = list cursor increment (a byte per class), y = byte selectors
+                               // (16-bit list base | cursor byte << 16), z = phase shift | group period << 8,
+                               // w = bits taken when the mantissa starts a field / group
     uint16_t hth[3 * 50];
     uint8_t  masktab[256];
     uint8_t  latab[256];
@@ -83,9 +86,8 @@ struct DecodeParams {
     StreamCarry*    carry;
     const uint16_t* dither_seq;      // state after n dither_gen() calls from seed 1, n = 0..65534
     int*            work_counter;
-    int             fbuf_bytes;      // bytes of one staged-frame buffer (multiple of 16)
-    int             ndelay;          // delay planes kept per group
-    int             group_bytes;     // shared-memory bytes per group
+    int             fbuf_bytes;      // bytes of the staged-frame buffer (multiple of 16)
+    int             warp_bytes;      // shared-memory bytes per warp
     // optional dumps
     uint8_t*        dbg_exp;
     uint8_t*        dbg_bap;

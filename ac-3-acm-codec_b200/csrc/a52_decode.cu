@@ -1,25 +1,30 @@
 // a52_decode.cu - batched AC-3 (ATSC A/52) decode for NVIDIA B200 (sm_100a).
 //
-// One persistent kernel decodes thousands of independent AC-3 streams.  A
-// "group" of 128 threads (4 warps) owns one stream at a time and walks its
-// sync frames in order; everything between the staged bitstream and the PCM
-// store lives in shared memory / registers:
+// One persistent kernel decodes thousands of independent AC-3 streams.  One
+// WARP owns one stream at a time and walks its sync frames in order;
+// everything between the staged bitstream and the PCM store lives in that
+// warp's slice of shared memory and in registers, so the only CTA-wide
+// synchronisation is the one after the table load:
 //
-//   stage   frame bytes  : TMA bulk copy (cp.async.bulk + mbarrier), double buffered
-//   parse   BSI + audio-block side info        (reference: liba52/parse.c:131-205, 558-804)
+//   stage   frame bytes  : TMA bulk copy (cp.async.bulk + mbarrier); the next frame is
+//                          requested as soon as the last block's mantissas are out
+//   parse   BSI + audio-block side info        (reference: liba52/parse.c:131-205, 558-804)  lane 0
 //   exps    exponent groups -> exponents       (parse.c:218-270)   lanes = groups, warp scan
-//   alloc   parametric bit allocation          (bit_allocate.c:124-265) one warp per channel
-//   locate  per-bin field positions            (parse.c:336-433)   prefix sums of bit widths
-//   unpack  mantissa extract + dequantise + dither (parse.c:310-433)
+//   alloc   parametric bit allocation          (bit_allocate.c:124-265) lanes = bands / bins
+//   locate  lanes own contiguous runs of the block's mantissas in coded order: count pass,
+//           warp prefix sums of group counters and bit widths, then an emit pass that writes
+//           a descriptor per mantissa and per-class work lists (parse.c:336-433)
+//   unpack  per class, convergent: dither (32 LFSR states kept in the warp, advanced 32 steps
+//           at a time), 3/5/11-level groups one lane per group code, plain fields
 //   couple  coupling fan-out, rematrix         (parse.c:435-556, 837-865)
 //   mix     downmix (coefficient or time domain) (downmix.c:162-619)
 //   imdct   512 / 2x256 transform: pre-twiddle, radix-4 FFT in shared memory,
 //           post-twiddle                        (imdct.c:258-345)
-//   ola     KBD window + overlap-add + PCM store (imdct.c:276-292)
+//   ola     KBD window + overlap-add + PCM store (imdct.c:276-292); the overlap tails
+//           stay in registers from block to block and frame to frame
 //
-// The overlap-add tail and the dither generator position are carried on chip
-// from frame to frame of a stream (and in/out of the call through
-// a52_stream_carry_t), so frames never wait on another group.
+// The dither generator position and the overlap tails enter and leave the call
+// through a52_stream_carry_t, so frames never wait on another warp.
 //
 // Integer stages are bit-exact with liba52; the float transform uses a
 // different FFT factorisation (tolerance 1e-5 relative RMS, measured ~1e-7).
@@ -96,54 +101,48 @@ struct __align__(16) GroupCtl {
     int8_t   deltba[7][50];
     Segment  seg[8];
     uint32_t total_bins;
-    // ---- scan scratch ----
-    uint32_t scan_a[kGroupWarps], scan_b[kGroupWarps], scan_c[kGroupWarps];
-    uint32_t blk_dither;       // dither calls of the block
-    uint32_t mant_bits;        // total mantissa bits of the block
+    float    wt[5][5];         // mix matrix [output][coded channel] in {-1, 0, +1} (downmix.c:480-619)
+    int      identity_mix;     // output channel o is exactly coded channel o
 };
 
-struct GroupPtrs {
+struct WarpPtrs {
     GroupCtl* ctl;
     uint8_t*  exp;     // [7][256]
     uint8_t*  bap;     // [7][256]  standard numbering 0..15
-    int16_t*  band;    // [4 warps][2][50] bit-allocation scratch
-    uint8_t*  grp;     // group codes: [0,512) bap1, [512,1024) bap2, [1024,1792) bap4
+    int16_t*  band;    // [2][50] bit-allocation scratch
+    uint16_t* list;    // [kListEntries] per-class work lists of plane slots
     float*    plane;   // [6][256]
-    float*    delay;   // [ndelay][128]
-    uint32_t* fbuf[2]; // staged frames (as native-endian 32-bit words after the swap pass)
-    uint64_t* mbar;    // [2]
+    uint32_t* fbuf;    // staged frame (native-endian 32-bit words after the swap pass)
+    uint64_t* mbar;
 };
 
-constexpr int kGrpOff2 = 512, kGrpOff4 = 1024, kGrpBytes = 1792;
+constexpr int kListEntries = 1504;   // >= 5*253 + 216 + 7 mantissa slots per block
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline int group_smem_bytes(int fbuf_bytes, int ndelay)
+__host__ __device__ inline int warp_smem_bytes(int fbuf_bytes)
 {
     int n = 0;
     n += align16((int)sizeof(GroupCtl));
     n += 7 * 256 * 2;
-    n += align16(kGroupWarps * 2 * 50 * 2);
-    n += kGrpBytes;
+    n += align16(2 * 50 * 2);
+    n += align16(kListEntries * 2);
     n += 6 * 256 * 4;
-    n += ndelay * 128 * 4;
-    n += 2 * fbuf_bytes;
+    n += fbuf_bytes;
     n += 16;
     return n;
 }
 
-__device__ inline GroupPtrs carve(uint8_t* base, int fbuf_bytes, int ndelay)
+__device__ inline WarpPtrs carve(uint8_t* base, int fbuf_bytes)
 {
-    GroupPtrs g;
+    WarpPtrs g;
     g.ctl = reinterpret_cast<GroupCtl*>(base);  base += align16((int)sizeof(GroupCtl));
     g.exp = base;                               base += 7 * 256;
     g.bap = base;                               base += 7 * 256;
-    g.band = reinterpret_cast<int16_t*>(base);  base += align16(kGroupWarps * 2 * 50 * 2);
-    g.grp = base;                               base += kGrpBytes;
+    g.band = reinterpret_cast<int16_t*>(base);  base += align16(2 * 50 * 2);
+    g.list = reinterpret_cast<uint16_t*>(base); base += align16(kListEntries * 2);
     g.plane = reinterpret_cast<float*>(base);   base += 6 * 256 * 4;
-    g.delay = reinterpret_cast<float*>(base);   base += ndelay * 128 * 4;
-    g.fbuf[0] = reinterpret_cast<uint32_t*>(base); base += fbuf_bytes;
-    g.fbuf[1] = reinterpret_cast<uint32_t*>(base); base += fbuf_bytes;
+    g.fbuf = reinterpret_cast<uint32_t*>(base); base += fbuf_bytes;
     g.mbar = reinterpret_cast<uint64_t*>(base);
     return g;
 }
@@ -151,11 +150,6 @@ __device__ inline GroupPtrs carve(uint8_t* base, int fbuf_bytes, int ndelay)
 // ---------------------------------------------------------------------------
 // small PTX helpers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void group_sync(int gid)
-{
-    asm volatile("bar.sync %0, %1;" :: "r"(gid + 1), "n"(kGroupThreads) : "memory");
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -598,6 +592,18 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         uniform = 0;                           // nothing to mix: per-channel transforms
     }
     c->uniform_path = uniform;
+
+    // mix matrix as float weights (so that the mixers are plain multiply-adds)
+    {
+        const MixEntry mx = c_mix[acmod * 11 + (c->output & M_MASK)];
+        for (int o = 0; o < 5; o++)
+            for (int ch = 0; ch < 5; ch++)
+                c->wt[o][ch] = ((mx.pos[o] >> ch) & 1) ? 1.f : ((mx.neg[o] >> ch) & 1) ? -1.f : 0.f;
+        int ident = (mx.nout == nfchans);
+        for (int o = 0; o < mx.nout && ident; o++)
+            if (mx.pos[o] != (1u << o) || mx.neg[o]) ident = 0;
+        c->identity_mix = ident;
+    }
     return 0;
 }
 
@@ -764,7 +770,7 @@ __device__ void bit_allocate_warp(const Tables& T, const GroupCtl* c, int arr, c
 }
 
 // ---------------------------------------------------------------------------
-// group-wide exclusive scans (128 threads)
+// warp helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 {
@@ -776,43 +782,86 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// ---------------------------------------------------------------------------
-// mantissa descriptors.  A 32-bit word per bin, written into the coefficient
-// plane slot the coefficient itself will later occupy:
-//   [4:0] exponent  [8:5] bap  [10:9] digit (grouped)  [11] dither enable
-//   bap 0        : [31:16] dither value (int16)
-//   bap 1,2,4    : [22:12] group index (code sits in the group-code array)
-//   other        : [26:12] bit position of the field
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t make_desc(uint32_t exp, uint32_t bap, uint32_t digit, uint32_t payload)
+// field of n (0..16) bits at bit position pos, zero past the end of the frame
+__device__ __forceinline__ uint32_t field_at(const uint32_t* w, uint32_t pos, uint32_t n, uint32_t limit)
 {
-    return exp | (bap << 5) | (digit << 9) | (payload << 12);
+    return (pos + n <= limit) ? peek_bits(w, pos, n) : 0u;
 }
 
-struct Cursor {           // walks the coded-order sequence
-    int seg;
-    int bin;              // bin within the segment's array
-    int left;             // bins left in the segment
-};
-
-__device__ __forceinline__ void cursor_seek(Cursor& cu, const GroupCtl* c, uint32_t flat)
+// dither generator (parse.c:310-319) advanced 32 steps: the step is linear over GF(2), so
+// state * x^256 = J_hi[state >> 8] ^ J_lo[state & 255]
+__device__ __forceinline__ uint32_t lfsr_jump32(const Tables& T, uint32_t s)
 {
-    int s = 0;
-    for (int k = 1; k < c->nseg; k++)
-        if (flat >= c->seg[k].first) s = k;
-    cu.seg = s;
-    uint32_t off = flat - c->seg[s].first;
-    cu.bin = c->seg[s].start + off;
-    cu.left = c->seg[s].count - off;
+    return (uint32_t)T.jump_hi[s >> 8] ^ (uint32_t)T.jump_lo[s & 255];
 }
 
-__device__ __forceinline__ void cursor_next(Cursor& cu, const GroupCtl* c)
+// ---------------------------------------------------------------------------
+// mantissa descriptors.  A 32-bit word per coded mantissa, written into the
+// coefficient-plane slot the coefficient itself will occupy:
+//   [4:0] exponent  [8:5] bap  [24:10] bit position of the field / of the group code
+// Planes receive q * 2^-(15+exp) (exact); the channel gain is applied later
+// (mix weights, or a gain pass when every channel is transformed on its own).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t make_desc(uint32_t exp, uint32_t bap, uint32_t pos)
 {
-    cu.bin++;
-    if (--cu.left == 0 && cu.seg + 1 < c->nseg) {
-        cu.seg++;
-        cu.bin = c->seg[cu.seg].start;
-        cu.left = c->seg[cu.seg].count;
+    return exp | (bap << 5) | (pos << 10);
+}
+
+// peek without a limit check: descriptor positions are clamped to the frame end at emit time
+// and the words past the frame end are zero
+__device__ __forceinline__ uint32_t peek_nz(const uint32_t* w, uint32_t pos, uint32_t n)
+{
+    uint32_t i = pos >> 5, s = pos & 31;
+    return __funnelshift_l(w[i + 1], w[i], s) >> (32 - n);
+}
+
+// 3-, 5- and 11-level groups: one lane per group code (parse.c:368-421)
+template <int PER, int WBITS, int QSTRIDE>
+__device__ __forceinline__ void unpack_groups(const WarpPtrs& G, const uint32_t* W, uint32_t base, uint32_t n,
+                                              const int16_t* qtab, int lane)
+{
+    uint32_t* planeU = reinterpret_cast<uint32_t*>(G.plane);
+    const uint32_t ng = (n + PER - 1) / PER;
+    for (uint32_t g = lane; g < ng; g += 32) {
+        const uint32_t k0 = g * PER;
+        uint32_t slot[PER], d[PER];
+#pragma unroll
+        for (int dg = 0; dg < PER; dg++) {
+            const uint32_t k = min(k0 + dg, n - 1);          // the last group may be partial
+            slot[dg] = G.list[base + k];
+            d[dg] = planeU[slot[dg]];
+        }
+        const uint32_t code = peek_nz(W, (d[0] >> 10) & 0x7fff, WBITS);
+#pragma unroll
+        for (int dg = PER - 1; dg >= 0; dg--) {                // descending: a clamped duplicate is overwritten
+            const int q = qtab[dg * QSTRIDE + code];
+            if (k0 + dg < n) G.plane[slot[dg]] = (float)q * pow2neg(15 + (d[dg] & 31));
+        }
+    }
+}
+
+// coefficient-domain downmix: out[o] = sum over coded channels of wg[o][ch] * in[ch]
+template <int NM>
+__device__ __forceinline__ void mix_planes(float* plane, const GroupCtl* c, int lane)
+{
+    float wg[NM][5];
+#pragma unroll
+    for (int o = 0; o < NM; o++)
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) wg[o][ch] = c->wt[o][ch] * c->gain[ch];
+#pragma unroll 2
+    for (int bin = lane; bin < 256; bin += 32) {
+        float in[5], acc[NM];
+#pragma unroll
+        for (int ch = 0; ch < 5; ch++) in[ch] = plane[ch * 256 + bin];       // planes past nfchans are zero
+#pragma unroll
+        for (int o = 0; o < NM; o++) {
+            acc[o] = wg[o][0] * in[0];
+#pragma unroll
+            for (int ch = 1; ch < 5; ch++) acc[o] = fmaf(wg[o][ch], in[ch], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < NM; o++) plane[o * 256 + bin] = acc[o];
     }
 }
 
@@ -998,17 +1047,24 @@ __device__ void imdct256_warp(const Tables& T, float* plane, int lane)
 }
 
 // ---------------------------------------------------------------------------
-// the kernel
+// the kernel: one warp per stream
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGroupThreads * kMaxGroupsPerCta, 1)
+__device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const WarpPtrs& G, uint32_t f)
+{
+    uint64_t a0 = P.frame_off[f] & ~(uint64_t)15;
+    uint32_t nb = stage_bytes(P, f);
+    fence_proxy_async();
+    mbar_expect_tx(G.mbar, nb);
+    tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
+}
+
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
 a52_decode_kernel(const DecodeParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     Tables& T = *reinterpret_cast<Tables*>(smem);
     const int tid = threadIdx.x;
-    const int gid = tid / kGroupThreads;          // group within the CTA
-    const int gt = tid % kGroupThreads;           // thread within the group
-    const int warp = gt >> 5, lane = gt & 31;
+    const int warp = tid >> 5, lane = tid & 31;
 
     // tables: global -> shared, whole CTA
     {
@@ -1016,69 +1072,67 @@ a52_decode_kernel(const DecodeParams P)
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
         for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    GroupPtrs G = carve(smem + align16((int)sizeof(Tables)) + gid * P.group_bytes, P.fbuf_bytes, P.ndelay);
+    WarpPtrs G = carve(smem + align16((int)sizeof(Tables)) + warp * P.warp_bytes, P.fbuf_bytes);
     GroupCtl* c = G.ctl;
-    if (gt == 0) {
-        mbar_init(&G.mbar[0], 1);
-        mbar_init(&G.mbar[1], 1);
+    uint32_t* const W = G.fbuf;
+    uint32_t* const planeU = reinterpret_cast<uint32_t*>(G.plane);
+    if (lane == 0) {
+        mbar_init(G.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero persistent decoder state once (liba52 leaves it uninitialised; valid streams never read it)
-    for (int i = gt; i < (int)(sizeof(GroupCtl) / 4); i += kGroupThreads)
-        reinterpret_cast<uint32_t*>(c)[i] = 0;
-    for (int i = gt; i < 7 * 256 * 2 / 4; i += kGroupThreads)
-        reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
+    for (int i = lane; i < (int)(sizeof(GroupCtl) / 4); i += 32) reinterpret_cast<uint32_t*>(c)[i] = 0;
+    for (int i = lane; i < 7 * 256 * 2 / 4; i += 32) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
     __syncthreads();
 
-    uint32_t phase[2] = {0, 0};
+    uint32_t phase = 0;
+    // overlap-add tails: dly[plane][r] <-> position p(r) = 64 (r >> 1) + 2 lane + (r & 1)
+    float dly[6][4];
 
     for (;;) {
         // ---- claim a stream ----
-        if (gt == 0) c->stream = atomicAdd(P.work_counter, 1);
-        group_sync(gid);
-        const int s = c->stream;
+        int s = 0;
+        if (lane == 0) s = atomicAdd(P.work_counter, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
         if (s >= P.nstreams) break;
         const uint32_t f0 = P.stream_first[s], f1 = P.stream_first[s + 1];
 
         // carry in
-        for (int i = gt; i < P.ndelay * 128; i += kGroupThreads)
-            G.delay[i] = P.carry ? P.carry[s].delay[i >> 7][i & 127] : 0.f;
-        if (gt == 0) {
-            c->dither_index = P.carry ? P.carry[s].dither_index % kDitherPeriod : 0;
-            c->per_channel = P.carry ? (P.carry[s].per_channel != 0) : 0;
+        uint32_t dither_index = 0;
+#pragma unroll
+        for (int o = 0; o < 6; o++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) dly[o][r] = 0.f;
+        if (P.carry) {
+            dither_index = P.carry[s].dither_index % kDitherPeriod;
+            if (lane == 0) c->per_channel = (P.carry[s].per_channel != 0);
+#pragma unroll
+            for (int o = 0; o < 6; o++)
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    float2 v = reinterpret_cast<const float2*>(P.carry[s].delay[o])[32 * jj + lane];
+                    dly[o][2 * jj] = v.x;
+                    dly[o][2 * jj + 1] = v.y;
+                }
+        } else if (lane == 0) {
+            c->per_channel = 0;
         }
+        // the next 32 dither generator states: ring (lane j) = state after dither_index + 1 + j steps
+        uint32_t ring = P.dither_seq[(dither_index + 1 + lane) % kDitherPeriod];
 
-        // prefetch the first frame
-        int cur = 0;
-        if (gt == 0 && f0 < f1) {
-            uint64_t off = P.frame_off[f0];
-            uint64_t a0 = off & ~(uint64_t)15;
-            uint32_t nb = stage_bytes(P, f0);
-            fence_proxy_async();
-            mbar_expect_tx(&G.mbar[0], nb);
-            tma_load_1d(G.fbuf[0], P.es + a0, nb, &G.mbar[0]);
-        }
-        group_sync(gid);
+        if (lane == 0 && f0 < f1) issue_frame_load(P, G, f0);
+        __syncwarp();
 
-        for (uint32_t f = f0; f < f1; f++, cur ^= 1) {
+        for (uint32_t f = f0; f < f1; f++) {
             const uint64_t off = P.frame_off[f];
-            uint32_t* W = G.fbuf[cur];
-            // wait for this frame, start the next one
-            mbar_wait(&G.mbar[cur], phase[cur]);
-            phase[cur] ^= 1;
-            if (gt == 0 && f + 1 < f1) {
-                uint64_t a1 = P.frame_off[f + 1] & ~(uint64_t)15;
-                uint32_t nb = stage_bytes(P, f + 1);
-                fence_proxy_async();
-                mbar_expect_tx(&G.mbar[cur ^ 1], nb);
-                tma_load_1d(G.fbuf[cur ^ 1], P.es + a1, nb, &G.mbar[cur ^ 1]);
-            }
+            bool next_issued = false;
+            mbar_wait(G.mbar, phase);
+            phase ^= 1;
             // big-endian bytes -> native words
-            for (int i = gt; i < P.fbuf_bytes / 4; i += kGroupThreads)
-                W[i] = __byte_perm(W[i], 0, 0x0123);
-            group_sync(gid);
+            for (int i = lane; i < P.fbuf_bytes / 4; i += 32) W[i] = __byte_perm(W[i], 0, 0x0123);
+            __syncwarp();
 
-            if (gt == 0) {
+            if (lane == 0) {
                 uint32_t base_bit = (uint32_t)(off & 15) * 8;
                 uint32_t avail = P.fbuf_bytes - 16 - (uint32_t)(off & 15);
                 // a frame never extends past the start of the next one / the end of the buffer
@@ -1093,243 +1147,271 @@ a52_decode_kernel(const DecodeParams P)
                 c->err = st;
                 if (P.frame_flags) P.frame_flags[f] = st ? 0 : c->output;
             }
-            group_sync(gid);
+            __syncwarp();
             int frame_status = c->err;            // 0, 1 (sync) or 2 (frame)
+            const bool frame_ok = c->frame_ok;
             uint8_t* out_frame = P.pcm + (size_t)f * P.frame_stride;
 
-            if (c->frame_ok) {
+            if (frame_ok) {
                 // zero the bits past the frame end so that overruns read zeros
-                {
-                    uint32_t lim = c->limit_bit;
-                    for (uint32_t i = (lim >> 5) + gt; i < (uint32_t)P.fbuf_bytes / 4; i += kGroupThreads) {
-                        if (i == (lim >> 5)) {
-                            uint32_t keep = lim & 31;
-                            W[i] = keep ? (W[i] & (0xffffffffu << (32 - keep))) : 0;
-                        } else W[i] = 0;
-                    }
+                uint32_t lim = c->limit_bit;
+                for (uint32_t i = (lim >> 5) + lane; i < (uint32_t)P.fbuf_bytes / 4; i += 32) {
+                    if (i == (lim >> 5)) {
+                        uint32_t keep = lim & 31;
+                        W[i] = keep ? (W[i] & (0xffffffffu << (32 - keep))) : 0;
+                    } else W[i] = 0;
                 }
-                group_sync(gid);
+                __syncwarp();
             }
 
             int blk = 0;
-            for (; blk < 6 && c->frame_ok; blk++) {
+            for (; blk < 6 && frame_ok; blk++) {
                 // ================= P: side info =================
-                if (gt == 0) c->err = parse_block(c, W, P);
-                group_sync(gid);
+                if (lane == 0) c->err = parse_block(c, W, P);
+                __syncwarp();
                 if (c->err) break;
                 const int nfchans = c->nfchans;
                 const uint32_t chincpl = c->chincpl;
+                const uint32_t limit = c->limit_bit;
 
                 // ================= E: exponents =================
                 {
-                    int bad = 0, k = 0;
+                    int bad = 0;
                     for (int a = 0; a < 7; a++) {
                         if (!c->expstr[a]) continue;
-                        if ((k++ & (kGroupWarps - 1)) != warp) continue;
                         uint8_t* e = G.exp + a * 256;
                         int dst = (a == 6) ? c->cplstrtmant : 1;
                         if (a != 6 && lane == 0) e[0] = c->exp_abs[a];
-                        bad |= decode_exponents(W, c->limit_bit, e + dst, c->expstr[a], c->exp_ngrp[a],
+                        bad |= decode_exponents(W, limit, e + dst, c->expstr[a], c->exp_ngrp[a],
                                                 c->exp_pos[a], c->exp_abs[a], lane);
                     }
-                    if (bad && lane == 0) c->err = 1;
+                    __syncwarp();
+                    if (bad) {
+                        if (lane == 0) c->err = 1;
+                        __syncwarp();
+                        break;
+                    }
                 }
-                group_sync(gid);
-                if (c->err) break;
 
                 // ================= B: bit allocation =================
                 if (c->do_alloc) {
-                    int k = 0;
                     for (int a = 0; a < 7; a++) {
                         if (!((c->do_alloc >> a) & 1)) continue;
-                        if ((k++ & (kGroupWarps - 1)) != warp) continue;
                         uint8_t* bp = G.bap + a * 256;
                         if (c->zero_alloc) {
                             for (int i = lane; i < 64; i += 32) reinterpret_cast<uint32_t*>(bp)[i] = 0;
                         } else {
-                            int16_t* scratch = G.band + warp * 100;
-                            bit_allocate_warp(T, c, a, G.exp + a * 256, bp, scratch, scratch + 50, lane);
+                            bit_allocate_warp(T, c, a, G.exp + a * 256, bp, G.band, G.band + 50, lane);
                         }
+                        __syncwarp();
                     }
-                    group_sync(gid);
                 }
 
                 // ================= L: locate =================
+                // planes start as zeros: bins past the coded range and undithered bap-0 bins stay zero
+                for (int i = lane; i < 6 * 256 / 4; i += 32)
+                    reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
                 const uint32_t total = c->total_bins;
-                const uint32_t K = (total + kGroupThreads - 1) / kGroupThreads;
-                const uint32_t my0 = min(gt * K, total), my1 = min(my0 + K, total);
-                const uint32_t ncpl_dith = __popc(chincpl & c->dithflag);
-                uint32_t n1 = 0, n2 = 0, n4 = 0, nd = 0, fixed = 0;
+                const uint32_t K = (total + 31) >> 5;
+                const uint32_t my0 = min(lane * K, total), my1 = min(my0 + K, total);
+                const uint32_t cpl_dith = chincpl & c->dithflag;
+                const uint32_t ncpl_dith = __popc(cpl_dith);
+                const int nseg = c->nseg;
+                int seg0 = 0;
+                for (int k = 1; k < nseg; k++)
+                    if (my0 >= c->seg[k].first) seg0 = k;
+                // cursor at my first bin: idx addresses exp[] (and bap[] = exp[] + 7*256)
+                uint32_t cur_idx, cur_left, cur_slot, cur_zmode;
                 {
-                    Cursor cu;
-                    if (my0 < my1) cursor_seek(cu, c, my0);
-                    for (uint32_t i = my0; i < my1; i++) {
-                        const Segment sg = c->seg[cu.seg];
-                        uint32_t b = G.bap[sg.arr * 256 + cu.bin];
-                        n1 += (b == 1); n2 += (b == 2); n4 += (b == 4);
-                        if (b == 0) nd += (sg.arr == 6) ? ncpl_dith : sg.dith;
-                        else if (b != 1 && b != 2 && b != 4) fixed += T.bap_bits[b];
-                        cursor_next(cu, c);
-                    }
+                    const Segment sg = c->seg[seg0];
+                    const uint32_t o = my0 - sg.first;
+                    cur_idx = sg.arr * 256 + sg.start + o;
+                    cur_slot = sg.plane * 256 + sg.start + o;
+                    cur_left = sg.count - o;
+                    cur_zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : sg.dith;
                 }
-                // scan 1: counts
-                uint32_t pa = n1 | (n2 << 16), pb = n4 | (nd << 16);
-                uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
-                if (lane == 31) { c->scan_a[warp] = ia; c->scan_b[warp] = ib; }
-                group_sync(gid);
-                uint32_t ea = ia - pa, eb = ib - pb;
-                for (int wv = 0; wv < warp; wv++) { ea += c->scan_a[wv]; eb += c->scan_b[wv]; }
-                const uint32_t c1 = ea & 0xffff, c2 = ea >> 16, c4 = eb & 0xffff, cd = eb >> 16;
-                // group codes started inside my chunk
-                uint32_t s1 = (c1 + n1 + 2) / 3 - (c1 + 2) / 3;
-                uint32_t s2 = (c2 + n2 + 2) / 3 - (c2 + 2) / 3;
-                uint32_t s4 = (c4 + n4 + 1) / 2 - (c4 + 1) / 2;
-                uint32_t mybits = fixed + 5 * s1 + 7 * s2 + 7 * s4;
-                uint32_t ic = warp_incl_scan(mybits, lane);
-                if (lane == 31) c->scan_c[warp] = ic;
-                if (gt == kGroupThreads - 1) c->blk_dither = cd + nd;
-                group_sync(gid);
-                uint32_t pos = c->bitpos + ic - mybits;
-                for (int wv = 0; wv < warp; wv++) pos += c->scan_c[wv];
-                if (gt == kGroupThreads - 1) c->mant_bits = pos + mybits - c->bitpos;
-
-                // walk 2: write descriptors, group codes, dither values
+                // pass 1: class counts of my run (lock step: every lane does K iterations)
+                uint32_t cnt = 0, fz = 0, nz = 0;
                 {
-                    Cursor cu;
-                    uint32_t k1 = c1, k2 = c2, k4 = c4;
-                    uint32_t lfsr = 0;
-                    if (nd) lfsr = P.dither_seq[(c->dither_index + cd) % kDitherPeriod];
-                    const uint32_t limit = c->limit_bit;
-                    if (my0 < my1) cursor_seek(cu, c, my0);
-                    for (uint32_t i = my0; i < my1; i++) {
-                        const Segment sg = c->seg[cu.seg];
-                        const uint32_t b = G.bap[sg.arr * 256 + cu.bin];
-                        const uint32_t e = G.exp[sg.arr * 256 + cu.bin];
-                        uint32_t* slot = reinterpret_cast<uint32_t*>(G.plane) + sg.plane * 256 + cu.bin;
+                    uint32_t idx = cur_idx, left = cur_left, zinc = (cur_zmode == 2) ? ncpl_dith : cur_zmode;
+                    int sgi = seg0;
+                    for (uint32_t k = my0; k < my1; k++) {
+                        const uint32_t b = G.bap[idx];
+                        const uint2 l = T.cnt_lut[b];
+                        cnt += l.x;
+                        fz += l.y;                                // plain field bits | zero count << 16
+                        idx++;
+                        if (--left == 0) {
+                            nz += (fz >> 16) * zinc;
+                            fz &= 0xffff;
+                            if (++sgi < nseg) {
+                                const Segment sg = c->seg[sgi];
+                                idx = sg.arr * 256 + sg.start;
+                                left = sg.count;
+                                zinc = (sg.arr == 6) ? ncpl_dith : sg.dith;
+                            }
+                        }
+                    }
+                    nz += (fz >> 16) * zinc;
+                    fz &= 0xffff;
+                }
+                const uint32_t fixed = fz;
+                const uint32_t n1 = cnt & 0xff, n2 = (cnt >> 8) & 0xff, n4 = (cnt >> 16) & 0xff, np = cnt >> 24;
+                const uint32_t pa = n1 | (n2 << 16), pb = n4 | (np << 16);
+                const uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
+                const uint32_t iz = warp_incl_scan(nz, lane);
+                const uint32_t ta = __shfl_sync(0xffffffffu, ia, 31), tb = __shfl_sync(0xffffffffu, ib, 31);
+                const uint32_t tz = __shfl_sync(0xffffffffu, iz, 31);
+                const uint32_t e1 = (ia - pa) & 0xffff, e2 = (ia - pa) >> 16;
+                const uint32_t e4 = (ib - pb) & 0xffff, ep = (ib - pb) >> 16, ez = iz - nz;
+                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
+                const uint32_t p1 = e1 % 3, p2 = e2 % 3, p4 = e4 & 1;
+                // group codes started inside my run
+                const uint32_t s1 = (p1 + n1 + 2) / 3 - (p1 != 0);
+                const uint32_t s2 = (p2 + n2 + 2) / 3 - (p2 != 0);
+                const uint32_t s4 = (p4 + n4 + 1) / 2 - (p4 != 0);
+                const uint32_t mybits = fixed + 5 * s1 + 7 * (s2 + s4);
+                const uint32_t ibits = warp_incl_scan(mybits, lane);
+                const uint32_t mant_bits = __shfl_sync(0xffffffffu, ibits, 31);
+                const uint32_t bitpos = c->bitpos;
+                // list layout: [class 1 | class 2 | class 4 | plain | dithered zeros]
+                const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
+
+                // pass 2: descriptors + work lists.  Branch-free for coded mantissas: the class of a
+                // bap selects, through emit_lut, which packed list cursor / phase counter moves.
+                {
+                    uint32_t pos = min(bitpos + ibits - mybits, limit);
+                    const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
+                    uint32_t run = 0;                              // list entries emitted so far, a byte per class
+                    uint32_t ph = p1 | (p2 << 2) | (p4 << 4);      // group phases, 2 bits per class (+ dummy)
+                    uint32_t bz = LZ + ez;
+                    uint32_t idx = cur_idx, left = cur_left, slot = cur_slot, zmode = cur_zmode;
+                    int sgi = seg0;
+                    for (uint32_t k = my0; k < my1; k++) {
+                        const uint32_t b = G.bap[idx], e = G.exp[idx];
                         if (b == 0) {
-                            if (sg.arr == 6) {
+                            if (zmode == 1) {
+                                G.list[bz++] = (uint16_t)slot;
+                                planeU[slot] = e;
+                            } else if (zmode == 2) {
                                 // one dither value per coupled channel, channel order (parse.c:466-481)
-                                for (int ch = 0; ch < nfchans; ch++) {
-                                    if (!((chincpl >> ch) & 1)) continue;
-                                    uint32_t d = make_desc(e, 0, 0, 0);
-                                    if ((c->dithflag >> ch) & 1) {
-                                        lfsr = (T.dither_lut[lfsr >> 8] ^ (lfsr << 8)) & 0xffff;
-                                        int dv = (3 * (int)(int16_t)lfsr) >> 2;
-                                        d = make_desc(e, 0, 0, 0) | (1u << 11) | ((uint32_t)dv << 16);
-                                    }
-                                    reinterpret_cast<uint32_t*>(G.plane)[ch * 256 + cu.bin] = d;
+                                uint32_t m = cpl_dith;
+                                while (m) {
+                                    const uint32_t ch = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const uint32_t s2 = ch * 256 + (slot & 255);
+                                    G.list[bz++] = (uint16_t)s2;
+                                    planeU[s2] = e;
                                 }
-                            } else {
-                                uint32_t d = make_desc(e, 0, 0, 0);
-                                if (sg.dith) {
-                                    lfsr = (T.dither_lut[lfsr >> 8] ^ (lfsr << 8)) & 0xffff;
-                                    int dv = (3 * (int)(int16_t)lfsr) >> 2;
-                                    d |= (1u << 11) | ((uint32_t)dv << 16);
-                                }
-                                *slot = d;
                             }
-                        } else if (b == 1 || b == 2 || b == 4) {
-                            uint32_t k, per, wbits, goff;
-                            if (b == 1) { k = k1++; per = 3; wbits = 5; goff = 0; }
-                            else if (b == 2) { k = k2++; per = 3; wbits = 7; goff = kGrpOff2; }
-                            else { k = k4++; per = 2; wbits = 7; goff = kGrpOff4; }
-                            uint32_t gi = k / per, dg = k - gi * per;
-                            if (dg == 0) {
-                                uint32_t code = (pos + wbits <= limit) ? peek_bits(W, pos, wbits) : 0;
-                                G.grp[goff + gi] = (uint8_t)code;
-                                pos += wbits;
-                            }
-                            *slot = make_desc(e, b, dg, gi);
                         } else {
-                            uint32_t wbits = T.bap_bits[b];
-                            *slot = make_desc(e, b, 0, pos);
-                            pos += wbits;
+                            const uint4 L = T.emit_lut[b];
+                            // L.x: cursor increment, L.y: byte selectors (base | count << 16),
+                            // L.z: phase shift | period << 8, L.w: field width
+                            const uint32_t li = (__byte_perm(base_lo, base_hi, L.y) +
+                                                 __byte_perm(run, 0, L.y >> 16)) & 0xffff;
+                            run += L.x;
+                            const uint32_t psh = L.z & 0xff, per = L.z >> 8;
+                            const uint32_t f = (ph >> psh) & 3;
+                            uint32_t nf = f + 1;
+                            nf = (nf == per) ? 0 : nf;
+                            ph ^= (f ^ nf) << psh;
+                            G.list[li] = (uint16_t)slot;
+                            planeU[slot] = make_desc(e, b, pos);
+                            pos = min(pos + (f == 0 ? L.w : 0u), limit);
                         }
-                        cursor_next(cu, c);
+                        idx++;
+                        slot++;
+                        if (--left == 0 && ++sgi < nseg) {
+                            const Segment sg = c->seg[sgi];
+                            idx = sg.arr * 256 + sg.start;
+                            slot = sg.plane * 256 + sg.start;
+                            left = sg.count;
+                            zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : sg.dith;
+                        }
                     }
                 }
-                group_sync(gid);
-                if (gt == 0) {
-                    c->bitpos += c->mant_bits;
-                    c->dither_index = (c->dither_index + c->blk_dither) % kDitherPeriod;
+                __syncwarp();
+                if (lane == 0) c->bitpos = bitpos + mant_bits;
+
+                // ================= U: unpack + dequantise, class by class =================
+                // dithered zeros: zero number k of the block takes the generator state dither_index + 1 + k
+                if (tz) {
+                    uint32_t ring_prev = ring;
+                    for (uint32_t r0 = 0; r0 < tz; r0 += 32) {
+                        const uint32_t k = r0 + lane;
+                        if (k < tz) {
+                            const uint32_t slot = G.list[LZ + k];
+                            const uint32_t e = planeU[slot];
+                            const int dv = (3 * (int)(int16_t)ring) >> 2;
+                            G.plane[slot] = (float)dv * pow2neg(15 + e);
+                        }
+                        ring_prev = ring;
+                        ring = lfsr_jump32(T, ring);
+                    }
+                    const uint32_t back = (32 - (tz & 31)) & 31;
+                    const uint32_t a = __shfl_sync(0xffffffffu, ring, (lane - back) & 31);
+                    const uint32_t b = __shfl_sync(0xffffffffu, ring_prev, (lane - back) & 31);
+                    ring = ((uint32_t)lane >= back) ? a : b;
+                    dither_index = (dither_index + tz) % kDitherPeriod;
+                }
+                if (t1) unpack_groups<3, 5, 32>(G, W, 0, t1, &T.q1[0][0], lane);
+                if (t2) unpack_groups<3, 7, 128>(G, W, L2, t2, &T.q2[0][0], lane);
+                if (t4) unpack_groups<2, 7, 128>(G, W, L4, t4, &T.q4[0][0], lane);
+                for (uint32_t k = lane; k < tp; k += 32) {
+                    const uint32_t slot = G.list[LP + k];
+                    const uint32_t d = planeU[slot];
+                    const uint32_t b = (d >> 5) & 15;
+                    const uint32_t wbits = T.bap_bits[b];
+                    const uint32_t raw = peek_nz(W, (d >> 10) & 0x7fff, wbits);
+                    // 7- and 15-level fields go through tables, wider ones are two's complement
+                    int q = ((int)(raw << (32 - wbits))) >> 16;
+                    if (b <= 5) q = T.q35[(b & 4) * 2 + raw];     // q3 at [0..7], q5 at [8..23]
+                    G.plane[slot] = (float)q * pow2neg(15 + (d & 31));
+                }
+                __syncwarp();
+                // the staged frame is no longer needed after the last block's mantissas: fetch the next one
+                if (blk == 5 && f + 1 < f1) {
+                    if (lane == 0) issue_frame_load(P, G, f + 1);
+                    next_issued = true;
                 }
 
-                // ================= U: unpack + dequantise =================
-                {
-                    const uint32_t limit = c->limit_bit;
-                    const int nplanes = c->out_lfe ? 6 : nfchans;
-                    const int first_cpl = chincpl ? __ffs(chincpl) - 1 : -1;
-                    for (int pl = 0; pl < nplanes; pl++) {
-                        if (pl >= nfchans && pl < 5) continue;
-                        int own_end, slot_end;
-                        float gain;
-                        if (pl == 5) { own_end = slot_end = 7; gain = c->gain[5]; }
-                        else {
-                            own_end = c->endmant[pl];
-                            slot_end = ((chincpl >> pl) & 1) ? c->cplendmant : own_end;
-                            gain = c->gain[pl];
-                        }
-                        for (int bin = gt; bin < 256; bin += kGroupThreads) {
-                            float* slotf = G.plane + pl * 256 + bin;
-                            float val = 0.f;
-                            // coupling range of a coupled channel: only the first coupled channel holds
-                            // the coupling channel's descriptors; the others hold dither descriptors
-                            // (coupling bap 0) or nothing yet (filled by the fan-out below)
-                            if (bin >= own_end && bin < slot_end && pl != first_cpl && G.bap[6 * 256 + bin] != 0)
-                                continue;
-                            if (bin < slot_end) {
-                                uint32_t d = __float_as_uint(*slotf);
-                                uint32_t e = d & 31, b = (d >> 5) & 15, dg = (d >> 9) & 3;
-                                // coupling-range slots hold the coupling channel's value without channel gain
-                                float g = (bin < own_end) ? gain : 1.0f;
-                                int q = 0;
-                                if (b == 0) {
-                                    q = (int)d >> 16;              // dither value or 0
-                                } else if (b == 1) {
-                                    q = T.q1[dg][G.grp[(d >> 12) & 0x7ff] & 31];
-                                } else if (b == 2) {
-                                    q = T.q2[dg][G.grp[kGrpOff2 + ((d >> 12) & 0x7ff)] & 127];
-                                } else if (b == 4) {
-                                    q = T.q4[dg][G.grp[kGrpOff4 + ((d >> 12) & 0x7ff)] & 127];
-                                } else {
-                                    uint32_t wbits = T.bap_bits[b];
-                                    uint32_t p = (d >> 12) & 0x7fff;
-                                    uint32_t raw = (p + wbits <= limit) ? peek_bits(W, p, wbits) : 0;
-                                    if (b == 3) q = T.q3[raw];
-                                    else if (b == 5) q = T.q5[raw];
-                                    else q = ((int)(raw << (32 - wbits))) >> 16;
-                                }
-                                val = (float)q * (g * pow2neg(15 + e));
-                            }
-                            *slotf = val;
-                        }
+                const bool unif = c->uniform_path;
+                // channel gains (downmix.c:162-330 folded into dequantisation by liba52, parse.c:347-348)
+                if (!unif) {
+                    for (int ch = 0; ch < nfchans; ch++) {
+                        const float g1 = c->gain[ch];
+                        const int end = c->endmant[ch];
+                        for (int bin = lane; bin < end; bin += 32) G.plane[ch * 256 + bin] *= g1;
                     }
                 }
-                group_sync(gid);
+                if (c->out_lfe && lane < 7) G.plane[5 * 256 + lane] *= c->gain[5];
+                __syncwarp();
 
                 // ================= C: coupling fan-out (parse.c:435-556) =================
                 if (chincpl) {
-                    int first = __ffs(chincpl) - 1;
-                    for (int bin = c->cplstrtmant + gt; bin < c->cplendmant; bin += kGroupThreads) {
-                        // coupling band of this bin
+                    const int first = __ffs(chincpl) - 1;
+                    for (int bin = c->cplstrtmant + lane; bin < c->cplendmant; bin += 32) {
                         int sub = (bin - c->cplstrtmant) / 12;
                         int bnd = sub - __popc(c->cplbndstrc & ((1u << sub) - 1));
                         bool zero_bap = (G.bap[6 * 256 + bin] == 0);
                         float cv = G.plane[first * 256 + bin];
                         for (int ch = nfchans - 1; ch >= 0; ch--) {
                             if (!((chincpl >> ch) & 1)) continue;
-                            float co = c->cplco[ch][bnd] * c->gain[ch];
+                            // channel gain: here when channels are transformed one by one, in the mix
+                            // weights otherwise (parse.c:456-457: cplco * coeff[ch])
+                            float co = unif ? c->cplco[ch][bnd] : c->cplco[ch][bnd] * c->gain[ch];
                             float src = zero_bap ? G.plane[ch * 256 + bin] : cv;
                             G.plane[ch * 256 + bin] = src * co;
                         }
                     }
-                    group_sync(gid);
+                    __syncwarp();
                 }
 
                 // ================= rematrix (parse.c:837-865) =================
                 if (c->acmod == 2 && c->rematflg) {
                     int end = min(c->endmant[0], c->endmant[1]);
-                    for (int bin = 13 + gt; bin < end; bin += kGroupThreads) {
+                    for (int bin = 13 + lane; bin < end; bin += 32) {
                         int band = (bin >= 61) ? 3 : (bin >= 37) ? 2 : (bin >= 25) ? 1 : 0;
                         if ((c->rematflg >> band) & 1) {
                             float a = G.plane[bin], b = G.plane[256 + bin];
@@ -1337,132 +1419,113 @@ a52_decode_kernel(const DecodeParams P)
                             G.plane[256 + bin] = a - b;
                         }
                     }
-                    group_sync(gid);
+                    __syncwarp();
                 }
 
                 // ---- optional dumps ----
                 if (P.dbg_exp) {
                     size_t o = ((size_t)f * 6 + blk) * 7 * 256;
-                    for (int i = gt; i < 7 * 256; i += kGroupThreads) {
+                    for (int i = lane; i < 7 * 256; i += 32) {
                         P.dbg_exp[o + i] = G.exp[i];
                         P.dbg_bap[o + i] = G.bap[i];
                     }
                 }
                 if (P.dbg_coef) {
                     size_t o = ((size_t)f * 6 + blk) * 6 * 256;
-                    for (int i = gt; i < 6 * 256; i += kGroupThreads) {
+                    for (int i = lane; i < 6 * 256; i += 32) {
                         int pl = i >> 8;
                         bool live = (pl < nfchans) || (pl == 5 && c->out_lfe);
-                        P.dbg_coef[o + i] = live ? G.plane[i] : 0.f;
+                        float v = live ? G.plane[i] : 0.f;
+                        if (unif && pl < 5) v *= c->gain[pl];
+                        P.dbg_coef[o + i] = v;
                     }
                 }
-                if (P.dbg_info && gt == 0) {
+                if (P.dbg_info && lane == 0) {
                     int32_t* o = P.dbg_info + ((size_t)f * 6 + blk) * 16;
                     for (int i = 0; i < 5; i++) o[i] = c->endmant[i];
                     o[5] = c->cplstrtmant; o[6] = c->cplendmant; o[7] = c->chincpl;
-                    o[8] = P.dither_seq[c->dither_index]; o[9] = c->acmod; o[10] = c->lfeon;
-                    o[11] = c->output; o[12] = c->blksw | (c->uniform_path << 8) | ((c->clev == 0.f) << 9) | ((c->slev == 0.f) << 10); o[13] = c->ncplbnd; o[14] = c->rematflg;
+                    o[8] = P.dither_seq[dither_index]; o[9] = c->acmod; o[10] = c->lfeon;
+                    o[11] = c->output;
+                    o[12] = c->blksw | (c->uniform_path << 8) | ((c->clev == 0.f) << 9) | ((c->slev == 0.f) << 10);
+                    o[13] = c->ncplbnd; o[14] = c->rematflg;
                     o[15] = c->csnroffst;
                 }
 
                 // ================= M: coefficient-domain mix =================
-                const MixEntry mx = c_mix[c->acmod * 11 + (c->output & M_MASK)];
-                const int nmain = mx.nout;
+                const int nmain = c->nout;
                 const bool uniform = c->uniform_path;
+                const int lfe_on = c->out_lfe;
                 if (uniform) {
-                    for (int bin = gt; bin < 256; bin += kGroupThreads) {
-                        float in[5], outv[5];
-#pragma unroll
-                        for (int ch = 0; ch < 5; ch++) in[ch] = (ch < nfchans) ? G.plane[ch * 256 + bin] : 0.f;
-#pragma unroll
-                        for (int o = 0; o < 5; o++) {
-                            float acc = 0.f;
-                            if (o < nmain) {
-#pragma unroll
-                                for (int ch = 0; ch < 5; ch++) {
-                                    if ((mx.pos[o] >> ch) & 1) acc += in[ch];
-                                    else if ((mx.neg[o] >> ch) & 1) acc -= in[ch];
-                                }
-                            }
-                            outv[o] = acc;
-                        }
-#pragma unroll
-                        for (int o = 0; o < 5; o++)
-                            if (o < nmain) G.plane[o * 256 + bin] = outv[o];
+                    switch (nmain) {
+                    case 1: mix_planes<1>(G.plane, c, lane); break;
+                    case 2: mix_planes<2>(G.plane, c, lane); break;
+                    case 3: mix_planes<3>(G.plane, c, lane); break;
+                    default: mix_planes<4>(G.plane, c, lane); break;
                     }
-                    group_sync(gid);
+                    __syncwarp();
                 }
 
                 // ================= T: transforms =================
                 {
                     const int ntr = uniform ? nmain : nfchans;
-                    const int njobs = ntr + (c->out_lfe ? 1 : 0);
-                    for (int j = warp; j < njobs; j += kGroupWarps) {
-                        int pl = (j < ntr) ? j : 5;
+                    for (int pl = 0; pl < 6; pl++) {
+                        if (pl < 5 ? (pl >= ntr) : !lfe_on) continue;
+                        if (!uniform && pl < 5 && c->gain[pl] == 0.f) continue;     // parse.c:897-909
                         bool shortblk = (pl < 5) && ((c->blksw >> (uniform ? 0 : pl)) & 1);
                         if (shortblk) imdct256_warp(T, G.plane + pl * 256, lane);
                         else imdct512_warp(T, G.plane + pl * 256, lane);
                     }
                 }
-                group_sync(gid);
+                __syncwarp();
 
                 // ================= O: window + overlap-add (+ time-domain mix) + store ========
-                // The delay planes follow liba52's state machine (parse.c:881-937): after a block that
-                // mixed coefficients they hold the downmixed tail (planes 0..nout-1); after a block that
+                // The tails follow liba52's state machine (parse.c:881-937): after a block that mixed
+                // coefficients they hold the downmixed tail (planes 0..nout-1); after a block that
                 // transformed every coded channel they hold per-channel tails (planes 0..nfchans-1).
                 // Switching representation = a52_downmix / a52_upmix on the delay (downmix.c:480-685);
                 // a channel whose gain is zero keeps its tail untouched and unheard (parse.c:897-909).
                 {
-                    const int lfe_on = c->out_lfe;
                     const int nout = nmain + lfe_on;
                     const float bias = P.bias;
-                    float* D = G.delay;
-                    const int p = gt;                              // kGroupThreads == 128 positions
-                    const float w0 = T.window[p], w1 = T.window[255 - p];
-                    float y0[6], y1[6];                            // by output channel (0 = LFE when present)
+                    const bool identity = c->identity_mix;
+                    const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
+                    const float2* win2 = reinterpret_cast<const float2*>(T.window);
+                    // y[oc][r]: r = 0,1 -> samples p, p+1 ; r = 2,3 -> samples 254-p, 255-p  (per jj)
+                    float y[2][6][4];
 #pragma unroll
-                    for (int o = 0; o < 6; o++) { y0[o] = 0.f; y1[o] = 0.f; }
-                    if (lfe_on) {
-                        float U = G.plane[5 * 256 + p], V = G.plane[5 * 256 + 128 + p], Dv = D[5 * 128 + p];
-                        y0[0] = Dv * w1 - U * w0;
-                        y1[0] = Dv * w0 + U * w1;
-                        D[5 * 128 + p] = V;
-                    }
-                    if (uniform) {
-                        if (c->per_channel) {
+                    for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                        for (int o = 0; o < 6; o++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++) y[jj][o][r] = 0.f;
+
+                    if (uniform && c->per_channel) {
+                        // a52_downmix on the per-channel tails; zero-gain channels are left out
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
                             float d[5], m[5];
 #pragma unroll
                             for (int ch = 0; ch < 5; ch++)
-                                d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? D[ch * 128 + p] : 0.f;
+                                d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? dly[ch][r] : 0.f;
 #pragma unroll
                             for (int o = 0; o < 5; o++) {
                                 float acc = 0.f;
 #pragma unroll
-                                for (int ch = 0; ch < 5; ch++) {
-                                    if ((mx.pos[o] >> ch) & 1) acc += d[ch];
-                                    else if ((mx.neg[o] >> ch) & 1) acc -= d[ch];
-                                }
+                                for (int ch = 0; ch < 5; ch++) acc = fmaf(c->wt[o][ch], d[ch], acc);
                                 m[o] = acc;
                             }
 #pragma unroll
                             for (int o = 0; o < 5; o++)
-                                if (o < nmain) D[o * 128 + p] = m[o];
+                                if (o < nmain) dly[o][r] = m[o];
                         }
+                    } else if (!uniform && !c->per_channel) {
+                        // a52_upmix: downmixed tails go back to the coded channels they belong to
+                        const MixEntry mx = c_mix[c->acmod * 11 + (c->output & M_MASK)];
 #pragma unroll
-                        for (int o = 0; o < 5; o++) {
-                            if (o < nmain) {
-                                float U = G.plane[o * 256 + p], V = G.plane[o * 256 + 128 + p], Dv = D[o * 128 + p];
-                                float a = Dv * w1 - U * w0, b = Dv * w0 + U * w1;
-                                D[o * 128 + p] = V;
-                                if (lfe_on) { y0[o + 1 > 5 ? 5 : o + 1] = a; y1[o + 1 > 5 ? 5 : o + 1] = b; }
-                                else { y0[o] = a; y1[o] = b; }
-                            }
-                        }
-                    } else {
-                        if (!c->per_channel) {
+                        for (int r = 0; r < 4; r++) {
                             float m[5];
 #pragma unroll
-                            for (int o = 0; o < 5; o++) m[o] = D[o * 128 + p];
+                            for (int o = 0; o < 5; o++) m[o] = dly[o][r];
 #pragma unroll
                             for (int ch = 0; ch < 5; ch++) {
                                 if (ch < nfchans) {
@@ -1470,76 +1533,131 @@ a52_decode_kernel(const DecodeParams P)
 #pragma unroll
                                     for (int o = 0; o < 5; o++)
                                         if (mx.up[ch] == o) v = m[o];
-                                    D[ch * 128 + p] = v;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int ch = 0; ch < 5; ch++) {
-                            if (ch < nfchans && c->gain[ch] != 0.f) {
-                                float U = G.plane[ch * 256 + p], V = G.plane[ch * 256 + 128 + p], Dv = D[ch * 128 + p];
-                                float a = Dv * w1 - U * w0, b = Dv * w0 + U * w1;
-                                D[ch * 128 + p] = V;
-#pragma unroll
-                                for (int o = 0; o < 5; o++) {
-                                    const int oo = lfe_on ? (o + 1 > 5 ? 5 : o + 1) : o;
-                                    if ((mx.pos[o] >> ch) & 1) { y0[oo] += a; y1[oo] += b; }
-                                    else if ((mx.neg[o] >> ch) & 1) { y0[oo] -= a; y1[oo] -= b; }
+                                    dly[ch][r] = v;
                                 }
                             }
                         }
                     }
+
 #pragma unroll
-                    for (int oc = 0; oc < 6; oc++) {
-                        if (oc < nout) {
-                            float a = y0[oc] + bias, b = y1[oc] + bias;
-                            if (P.out_fmt == 0) {
-                                float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
-                                dst[p] = a;
-                                dst[255 - p] = b;
-                            } else if (P.out_fmt == 1) {
-                                float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
-                                dst[p * nout + oc] = a;
-                                dst[(255 - p) * nout + oc] = b;
+                    for (int pl = 0; pl < 6; pl++) {
+                        const bool is_lfe = (pl == 5);
+                        bool live;
+                        if (is_lfe) live = lfe_on;
+                        else if (uniform) live = pl < nmain;
+                        else live = pl < nfchans && c->gain[pl] != 0.f;
+                        if (!live) continue;
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const int q = 32 * jj + lane;                    // float2 index: p = 2 q
+                            const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
+                            const float2 wl = win2[q], wh = win2[127 - q];  // (w[p], w[p+1]), (w[254-p], w[255-p])
+                            const float D0 = dly[pl][2 * jj], D1 = dly[pl][2 * jj + 1];
+                            const float a0 = D0 * wh.y - U.x * wl.x;        // sample p
+                            const float a1 = D1 * wh.x - U.y * wl.y;        // sample p + 1
+                            const float b0 = D0 * wl.x + U.x * wh.y;        // sample 255 - p
+                            const float b1 = D1 * wl.y + U.y * wh.x;        // sample 254 - p
+                            dly[pl][2 * jj] = V.x;
+                            dly[pl][2 * jj + 1] = V.y;
+                            if (is_lfe) {
+                                y[jj][0][0] = a0; y[jj][0][1] = a1; y[jj][0][2] = b1; y[jj][0][3] = b0;
+                            } else if (uniform || identity) {
+#pragma unroll
+                                for (int o = 0; o < 5; o++) {
+                                    if (o == pl) {
+#pragma unroll
+                                        for (int oo = 0; oo < 6; oo++)
+                                            if (oo == o + lfe_on) {
+                                                y[jj][oo][0] = a0; y[jj][oo][1] = a1; y[jj][oo][2] = b1; y[jj][oo][3] = b0;
+                                            }
+                                    }
+                                }
                             } else {
-                                int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
-                                int ia = __float2int_rn(y0[oc] * 32768.f), ib = __float2int_rn(y1[oc] * 32768.f);
-                                ia = min(max(ia, -32768), 32767);
-                                ib = min(max(ib, -32768), 32767);
-                                dst[p * nout + oc] = (int16_t)ia;
-                                dst[(255 - p) * nout + oc] = (int16_t)ib;
+#pragma unroll
+                                for (int o = 0; o < 5; o++) {
+                                    const float wgt = c->wt[o][pl];
+#pragma unroll
+                                    for (int oo = 0; oo < 6; oo++)
+                                        if (o < nmain && oo == o + lfe_on) {
+                                            y[jj][oo][0] = fmaf(wgt, a0, y[jj][oo][0]);
+                                            y[jj][oo][1] = fmaf(wgt, a1, y[jj][oo][1]);
+                                            y[jj][oo][2] = fmaf(wgt, b1, y[jj][oo][2]);
+                                            y[jj][oo][3] = fmaf(wgt, b0, y[jj][oo][3]);
+                                        }
+                                }
+                            }
+                        }
+                    }
+
+                    // stores: samples (p, p+1) and (254-p, 255-p), p = 2 (32 jj + lane)
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++) {
+                        const int p = 2 * (32 * jj + lane);
+                        if (P.out_fmt == 1 && nout == 2) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
+                            dst[p >> 1] = make_float4(y[jj][0][0] + bias, y[jj][1][0] + bias, y[jj][0][1] + bias, y[jj][1][1] + bias);
+                            dst[(254 - p) >> 1] = make_float4(y[jj][0][2] + bias, y[jj][1][2] + bias, y[jj][0][3] + bias, y[jj][1][3] + bias);
+                        } else {
+#pragma unroll
+                            for (int oc = 0; oc < 6; oc++) {
+                                if (oc >= nout) continue;
+                                const float v0 = y[jj][oc][0], v1 = y[jj][oc][1], v2 = y[jj][oc][2], v3 = y[jj][oc][3];
+                                if (P.out_fmt == 0) {
+                                    float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
+                                    *reinterpret_cast<float2*>(dst + p) = make_float2(v0 + bias, v1 + bias);
+                                    *reinterpret_cast<float2*>(dst + 254 - p) = make_float2(v2 + bias, v3 + bias);
+                                } else if (P.out_fmt == 1) {
+                                    float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
+                                    dst[p * nout + oc] = v0 + bias;
+                                    dst[(p + 1) * nout + oc] = v1 + bias;
+                                    dst[(254 - p) * nout + oc] = v2 + bias;
+                                    dst[(255 - p) * nout + oc] = v3 + bias;
+                                } else {
+                                    int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
+                                    dst[p * nout + oc] = (int16_t)min(max(__float2int_rn(v0 * 32768.f), -32768), 32767);
+                                    dst[(p + 1) * nout + oc] = (int16_t)min(max(__float2int_rn(v1 * 32768.f), -32768), 32767);
+                                    dst[(254 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v2 * 32768.f), -32768), 32767);
+                                    dst[(255 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v3 * 32768.f), -32768), 32767);
+                                }
                             }
                         }
                     }
                 }
-                group_sync(gid);
-                if (gt == 0) c->per_channel = uniform ? 0 : 1;
+                __syncwarp();
+                if (lane == 0) c->per_channel = uniform ? 0 : 1;
+                __syncwarp();
             }   // blocks
 
-            if (c->frame_ok && blk < 6) frame_status = 16 + blk;     // A52_ST_BAD_BLOCK + block
+            if (frame_ok && blk < 6) frame_status = 16 + blk;     // A52_ST_BAD_BLOCK + block
             if (frame_status) {
                 // silence for everything not produced
-                int nout = c->frame_ok ? (c->nout + c->out_lfe) : P.nout_req;
+                int nout = frame_ok ? (c->nout + c->out_lfe) : P.nout_req;
                 int ssz = (P.out_fmt == 2) ? 2 : 4;
                 size_t from = (size_t)blk * 256 * nout * ssz;
                 size_t to = (size_t)6 * 256 * nout * ssz;
-                for (size_t i = from + gt * 4; i < to; i += kGroupThreads * 4)
+                for (size_t i = from + lane * 4; i < to; i += 32 * 4)
                     *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
             }
-            if (gt == 0 && P.status) P.status[f] = frame_status;
-            group_sync(gid);
+            if (lane == 0 && P.status) P.status[f] = frame_status;
+            __syncwarp();
+            if (!next_issued && f + 1 < f1 && lane == 0) issue_frame_load(P, G, f + 1);
+            __syncwarp();
         }   // frames
 
         // carry out
         if (P.carry) {
-            for (int i = gt; i < P.ndelay * 128; i += kGroupThreads)
-                P.carry[s].delay[i >> 7][i & 127] = G.delay[i];
-            if (gt == 0) {
-                P.carry[s].dither_index = c->dither_index;
+#pragma unroll
+            for (int o = 0; o < 6; o++)
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++)
+                    reinterpret_cast<float2*>(P.carry[s].delay[o])[32 * jj + lane] =
+                        make_float2(dly[o][2 * jj], dly[o][2 * jj + 1]);
+            if (lane == 0) {
+                P.carry[s].dither_index = dither_index;
                 P.carry[s].per_channel = c->per_channel;
             }
         }
-        group_sync(gid);
+        __syncwarp();
     }
 }
 

@@ -212,8 +212,8 @@ static void build_tables(Tables* T)
         for (int d = 0; d < 3; d++) T->q2[d][c] = c < 125 ? ac3_q5[d5[d]] : 0;
         for (int d = 0; d < 2; d++) T->q4[d][c] = c < 121 ? ac3_q11[d11[d]] : 0;
     }
-    for (int i = 0; i < 8; i++) T->q3[i] = ac3_q7[i];
-    for (int i = 0; i < 16; i++) T->q5[i] = ac3_q15[i];
+    for (int i = 0; i < 8; i++) T->q35[i] = ac3_q7[i];
+    for (int i = 0; i < 16; i++) T->q35[8 + i] = ac3_q15[i];
     for (int i = 0; i < 256; i++) {
         T->dither_lut[i] = ac3_dither_lut[i];
         T->masktab[i] = ac3_masktab[i];
@@ -224,6 +224,32 @@ static void build_tables(Tables* T)
     for (int i = 0; i < 51; i++) T->bndtab[i] = ac3_bndtab[i];
     T->bndtab[51] = 253;
     for (int i = 0; i < 16; i++) T->bap_bits[i] = ac3_bap_bits[i];
+    // dither generator, 32 steps at once: linear over GF(2), so split by byte
+    for (int v = 0; v < 256; v++) {
+        uint16_t hi = (uint16_t)(v << 8), lo = (uint16_t)v;
+        for (int k = 0; k < 32; k++) {
+            hi = (uint16_t)(ac3_dither_lut[hi >> 8] ^ (uint16_t)(hi << 8));
+            lo = (uint16_t)(ac3_dither_lut[lo >> 8] ^ (uint16_t)(lo << 8));
+        }
+        T->jump_hi[v] = hi;
+        T->jump_lo[v] = lo;
+    }
+    for (int b = 0; b < 16; b++) {
+        uint32_t x = 0, y = 0;
+        if (b == 1) x = 1;
+        else if (b == 2) x = 1u << 8;
+        else if (b == 4) x = 1u << 16;
+        else if (b != 0) { x = 1u << 24; y = ac3_bap_bits[b]; }
+        else y = 1u << 16;
+        T->cnt_lut[b] = make_uint2(x, y);
+        // emit: class 0 = 3-level, 1 = 5-level, 2 = 11-level, 3 = everything else that carries bits
+        int cls = b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3;
+        uint32_t selbase = cls == 0 ? 0x4410u : cls == 1 ? 0x4432u : cls == 2 ? 0x4454u : 0x4476u;
+        uint32_t selcnt = 0x4440u | (uint32_t)cls;      // run byte `cls`, zero-extended (b operand is 0)
+        uint32_t per = cls < 2 ? 3 : cls == 2 ? 2 : 1;  // period 1: every plain mantissa starts a field
+        uint32_t width = cls < 1 ? 5 : cls <= 2 ? 7 : ac3_bap_bits[b];
+        T->emit_lut[b] = make_uint4(1u << (8 * cls), selbase | (selcnt << 16), (uint32_t)(2 * cls) | (per << 8), width);
+    }
 }
 
 static int nout_of_flags(int flags)
@@ -259,7 +285,7 @@ __global__ void a52_maxlen_kernel(const uint8_t* es, const uint64_t* off, int nf
 struct a52_batch_s {
     int device = 0;
     int num_sms = 0;
-    int groups_per_cta = 2;
+    int warps_per_cta = 0;         // 0 = as many as fit
     int max_frame_hint = 0;
     uint16_t* d_dither = nullptr;
     int* d_counter = nullptr;      // [0] work counter, [1] max frame length
@@ -311,10 +337,8 @@ a52_batch_t* a52_batch_create(int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->num_sms = prop.multiProcessorCount;
-    const char* g = getenv("A52_B200_GROUPS_PER_CTA");
-    if (g) ctx->groups_per_cta = atoi(g);
-    if (ctx->groups_per_cta < 1) ctx->groups_per_cta = 1;
-    if (ctx->groups_per_cta > a52::kMaxGroupsPerCta) ctx->groups_per_cta = a52::kMaxGroupsPerCta;
+    const char* g = getenv("A52_B200_WARPS_PER_CTA");
+    if (g) ctx->warps_per_cta = atoi(g);
 
     // constant tables
     a52::Tables* T = new a52::Tables;
@@ -421,22 +445,25 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     if (max_frame_bytes < 128) max_frame_bytes = 128;
     if (max_frame_bytes > 3840) max_frame_bytes = 3840;
     P.fbuf_bytes = align16(max_frame_bytes + 15) + 16 + 16;
-    P.ndelay = 6;
-    P.group_bytes = group_smem_bytes(P.fbuf_bytes, P.ndelay);
+    P.warp_bytes = warp_smem_bytes(P.fbuf_bytes);
     P.dither_seq = ctx->d_dither;
     P.work_counter = ctx->d_counter;
-    const int G = ctx->groups_per_cta;
-    const int threads = G * kGroupThreads;
-    const size_t smem = align16((int)sizeof(Tables)) + (size_t)G * P.group_bytes;
-    int occ = 0;
-    A52_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, a52_decode_kernel, threads, smem));
-    if (occ < 1) {
-        snprintf(ctx->err, sizeof(ctx->err), "decode kernel does not fit: %zu bytes of shared memory", smem);
+    const int tables = align16((int)sizeof(Tables));
+    int fit = (227 * 1024 - tables) / P.warp_bytes;
+    if (fit > kMaxWarpsPerCta) fit = kMaxWarpsPerCta;
+    if (fit < 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "decode kernel does not fit: %d bytes of shared memory per warp", P.warp_bytes);
         return -2;
     }
-    int grid = ctx->num_sms * occ;
-    int need = (P.nstreams + G - 1) / G;
-    if (grid > need) grid = need;
+    int G = fit;
+    if (ctx->warps_per_cta > 0 && ctx->warps_per_cta < G) G = ctx->warps_per_cta;
+    // small batches: spread the streams over all SMs
+    int per_sm = (P.nstreams + ctx->num_sms - 1) / ctx->num_sms;
+    if (per_sm < G) G = per_sm < 1 ? 1 : per_sm;
+    const int threads = G * 32;
+    const size_t smem = (size_t)tables + (size_t)G * P.warp_bytes;
+    int grid = (P.nstreams + G - 1) / G;
+    if (grid > ctx->num_sms) grid = ctx->num_sms;
     if (grid < 1) grid = 1;
     A52_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
     // timing events
