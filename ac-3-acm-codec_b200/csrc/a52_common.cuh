@@ -11,7 +11,7 @@
 
 namespace a52 {
 
-constexpr int kMaxWarpsPerCta = 16;  // one warp walks one stream; a CTA is just a bag of warps
+constexpr int kMaxWarpsPerCta = 14;  // one warp walks one stream; a CTA is just a bag of warps
 constexpr int kDitherPeriod = 65535;
 
 // output mode ids == liba52's A52_* flag values (include/a52.h)
@@ -35,17 +35,15 @@ struct __align__(16) Tables {
     uint16_t dither_lut[256];  // CRC-16/0xA011 byte step (tables.h:213-246)
     uint16_t jump_hi[256];     // dither generator advanced 32 steps: contribution of the high byte
     uint16_t jump_lo[256];     //                                      and of the low byte
-    uint2    cnt_lut[16];      // per bap: x = n1 | n2 << 8 | n4 << 16 | nplain << 24, y = plain field bits | zero << 16
-    uint4    emit_lut[16];     // per bap: x = list cursor increment (a byte per class), y = byte selectors
-                               // (16-bit list base | cursor byte << 16), z = phase shift | group period << 8,
-                               // w = bits taken when the mantissa starts a field / group
+    uint2    cnt_lut[18];      // per bap: x = n1 | n2 << 8 | n4 << 16 | nplain << 24, y = plain field bits | zero << 16
+    uint4    emit_lut[32];     // per bap (+16: bap-0 mantissas of this run are dithered), see build_tables()
     uint16_t hth[3 * 50];
     uint8_t  masktab[256];
     uint8_t  latab[256];
     uint8_t  baptab[64];
     uint8_t  bndtab[52];
     uint8_t  bap_bits[16];
-    uint8_t  pad_[12];
+    uint8_t  pad_[8];
 };
 
 // ---- per-(requested output, acmod, mix levels) constants, host-computed ----

@@ -30,6 +30,7 @@
 // different FFT factorisation (tolerance 1e-5 relative RMS, measured ~1e-7).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -101,6 +102,11 @@ struct __align__(16) GroupCtl {
     int8_t   deltba[7][50];
     Segment  seg[8];
     uint32_t total_bins;
+    // ---- lane plan of the locate passes ----
+    uint16_t plan_count[8];
+    uint8_t  plan_lane0[9];    // first lane of each segment (+ end)
+    uint8_t  plan_nseg;
+    uint16_t plan_K;           // run length per lane
     float    wt[5][5];         // mix matrix [output][coded channel] in {-1, 0, +1} (downmix.c:480-619)
     int      identity_mix;     // output channel o is exactly coded channel o
 };
@@ -581,6 +587,32 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     }
     c->nseg = ns;
     c->total_bins = flat;
+    // Lanes of the locate passes: every lane walks a run of at most K mantissas of ONE segment,
+    // lanes in coded order (so that one warp scan orders the whole block).  K = smallest run
+    // length for which the segments need no more than 32 lanes; recomputed only when the
+    // segment sizes change.
+    {
+        bool same = (ns == c->plan_nseg);
+        for (int k = 0; k < ns; k++) same = same && (c->seg[k].count == c->plan_count[k]);
+        if (!same) {
+            uint32_t K = (flat + 31) >> 5;
+            if (K < 1) K = 1;
+            for (;; K++) {
+                uint32_t lanes = 0;
+                for (int k = 0; k < ns; k++) lanes += (c->seg[k].count + K - 1) / K;
+                if (lanes <= 32) break;
+            }
+            uint32_t l0 = 0;
+            for (int k = 0; k < ns; k++) {
+                c->plan_lane0[k] = (uint8_t)l0;
+                c->plan_count[k] = c->seg[k].count;
+                l0 += (c->seg[k].count + K - 1) / K;
+            }
+            c->plan_lane0[ns] = (uint8_t)l0;
+            c->plan_nseg = ns;
+            c->plan_K = K;
+        }
+    }
 
     // transform path (parse.c:881-886): mix coefficients first unless block
     // switch flags differ between channels that get mixed
@@ -805,6 +837,28 @@ __device__ __forceinline__ uint32_t lfsr_jump32(const Tables& T, uint32_t s)
 __device__ __forceinline__ uint32_t make_desc(uint32_t exp, uint32_t bap, uint32_t pos)
 {
     return exp | (bap << 5) | (pos << 10);
+}
+
+// byte permute without the 0x7777 selector masking __byte_perm adds (selector nibbles here are 0..7)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// read-only table loads through 32-bit shared addresses (keeps the shared-window base out of the loops)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
 }
 
 // peek without a limit check: descriptor positions are clamped to the frame end at emit time
@@ -1085,6 +1139,10 @@ a52_decode_kernel(const DecodeParams P)
     for (int i = lane; i < 7 * 256 * 2 / 4; i += 32) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
     __syncthreads();
 
+    // 32-bit shared address of the tables, made opaque so that it lives in a register instead of
+    // being rebuilt from the shared-window base inside the hot loops
+    uint32_t tab_base;
+    asm volatile("mov.u32 %0, %1;" : "=r"(tab_base) : "r"(smem_u32(&T)));
     uint32_t phase = 0;
     // overlap-add tails: dly[plane][r] <-> position p(r) = 64 (r >> 1) + 2 lane + (r & 1)
     float dly[6][4];
@@ -1211,51 +1269,36 @@ a52_decode_kernel(const DecodeParams P)
                 // planes start as zeros: bins past the coded range and undithered bap-0 bins stay zero
                 for (int i = lane; i < 6 * 256 / 4; i += 32)
                     reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
-                const uint32_t total = c->total_bins;
-                const uint32_t K = (total + 31) >> 5;
-                const uint32_t my0 = min(lane * K, total), my1 = min(my0 + K, total);
+                const uint32_t K = c->plan_K;
                 const uint32_t cpl_dith = chincpl & c->dithflag;
                 const uint32_t ncpl_dith = __popc(cpl_dith);
                 const int nseg = c->nseg;
-                int seg0 = 0;
-                for (int k = 1; k < nseg; k++)
-                    if (my0 >= c->seg[k].first) seg0 = k;
-                // cursor at my first bin: idx addresses exp[] (and bap[] = exp[] + 7*256)
-                uint32_t cur_idx, cur_left, cur_slot, cur_zmode;
+                // my run: n mantissas of segment sgi starting at offset o
+                uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
                 {
-                    const Segment sg = c->seg[seg0];
-                    const uint32_t o = my0 - sg.first;
-                    cur_idx = sg.arr * 256 + sg.start + o;
-                    cur_slot = sg.plane * 256 + sg.start + o;
-                    cur_left = sg.count - o;
-                    cur_zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : sg.dith;
-                }
-                // pass 1: class counts of my run (lock step: every lane does K iterations)
-                uint32_t cnt = 0, fz = 0, nz = 0;
-                {
-                    uint32_t idx = cur_idx, left = cur_left, zinc = (cur_zmode == 2) ? ncpl_dith : cur_zmode;
-                    int sgi = seg0;
-                    for (uint32_t k = my0; k < my1; k++) {
-                        const uint32_t b = G.bap[idx];
-                        const uint2 l = T.cnt_lut[b];
-                        cnt += l.x;
-                        fz += l.y;                                // plain field bits | zero count << 16
-                        idx++;
-                        if (--left == 0) {
-                            nz += (fz >> 16) * zinc;
-                            fz &= 0xffff;
-                            if (++sgi < nseg) {
-                                const Segment sg = c->seg[sgi];
-                                idx = sg.arr * 256 + sg.start;
-                                left = sg.count;
-                                zinc = (sg.arr == 6) ? ncpl_dith : sg.dith;
-                            }
-                        }
+                    int sgi = -1;
+                    for (int k = 0; k < nseg; k++)
+                        if (lane >= c->plan_lane0[k] && lane < c->plan_lane0[k + 1]) sgi = k;
+                    if (sgi >= 0) {
+                        const Segment sg = c->seg[sgi];
+                        const uint32_t o = (lane - c->plan_lane0[sgi]) * K;
+                        run_idx = sg.arr * 256 + sg.start + o;       // addresses exp[] (and bap[] = exp[] + 7*256)
+                        run_slot = sg.plane * 256 + sg.start + o;
+                        run_n = min(K, (uint32_t)sg.count - o);
+                        zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : sg.dith;
                     }
-                    nz += (fz >> 16) * zinc;
-                    fz &= 0xffff;
                 }
-                const uint32_t fixed = fz;
+                // pass 1: class counts of my run (lock step; bins past my run read the all-zero LUT row)
+                uint32_t cnt = 0, fz = 0;
+                const uint32_t cnt_lut_addr = tab_base + (uint32_t)offsetof(Tables, cnt_lut);
+                for (uint32_t k = 0; k < K; k++) {
+                    const uint32_t b = (k < run_n) ? (uint32_t)G.bap[run_idx + k] : 16u;
+                    const uint2 l = lds_v2(cnt_lut_addr + b * 8);
+                    cnt += l.x;
+                    fz += l.y;                                        // plain field bits | zero count << 16
+                }
+                const uint32_t fixed = fz & 0xffff;
+                const uint32_t nz = (fz >> 16) * (zmode == 2 ? ncpl_dith : zmode);
                 const uint32_t n1 = cnt & 0xff, n2 = (cnt >> 8) & 0xff, n4 = (cnt >> 16) & 0xff, np = cnt >> 24;
                 const uint32_t pa = n1 | (n2 << 16), pb = n4 | (np << 16);
                 const uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
@@ -1277,57 +1320,49 @@ a52_decode_kernel(const DecodeParams P)
                 // list layout: [class 1 | class 2 | class 4 | plain | dithered zeros]
                 const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
 
-                // pass 2: descriptors + work lists.  Branch-free for coded mantissas: the class of a
-                // bap selects, through emit_lut, which packed list cursor / phase counter moves.
+                // pass 2: descriptors + work lists, branch-free: the class of a bap selects, through
+                // emit_lut, which list cursor moves and whether the mantissa starts a new field.
                 {
                     uint32_t pos = min(bitpos + ibits - mybits, limit);
                     const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
-                    uint32_t run = 0;                              // list entries emitted so far, a byte per class
-                    uint32_t ph = p1 | (p2 << 2) | (p4 << 4);      // group phases, 2 bits per class (+ dummy)
-                    uint32_t bz = LZ + ez;
-                    uint32_t idx = cur_idx, left = cur_left, slot = cur_slot, zmode = cur_zmode;
-                    int sgi = seg0;
-                    for (uint32_t k = my0; k < my1; k++) {
-                        const uint32_t b = G.bap[idx], e = G.exp[idx];
-                        if (b == 0) {
-                            if (zmode == 1) {
-                                G.list[bz++] = (uint16_t)slot;
-                                planeU[slot] = e;
-                            } else if (zmode == 2) {
-                                // one dither value per coupled channel, channel order (parse.c:466-481)
-                                uint32_t m = cpl_dith;
-                                while (m) {
-                                    const uint32_t ch = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const uint32_t s2 = ch * 256 + (slot & 255);
-                                    G.list[bz++] = (uint16_t)s2;
-                                    planeU[s2] = e;
-                                }
+                    const uint32_t base_z = LZ + ez;
+                    const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);   // group phase at my first mantissa
+                    uint32_t run_a = 0, run_z = 0;                         // entries emitted so far, a byte per class
+                    const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
+                    const uint32_t zrow = (zmode == 1) ? 16u : 0u;
+                    for (uint32_t k = 0; k < K; k++) {
+                        const bool valid = k < run_n;
+                        const uint32_t b = G.bap[run_idx + k], e = G.exp[run_idx + k], slot = run_slot + k;
+                        if (zmode == 2 && b == 0 && valid) {
+                            // one dither value per coupled channel, channel order (parse.c:466-481)
+                            uint32_t m = cpl_dith;
+                            while (m) {
+                                const uint32_t ch = __ffs(m) - 1;
+                                m &= m - 1;
+                                const uint32_t s2 = ch * 256 + (slot & 255);
+                                G.list[base_z + run_z] = (uint16_t)s2;
+                                run_z++;
+                                planeU[s2] = e;
                             }
                         } else {
-                            const uint4 L = T.emit_lut[b];
-                            // L.x: cursor increment, L.y: byte selectors (base | count << 16),
-                            // L.z: phase shift | period << 8, L.w: field width
-                            const uint32_t li = (__byte_perm(base_lo, base_hi, L.y) +
-                                                 __byte_perm(run, 0, L.y >> 16)) & 0xffff;
-                            run += L.x;
-                            const uint32_t psh = L.z & 0xff, per = L.z >> 8;
-                            const uint32_t f = (ph >> psh) & 3;
-                            uint32_t nf = f + 1;
-                            nf = (nf == per) ? 0 : nf;
-                            ph ^= (f ^ nf) << psh;
-                            G.list[li] = (uint16_t)slot;
-                            planeU[slot] = make_desc(e, b, pos);
-                            pos = min(pos + (f == 0 ? L.w : 0u), limit);
-                        }
-                        idx++;
-                        slot++;
-                        if (--left == 0 && ++sgi < nseg) {
-                            const Segment sg = c->seg[sgi];
-                            idx = sg.arr * 256 + sg.start;
-                            slot = sg.plane * 256 + sg.start;
-                            left = sg.count;
-                            zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : sg.dith;
+                            // bins past my run take the row of an undithered zero: nothing moves
+                            const uint4 L = lds_v4(lut_addr + (valid ? (b + zrow) : 0u) * 16);
+                            // x: cursor increment (classes 1, 2, 4, plain); y: base selector A | width << 16 |
+                            // emit << 24; z: base selector B | 256/period << 16; w: count selector |
+                            // period << 16 | zero-list increment << 24
+                            const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
+                            const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
+                            // starts a field / group code when (phase0 + occurrences so far) % period == 0
+                            const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
+                            const uint32_t per = prmt(L.w, 0, 0x4442);
+                            const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
+                            run_a += L.x;
+                            run_z += L.w >> 24;
+                            if (L.y & 0x1000000u) {
+                                G.list[li] = (uint16_t)slot;
+                                planeU[slot] = make_desc(e, b, pos);
+                            }
+                            pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
                         }
                     }
                 }

@@ -242,14 +242,30 @@ static void build_tables(Tables* T)
         else if (b != 0) { x = 1u << 24; y = ac3_bap_bits[b]; }
         else y = 1u << 16;
         T->cnt_lut[b] = make_uint2(x, y);
-        // emit: class 0 = 3-level, 1 = 5-level, 2 = 11-level, 3 = everything else that carries bits
-        int cls = b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3;
-        uint32_t selbase = cls == 0 ? 0x4410u : cls == 1 ? 0x4432u : cls == 2 ? 0x4454u : 0x4476u;
-        uint32_t selcnt = 0x4440u | (uint32_t)cls;      // run byte `cls`, zero-extended (b operand is 0)
-        uint32_t per = cls < 2 ? 3 : cls == 2 ? 2 : 1;  // period 1: every plain mantissa starts a field
-        uint32_t width = cls < 1 ? 5 : cls <= 2 ? 7 : ac3_bap_bits[b];
-        T->emit_lut[b] = make_uint4(1u << (8 * cls), selbase | (selcnt << 16), (uint32_t)(2 * cls) | (per << 8), width);
     }
+    // emit_lut: how pass 2 of the locate stage treats a mantissa of a given bap.
+    //   classes: 0 = 3-level groups, 1 = 5-level, 2 = 11-level, 3 = plain fields, 4 = dithered zero
+    //   x: increment of the packed per-class counters (bytes 0..3 = classes 0..3)
+    //   y: [15:0] byte selector picking the class's 16-bit list base out of (base_lo, base_hi),
+    //      [23:16] bits taken when the mantissa starts a field / group, [24] emit list entry + descriptor
+    //   z: [15:0] byte selector keeping that base or replacing it by base_z, [31:16] 256 / period
+    //   w: [15:0] byte selector picking the class's counter out of (run_a, run_z) (also used on the
+    //      packed phases, where the zero class reads 0), [23:16] period, [31:24] increment of run_z
+    for (int z = 0; z < 2; z++)
+        for (int b = 0; b < 16; b++) {
+            int cls = b == 0 ? 4 : b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3;
+            uint32_t emit = (b != 0 || z) ? 1 : 0;
+            uint32_t per = cls < 2 ? 3 : cls == 2 ? 2 : 1;
+            uint32_t recip = cls < 2 ? 86 : cls == 2 ? 128 : 256;     // (x * recip) >> 8 == x / period, x < 128
+            uint32_t width = cls == 0 ? 5 : cls <= 2 ? 7 : cls == 3 ? ac3_bap_bits[b] : 0;
+            static const uint32_t selA[5] = {0x4410, 0x4432, 0x4454, 0x4476, 0x4410};
+            uint32_t selB = cls == 4 ? 0x7654 : 0x7610;               // bytes 6, 7 of base_z are zero
+            uint32_t selC = cls == 4 ? 0x7774 : (0x7770u | (uint32_t)cls);   // bytes 5..7 of run_z are zero
+            uint32_t x = cls < 4 ? (1u << (8 * cls)) : 0;
+            uint32_t incz = (cls == 4 && z) ? 1 : 0;
+            T->emit_lut[z * 16 + b] = make_uint4(x, selA[cls] | (width << 16) | (emit << 24),
+                                                 selB | (recip << 16), selC | (per << 16) | (incz << 24));
+        }
 }
 
 static int nout_of_flags(int flags)
