@@ -700,50 +700,89 @@ __device__ __forceinline__ int lowcomp_step(int a, int b0, int b1, int band)
     return a;
 }
 
-__device__ void bit_allocate_warp(const Tables& T, const GroupCtl* c, int arr, const uint8_t* exp,
-                                  uint8_t* bap, int16_t* bndpsd, int16_t* mask, int lane)
+__device__ __forceinline__ void alloc_range(const GroupCtl* c, int a, int& start, int& end)
 {
-    int start = 0, end;
-    int fastleak = 0, slowleak = 0;
-    const bool is_lfe = (arr == 5);
-    if (arr == 6) {
-        start = c->cplstrtmant; end = c->cplendmant;
-        fastleak = (c->cplfleak << 8) + 768;
-        slowleak = (c->cplsleak << 8) + 768;
-    } else if (arr == 5) {
-        end = 7;
-    } else {
-        end = c->endmant[arr];
-    }
-    const int bai = c->bai, chbai = c->chbai[arr], half = c->halfrate;
-    const int sdecay = (0x0f + 2 * (bai >> 9)) >> half;
-    const int fdecay = (0x3f + 0x14 * ((bai >> 7) & 3)) >> half;
-    const int sgain = c_sgain[(bai >> 5) & 3];
-    const int dbknee = c_dbknee[(bai >> 3) & 3];
-    const int floorv = c_floor[bai & 7];
-    const int fgain = 0x80 * ((chbai & 7) + 1);
-    const int snroffset = (((c->csnroffst - 15) << 4) + (chbai >> 3)) << 2;
-    const int deltbae = c->deltbae[arr];
-    const int bndstrt = T.masktab[start];
-    const int bndend = T.masktab[end - 1] + 1;
+    start = 0;
+    if (a == 6) { start = c->cplstrtmant; end = c->cplendmant; }
+    else if (a == 5) end = 7;
+    else end = c->endmant[a];
+}
 
-    // 1. band PSD integration (log-addition is not associative: serial inside a band)
-    for (int band = bndstrt + lane; band < bndend; band += 32) {
-        int b0 = max((int)T.bndtab[band], start);
-        int b1 = min((int)T.bndtab[band + 1], end);
-        int v = 3072 - (exp[b0] << 7);
-        for (int bin = b0 + 1; bin < b1; bin++) {
-            int p = 3072 - (exp[bin] << 7);
-            int d = v - p;
-            int adr = min(abs(d) >> 1, 255);
-            v = max(v, p) + T.latab[adr];
+// Bit allocation of every array flagged in `todo` (bit a: 0..4 fbw, 5 lfe, 6 coupling), one warp.
+//   1. band PSD        lanes = (array, band); bands of equal width together so that the serial
+//                      log-add inside a band runs in lock step
+//   2. excitation      lanes = arrays; the leak recurrences are serial over bands
+//   3. masking curve   lanes = (array, band)
+//   4. bap lookup      lanes = bins
+// psd / mask scratch: int16 [7][50] each.
+__device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t todo, const uint8_t* exp_all,
+                                   uint8_t* bap_all, int16_t* psd_all, int16_t* mask_all, int lane)
+{
+    // compact list of the arrays to do, 3 bits each
+    uint32_t act = 0;
+    int na = 0;
+    for (uint32_t m = todo; m; m &= m - 1) act |= (uint32_t)(__ffs(m) - 1) << (3 * na++);
+    const int half = c->halfrate;
+
+    // ---- 1a. single-bin bands (0..27) ----
+    for (int t = lane; t < na * 28; t += 32) {
+        const int j = t / 28, band = t - j * 28;
+        const int a = (act >> (3 * j)) & 7;
+        int start, end;
+        alloc_range(c, a, start, end);
+        if (band >= start && band < end) psd_all[a * 50 + band] = (int16_t)(3072 - (exp_all[a * 256 + band] << 7));
+    }
+    // ---- 1b. integrated bands: width 3 (28..34), 6 (35..40), 12 (41..44), 24 (45..49) ----
+#pragma unroll 1
+    for (int cls = 0; cls < 4; cls++) {
+        const int fb = (cls == 0) ? 28 : (cls == 1) ? 35 : (cls == 2) ? 41 : 45;
+        const int nb = (cls == 0) ? 7 : (cls == 1) ? 6 : (cls == 2) ? 4 : 5;
+        for (int t0 = 0; t0 < na * nb; t0 += 32) {
+            const int t = t0 + lane;
+            int b0 = 0, b1 = 0, a = 0, band = 0;
+            if (t < na * nb) {
+                const int j = t / nb;
+                band = fb + (t - j * nb);
+                a = (act >> (3 * j)) & 7;
+                int start, end;
+                alloc_range(c, a, start, end);
+                b0 = max((int)T.bndtab[band], start);
+                b1 = min((int)T.bndtab[band + 1], end);
+            }
+            if (b0 < b1) {
+                const uint8_t* e = exp_all + a * 256;
+                int v = 3072 - (e[b0] << 7);
+                for (int bin = b0 + 1; bin < b1; bin++) {
+                    const int p = 3072 - (e[bin] << 7);
+                    const int adr = min(abs(v - p) >> 1, 255);
+                    v = max(v, p) + T.latab[adr];
+                }
+                psd_all[a * 50 + band] = (int16_t)v;
+            }
         }
-        bndpsd[band] = (int16_t)v;
     }
     __syncwarp();
 
-    // 2. excitation (serial recurrences; one lane), result left in mask[]
-    if (lane == 0) {
+    // ---- 2. excitation (serial recurrences), result left in mask[] ----
+    if (lane < na) {
+        const int a = (act >> (3 * lane)) & 7;
+        const int16_t* bndpsd = psd_all + a * 50;
+        int16_t* mask = mask_all + a * 50;
+        int start, end;
+        alloc_range(c, a, start, end);
+        const bool is_lfe = (a == 5);
+        int fastleak = 0, slowleak = 0;
+        if (a == 6) {
+            fastleak = (c->cplfleak << 8) + 768;
+            slowleak = (c->cplsleak << 8) + 768;
+        }
+        const int bai = c->bai, chbai = c->chbai[a];
+        const int sdecay = (0x0f + 2 * (bai >> 9)) >> half;
+        const int fdecay = (0x3f + 0x14 * ((bai >> 7) & 3)) >> half;
+        const int sgain = c_sgain[(bai >> 5) & 3];
+        const int fgain = 0x80 * ((chbai & 7) + 1);
+        const int bndstrt = T.masktab[start];
+        const int bndend = T.masktab[end - 1] + 1;
         int band, begin, lowcomp = 0;
         if (bndstrt == 0) {
             lowcomp = lowcomp_step(lowcomp, bndpsd[0], bndpsd[1], 0);
@@ -779,25 +818,49 @@ __device__ void bit_allocate_warp(const Tables& T, const GroupCtl* c, int arr, c
     }
     __syncwarp();
 
-    // 3. masking curve, delta, snr offset (per band)
-    for (int band = bndstrt + lane; band < bndend; band += 32) {
-        int v = mask[band];
-        int p = bndpsd[band];
-        if (p < dbknee) v += (dbknee - p) >> 2;
-        v = max(v, (int)T.hth[c->fscod * 50 + (band >> half)]);
-        if (deltbae == 0 || deltbae == 1) v += c->deltba[arr][band] * 128;
-        v -= snroffset + floorv;
-        v = max(v, 0) & 0x1fe0;
-        mask[band] = (int16_t)(v + floorv);
+    // ---- 3. masking curve, delta, snr offset (per band) ----
+    {
+        const int bai = c->bai;
+        const int dbknee = c_dbknee[(bai >> 3) & 3];
+        const int floorv = c_floor[bai & 7];
+        const int csnr = c->csnroffst;
+        const uint16_t* hth = T.hth + c->fscod * 50;
+        for (int t = lane; t < na * 50; t += 32) {
+            const int j = t / 50, band = t - j * 50;
+            const int a = (act >> (3 * j)) & 7;
+            int start, end;
+            alloc_range(c, a, start, end);
+            const int bndstrt = T.masktab[start];
+            const int bndend = T.masktab[end - 1] + 1;
+            if (band < bndstrt || band >= bndend) continue;
+            const int snroffset = (((csnr - 15) << 4) + (c->chbai[a] >> 3)) << 2;
+            const int deltbae = c->deltbae[a];
+            int v = mask_all[a * 50 + band];
+            const int p = psd_all[a * 50 + band];
+            if (p < dbknee) v += (dbknee - p) >> 2;
+            v = max(v, (int)hth[band >> half]);
+            if (deltbae == 0 || deltbae == 1) v += c->deltba[a][band] * 128;
+            v -= snroffset + floorv;
+            v = max(v, 0) & 0x1fe0;
+            mask_all[a * 50 + band] = (int16_t)(v + floorv);
+        }
     }
     __syncwarp();
 
-    // 4. pointer lookup per bin
-    for (int bin = start + lane; bin < end; bin += 32) {
-        int p = 3072 - (exp[bin] << 7);
-        int a = (p - mask[T.masktab[bin]]) >> 5;
-        a = min(max(a, 0), 63);
-        bap[bin] = T.baptab[a];
+    // ---- 4. pointer lookup per bin ----
+    for (int j = 0; j < na; j++) {
+        const int a = (act >> (3 * j)) & 7;
+        int start, end;
+        alloc_range(c, a, start, end);
+        const uint8_t* e = exp_all + a * 256;
+        const int16_t* mask = mask_all + a * 50;
+        uint8_t* bap = bap_all + a * 256;
+        for (int bin = start + lane; bin < end; bin += 32) {
+            const int p = 3072 - (e[bin] << 7);
+            int q = (p - mask[T.masktab[bin]]) >> 5;
+            q = min(max(q, 0), 63);
+            bap[bin] = T.baptab[q];
+        }
     }
 }
 
@@ -1253,16 +1316,16 @@ a52_decode_kernel(const DecodeParams P)
 
                 // ================= B: bit allocation =================
                 if (c->do_alloc) {
-                    for (int a = 0; a < 7; a++) {
-                        if (!((c->do_alloc >> a) & 1)) continue;
-                        uint8_t* bp = G.bap + a * 256;
-                        if (c->zero_alloc) {
-                            for (int i = lane; i < 64; i += 32) reinterpret_cast<uint32_t*>(bp)[i] = 0;
-                        } else {
-                            bit_allocate_warp(T, c, a, G.exp + a * 256, bp, G.band, G.band + 50, lane);
-                        }
-                        __syncwarp();
+                    if (c->zero_alloc) {
+                        for (int a = 0; a < 7; a++)
+                            if ((c->do_alloc >> a) & 1)
+                                for (int i = lane; i < 64; i += 32) reinterpret_cast<uint32_t*>(G.bap + a * 256)[i] = 0;
+                    } else {
+                        // psd / mask scratch lives in the work-list area (not in use before the locate stage)
+                        int16_t* scratch = reinterpret_cast<int16_t*>(G.list);
+                        bit_allocate_block(T, c, c->do_alloc, G.exp, G.bap, scratch, scratch + 7 * 50, lane);
                     }
+                    __syncwarp();
                 }
 
                 // ================= L: locate =================
