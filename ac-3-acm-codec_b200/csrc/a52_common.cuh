@@ -11,7 +11,7 @@
 
 namespace a52 {
 
-constexpr int kMaxWarpsPerCta = 14;  // one warp walks one stream; a CTA is just a bag of warps
+constexpr int kMaxWarpsPerCta = 16;  // one warp walks one stream; a CTA is just a bag of warps
 constexpr int kDitherPeriod = 65535;
 
 // output mode ids == liba52's A52_* flag values (include/a52.h)
@@ -86,6 +86,7 @@ struct DecodeParams {
     int*            work_counter;
     int             fbuf_bytes;      // bytes of the staged-frame buffer (multiple of 16)
     int             warp_bytes;      // shared-memory bytes per warp
+    int             nplanes;         // coefficient planes per warp: 5, or 6 when the LFE is requested
     // optional dumps
     uint8_t*        dbg_exp;
     uint8_t*        dbg_bap;

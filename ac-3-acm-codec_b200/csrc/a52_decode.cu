@@ -109,15 +109,16 @@ struct __align__(16) GroupCtl {
     uint16_t plan_K;           // run length per lane
     float    wt[5][5];         // mix matrix [output][coded channel] in {-1, 0, +1} (downmix.c:480-619)
     int      identity_mix;     // output channel o is exactly coded channel o
+    uint8_t  gains_dirty;      // dynrng / frame parameters changed since compute_gains()
+    uint8_t  segs_dirty;       // coded ranges changed since the segment table was built
 };
 
 struct WarpPtrs {
     GroupCtl* ctl;
     uint8_t*  exp;     // [7][256]
     uint8_t*  bap;     // [7][256]  standard numbering 0..15
-    int16_t*  band;    // [2][50] bit-allocation scratch
     uint16_t* list;    // [kListEntries] per-class work lists of plane slots
-    float*    plane;   // [6][256]
+    float*    plane;   // [nplanes][256]: 5 fbw planes (+ the LFE plane when it is an output)
     uint32_t* fbuf;    // staged frame (native-endian 32-bit words after the swap pass)
     uint64_t* mbar;
 };
@@ -126,28 +127,26 @@ constexpr int kListEntries = 1504;   // >= 5*253 + 216 + 7 mantissa slots per bl
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline int warp_smem_bytes(int fbuf_bytes)
+__host__ __device__ inline int warp_smem_bytes(int fbuf_bytes, int nplanes)
 {
     int n = 0;
     n += align16((int)sizeof(GroupCtl));
     n += 7 * 256 * 2;
-    n += align16(2 * 50 * 2);
     n += align16(kListEntries * 2);
-    n += 6 * 256 * 4;
+    n += nplanes * 256 * 4;
     n += fbuf_bytes;
     n += 16;
     return n;
 }
 
-__device__ inline WarpPtrs carve(uint8_t* base, int fbuf_bytes)
+__device__ inline WarpPtrs carve(uint8_t* base, int fbuf_bytes, int nplanes)
 {
     WarpPtrs g;
     g.ctl = reinterpret_cast<GroupCtl*>(base);  base += align16((int)sizeof(GroupCtl));
     g.exp = base;                               base += 7 * 256;
     g.bap = base;                               base += 7 * 256;
-    g.band = reinterpret_cast<int16_t*>(base);  base += align16(2 * 50 * 2);
     g.list = reinterpret_cast<uint16_t*>(base); base += align16(kListEntries * 2);
-    g.plane = reinterpret_cast<float*>(base);   base += 6 * 256 * 4;
+    g.plane = reinterpret_cast<float*>(base);   base += nplanes * 256 * 4;
     g.fbuf = reinterpret_cast<uint32_t*>(base); base += fbuf_bytes;
     g.mbar = reinterpret_cast<uint64_t*>(base);
     return g;
@@ -299,6 +298,19 @@ __device__ int parse_frame_header(GroupCtl* c, const uint32_t* w, uint32_t base_
     c->nout = c_mix[acmod * 11 + me.output].nout;
     c->level = me.level * 2.0f;                                // parse.c:169
     c->dynrng = c->level;
+    c->gains_dirty = 1;
+    c->segs_dirty = 1;
+    // mix matrix as float weights (so that the mixers are plain multiply-adds); fixed for the frame
+    {
+        const MixEntry mx = c_mix[acmod * 11 + me.output];
+        for (int o = 0; o < 5; o++)
+            for (int ch = 0; ch < 5; ch++)
+                c->wt[o][ch] = ((mx.pos[o] >> ch) & 1) ? 1.f : ((mx.neg[o] >> ch) & 1) ? -1.f : 0.f;
+        int ident = (mx.nout == c->nfchans);
+        for (int o = 0; o < mx.nout && ident; o++)
+            if (mx.pos[o] != (1u << o) || mx.neg[o]) ident = 0;
+        c->identity_mix = ident;
+    }
     // delta bit allocation is reset per frame for cpl + fbw (parse.c:173-175)
     c->deltbae[6] = 2;
     for (int i = 0; i < 5; i++) c->deltbae[i] = 2;
@@ -384,11 +396,10 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     const int acmod = c->acmod;
 
     uint32_t v = br.get(2 * nfchans);          // blksw[nfchans], dithflag[nfchans]
-    uint32_t blksw = 0, dith = 0;
-    for (int i = 0; i < nfchans; i++) {
-        blksw |= ((v >> (2 * nfchans - 1 - i)) & 1) << i;
-        dith  |= ((v >> (nfchans - 1 - i)) & 1) << i;
-    }
+    // the fields are sent channel 0 first (msb): bit-reverse them so that bit i = channel i
+    const uint32_t chmask = (1u << nfchans) - 1;
+    const uint32_t blksw = __brev(v >> nfchans) >> (32 - nfchans);
+    const uint32_t dith = __brev(v & chmask) >> (32 - nfchans);
     c->blksw = blksw;
     c->dithflag = dith;
 
@@ -399,15 +410,16 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             if (!P.drc_off) {
                 float range = (float)(((d & 0x1f) | 0x20) << 13) * pow2neg(15 + 3 - (d >> 5));
                 c->dynrng = c->level * range;
+                c->gains_dirty = 1;
             }
         }
     }
 
     if (br.get(1)) {                           // cplstre (parse.c:600-634)
         c->chincpl = 0;
+        c->segs_dirty = 1;
         if (br.get(1)) {
-            uint32_t m = br.get(nfchans), chincpl = 0;
-            for (int i = 0; i < nfchans; i++) chincpl |= ((m >> (nfchans - 1 - i)) & 1) << i;
+            const uint32_t chincpl = __brev(br.get(nfchans)) >> (32 - nfchans);
             c->chincpl = chincpl;
             if (acmod < 2) return 1;
             if (acmod == 2) c->phsflginu = br.get(1);
@@ -456,7 +468,11 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     // exponent strategies (parse.c:680-701)
     uint8_t expstr[7] = {0, 0, 0, 0, 0, 0, 0};
     if (chincpl) expstr[6] = br.get(2);
-    for (int i = 0; i < nfchans; i++) expstr[i] = br.get(2);
+    {
+        const uint32_t ev = br.get(2 * nfchans);
+        for (int i = 0; i < nfchans; i++) expstr[i] = (ev >> (2 * (nfchans - 1 - i))) & 3;
+        if (ev) c->segs_dirty = 1;              // a channel's coded range may change with new exponents
+    }
     if (c->lfeon) expstr[5] = br.get(1);
     for (int i = 0; i < nfchans; i++)
         if (expstr[i]) {
@@ -560,14 +576,19 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     }
     c->bitpos = br.pos;
 
-    compute_gains(c);
+    if (c->gains_dirty) {
+        compute_gains(c);
+        c->gains_dirty = 0;
+    }
+    if (c->segs_dirty) {
+    c->segs_dirty = 0;
 
     // coded order of the mantissas (parse.c:816-835, 867-879)
     int ns = 0, done_cpl = 0;
     uint32_t flat = 0;
     for (int i = 0; i < nfchans; i++) {
         Segment s;
-        s.arr = i; s.plane = i; s.start = 0; s.dith = (dith >> i) & 1;
+        s.arr = i; s.plane = i; s.start = 0; s.dith = 0;
         s.count = c->endmant[i]; s.first = flat;
         c->seg[ns++] = s;
         flat += s.count;
@@ -613,6 +634,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             c->plan_K = K;
         }
     }
+    }
 
     // transform path (parse.c:881-886): mix coefficients first unless block
     // switch flags differ between channels that get mixed
@@ -625,17 +647,6 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     }
     c->uniform_path = uniform;
 
-    // mix matrix as float weights (so that the mixers are plain multiply-adds)
-    {
-        const MixEntry mx = c_mix[acmod * 11 + (c->output & M_MASK)];
-        for (int o = 0; o < 5; o++)
-            for (int ch = 0; ch < 5; ch++)
-                c->wt[o][ch] = ((mx.pos[o] >> ch) & 1) ? 1.f : ((mx.neg[o] >> ch) & 1) ? -1.f : 0.f;
-        int ident = (mx.nout == nfchans);
-        for (int o = 0; o < mx.nout && ident; o++)
-            if (mx.pos[o] != (1u << o) || mx.neg[o]) ident = 0;
-        c->identity_mix = ident;
-    }
     return 0;
 }
 
@@ -885,9 +896,12 @@ __device__ __forceinline__ uint32_t field_at(const uint32_t* w, uint32_t pos, ui
 
 // dither generator (parse.c:310-319) advanced 32 steps: the step is linear over GF(2), so
 // state * x^256 = J_hi[state >> 8] ^ J_lo[state & 255]
-__device__ __forceinline__ uint32_t lfsr_jump32(const Tables& T, uint32_t s)
+__device__ __forceinline__ uint32_t lfsr_jump32(uint32_t tab_base, uint32_t s)
 {
-    return (uint32_t)T.jump_hi[s >> 8] ^ (uint32_t)T.jump_lo[s & 255];
+    uint32_t hi, lo;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(tab_base + (uint32_t)offsetof(Tables, jump_hi) + (s >> 8) * 2));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(tab_base + (uint32_t)offsetof(Tables, jump_lo) + (s & 255) * 2));
+    return hi ^ lo;
 }
 
 // ---------------------------------------------------------------------------
@@ -1175,6 +1189,8 @@ __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const Wa
     tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
 }
 
+static_assert(sizeof(GroupCtl) <= 1200, "GroupCtl grew: check the shared-memory budget per warp");
+
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
 a52_decode_kernel(const DecodeParams P)
 {
@@ -1189,7 +1205,7 @@ a52_decode_kernel(const DecodeParams P)
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
         for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    WarpPtrs G = carve(smem + align16((int)sizeof(Tables)) + warp * P.warp_bytes, P.fbuf_bytes);
+    WarpPtrs G = carve(smem + align16((int)sizeof(Tables)) + warp * P.warp_bytes, P.fbuf_bytes, P.nplanes);
     GroupCtl* c = G.ctl;
     uint32_t* const W = G.fbuf;
     uint32_t* const planeU = reinterpret_cast<uint32_t*>(G.plane);
@@ -1330,7 +1346,7 @@ a52_decode_kernel(const DecodeParams P)
 
                 // ================= L: locate =================
                 // planes start as zeros: bins past the coded range and undithered bap-0 bins stay zero
-                for (int i = lane; i < 6 * 256 / 4; i += 32)
+                for (int i = lane; i < P.nplanes * 256 / 4; i += 32)
                     reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
                 const uint32_t K = c->plan_K;
                 const uint32_t cpl_dith = chincpl & c->dithflag;
@@ -1338,6 +1354,7 @@ a52_decode_kernel(const DecodeParams P)
                 const int nseg = c->nseg;
                 // my run: n mantissas of segment sgi starting at offset o
                 uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
+                bool mute = false;          // LFE mantissas when the LFE is not an output: skipped, not stored
                 {
                     int sgi = -1;
                     for (int k = 0; k < nseg; k++)
@@ -1348,12 +1365,14 @@ a52_decode_kernel(const DecodeParams P)
                         run_idx = sg.arr * 256 + sg.start + o;       // addresses exp[] (and bap[] = exp[] + 7*256)
                         run_slot = sg.plane * 256 + sg.start + o;
                         run_n = min(K, (uint32_t)sg.count - o);
-                        zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : sg.dith;
+                        zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : ((c->dithflag >> sg.arr) & 1u);
+                        mute = (sg.arr == 5) && !c->out_lfe;
                     }
                 }
                 // pass 1: class counts of my run (lock step; bins past my run read the all-zero LUT row)
                 uint32_t cnt = 0, fz = 0;
                 const uint32_t cnt_lut_addr = tab_base + (uint32_t)offsetof(Tables, cnt_lut);
+#pragma unroll 4
                 for (uint32_t k = 0; k < K; k++) {
                     const uint32_t b = (k < run_n) ? (uint32_t)G.bap[run_idx + k] : 16u;
                     const uint2 l = lds_v2(cnt_lut_addr + b * 8);
@@ -1363,7 +1382,9 @@ a52_decode_kernel(const DecodeParams P)
                 const uint32_t fixed = fz & 0xffff;
                 const uint32_t nz = (fz >> 16) * (zmode == 2 ? ncpl_dith : zmode);
                 const uint32_t n1 = cnt & 0xff, n2 = (cnt >> 8) & 0xff, n4 = (cnt >> 16) & 0xff, np = cnt >> 24;
-                const uint32_t pa = n1 | (n2 << 16), pb = n4 | (np << 16);
+                // (the LFE comes last in coded order, so leaving a muted run out of the list cursors
+                // only shortens the lists)
+                const uint32_t pa = mute ? 0u : (n1 | (n2 << 16)), pb = mute ? 0u : (n4 | (np << 16));
                 const uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
                 const uint32_t iz = warp_incl_scan(nz, lane);
                 const uint32_t ta = __shfl_sync(0xffffffffu, ia, 31), tb = __shfl_sync(0xffffffffu, ib, 31);
@@ -1393,9 +1414,17 @@ a52_decode_kernel(const DecodeParams P)
                     uint32_t run_a = 0, run_z = 0;                         // entries emitted so far, a byte per class
                     const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
                     const uint32_t zrow = (zmode == 1) ? 16u : 0u;
+                    const uint32_t emit_bit = mute ? 0u : 0x1000000u;
+                    // software pipeline: the bap / exponent bytes of mantissa k+1 and its LUT row are
+                    // fetched before the stores of mantissa k (the compiler cannot hoist them itself:
+                    // byte loads may alias the list / descriptor stores)
+                    uint32_t b = G.bap[run_idx], e = G.exp[run_idx];
+                    uint4 L = lds_v4(lut_addr + (run_n ? (b + zrow) : 0u) * 16);
                     for (uint32_t k = 0; k < K; k++) {
                         const bool valid = k < run_n;
-                        const uint32_t b = G.bap[run_idx + k], e = G.exp[run_idx + k], slot = run_slot + k;
+                        const uint32_t slot = run_slot + k;
+                        const uint32_t bn = G.bap[run_idx + k + 1], en = G.exp[run_idx + k + 1];
+                        const uint4 Ln = lds_v4(lut_addr + ((k + 1 < run_n) ? (bn + zrow) : 0u) * 16);
                         if (zmode == 2 && b == 0 && valid) {
                             // one dither value per coupled channel, channel order (parse.c:466-481)
                             uint32_t m = cpl_dith;
@@ -1409,7 +1438,6 @@ a52_decode_kernel(const DecodeParams P)
                             }
                         } else {
                             // bins past my run take the row of an undithered zero: nothing moves
-                            const uint4 L = lds_v4(lut_addr + (valid ? (b + zrow) : 0u) * 16);
                             // x: cursor increment (classes 1, 2, 4, plain); y: base selector A | width << 16 |
                             // emit << 24; z: base selector B | 256/period << 16; w: count selector |
                             // period << 16 | zero-list increment << 24
@@ -1421,12 +1449,15 @@ a52_decode_kernel(const DecodeParams P)
                             const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
                             run_a += L.x;
                             run_z += L.w >> 24;
-                            if (L.y & 0x1000000u) {
+                            if (L.y & emit_bit) {
                                 G.list[li] = (uint16_t)slot;
                                 planeU[slot] = make_desc(e, b, pos);
                             }
                             pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
                         }
+                        b = bn;
+                        e = en;
+                        L = Ln;
                     }
                 }
                 __syncwarp();
@@ -1445,7 +1476,7 @@ a52_decode_kernel(const DecodeParams P)
                             G.plane[slot] = (float)dv * pow2neg(15 + e);
                         }
                         ring_prev = ring;
-                        ring = lfsr_jump32(T, ring);
+                        ring = lfsr_jump32(tab_base, ring);
                     }
                     const uint32_t back = (32 - (tz & 31)) & 31;
                     const uint32_t a = __shfl_sync(0xffffffffu, ring, (lane - back) & 31);

@@ -461,7 +461,8 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     if (max_frame_bytes < 128) max_frame_bytes = 128;
     if (max_frame_bytes > 3840) max_frame_bytes = 3840;
     P.fbuf_bytes = align16(max_frame_bytes + 15) + 16 + 16;
-    P.warp_bytes = warp_smem_bytes(P.fbuf_bytes);
+    P.nplanes = (P.req_flags & M_LFE) ? 6 : 5;
+    P.warp_bytes = warp_smem_bytes(P.fbuf_bytes, P.nplanes);
     P.dither_seq = ctx->d_dither;
     P.work_counter = ctx->d_counter;
     const int tables = align16((int)sizeof(Tables));
