@@ -304,7 +304,9 @@ struct a52_batch_s {
     int warps_per_cta = 0;         // 0 = as many as fit
     int max_frame_hint = 0;
     uint16_t* d_dither = nullptr;
-    int* d_counter = nullptr;      // [0] work counter, [1] max frame length
+    int* d_counter = nullptr;      // [0..31] work counters (one per pipelined chunk), [63] max frame length
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_run = nullptr;   // host-mode pipeline: H2D, D2H, kernels
+    cudaEvent_t ev_in[32] = {nullptr}, ev_run[32] = {nullptr};
     char err[256] = {0};
     long launches = 0;
     // timing
@@ -373,7 +375,7 @@ a52_batch_t* a52_batch_create(int device)
     }
     ok = ok && cudaMalloc(&ctx->d_dither, seq.size() * 2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_counter, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024) == cudaSuccess;
     if (!ok) {
@@ -394,6 +396,13 @@ void a52_batch_destroy(a52_batch_t* ctx)
         if (b->p) cudaFree(b->p);
     if (ctx->d_dither) cudaFree(ctx->d_dither);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->s_run) cudaStreamDestroy(ctx->s_run);
+    for (int i = 0; i < 32; i++) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_run[i]) cudaEventDestroy(ctx->ev_run[i]);
+    }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
@@ -445,7 +454,7 @@ double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
 }
 
 static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int max_frame_bytes,
-                         float level, cudaStream_t st)
+                         float level, cudaStream_t st, int counter_slot = 0)
 {
     using namespace a52;
     // per-request constants
@@ -464,7 +473,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.nplanes = (P.req_flags & M_LFE) ? 6 : 5;
     P.warp_bytes = warp_smem_bytes(P.fbuf_bytes, P.nplanes);
     P.dither_seq = ctx->d_dither;
-    P.work_counter = ctx->d_counter;
+    P.work_counter = ctx->d_counter + counter_slot;
     const int tables = align16((int)sizeof(Tables));
     int fit = (227 * 1024 - tables) / P.warp_bytes;
     if (fit > kMaxWarpsPerCta) fit = kMaxWarpsPerCta;
@@ -482,7 +491,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     int grid = (P.nstreams + G - 1) / G;
     if (grid > ctx->num_sms) grid = ctx->num_sms;
     if (grid < 1) grid = 1;
-    A52_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+    A52_CUDA(cudaMemsetAsync(ctx->d_counter + counter_slot, 0, sizeof(int), st));
     // timing events
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
         if (ctx->ev_pool.size() < 8192) {
@@ -550,16 +559,29 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         if (debug) { P.dbg_exp = debug->exp; P.dbg_bap = debug->bap; P.dbg_coef = debug->coef; P.dbg_info = debug->info; }
         int maxlen = ctx->max_frame_hint;
         if (maxlen <= 0) {
-            A52_CUDA(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(int), st));
-            a52_maxlen_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(es, frame_off, nframes, ctx->d_counter + 1);
-            A52_CUDA(cudaMemcpyAsync(&maxlen, ctx->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaMemsetAsync(ctx->d_counter + 63, 0, sizeof(int), st));
+            a52_maxlen_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(es, frame_off, nframes, ctx->d_counter + 63);
+            A52_CUDA(cudaMemcpyAsync(&maxlen, ctx->d_counter + 63, sizeof(int), cudaMemcpyDeviceToHost, st));
             A52_CUDA(cudaStreamSynchronize(st));
             ctx->launches++;
         }
         return launch_decode(ctx, P, nframes, maxlen, level, st);
     }
 
-    // ---- host pointers: stage in, decode, stage out (synchronous) ----
+    // ---- host pointers: stage in, decode, stage out (synchronous for the caller) ----
+    // Large batches are cut into chunks of streams that flow through three CUDA streams:
+    // bitstream H2D | decode kernel | PCM D2H, so that with pinned host buffers the PCIe copies
+    // overlap each other and the kernels.  (Pageable buffers work too, without the overlap.)
+    if (!ctx->s_in) {
+        A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking));
+        for (int i = 0; i < 32; i++) {
+            A52_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            A52_CUDA(cudaEventCreateWithFlags(&ctx->ev_run[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t s_in = ctx->s_in, s_out = ctx->s_out, s_run = st ? st : ctx->s_run;
     int maxlen = 0;
     for (int i = 0; i < nframes; i++) {
         int fl, sr, br;
@@ -568,28 +590,25 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             if (len > maxlen) maxlen = len;
         }
     }
-    if (ensure(ctx, ctx->b_es, es_bytes + 32)) return -1;
+    if (ensure(ctx, ctx->b_es, es_bytes + 64)) return -1;
     if (ensure(ctx, ctx->b_off, (size_t)(nframes + 1) * 8)) return -1;
     if (ensure(ctx, ctx->b_first, (size_t)(nstreams + 1) * 4)) return -1;
     if (ensure(ctx, ctx->b_pcm, stride * nframes)) return -1;
     if (ensure(ctx, ctx->b_status, (size_t)nframes * 4)) return -1;
     if (ensure(ctx, ctx->b_flags, (size_t)nframes * 4)) return -1;
-    A52_CUDA(cudaMemcpyAsync(ctx->b_es.p, es, es_bytes, cudaMemcpyHostToDevice, st));
-    A52_CUDA(cudaMemsetAsync((uint8_t*)ctx->b_es.p + es_bytes, 0, 32, st));
+    A52_CUDA(cudaMemsetAsync((uint8_t*)ctx->b_es.p + es_bytes, 0, 64, s_run));
     std::vector<uint64_t> off(frame_off, frame_off + nframes);
     off.push_back(es_bytes);
-    A52_CUDA(cudaMemcpyAsync(ctx->b_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
-    A52_CUDA(cudaMemcpyAsync(ctx->b_first.p, stream_first, (size_t)(nstreams + 1) * 4, cudaMemcpyHostToDevice, st));
+    A52_CUDA(cudaMemcpyAsync(ctx->b_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s_run));
+    A52_CUDA(cudaMemcpyAsync(ctx->b_first.p, stream_first, (size_t)(nstreams + 1) * 4, cudaMemcpyHostToDevice, s_run));
     P.es = (const uint8_t*)ctx->b_es.p;
     P.frame_off = (const uint64_t*)ctx->b_off.p;
-    P.stream_first = (const uint32_t*)ctx->b_first.p;
     P.pcm = (uint8_t*)ctx->b_pcm.p;
     P.status = (int32_t*)ctx->b_status.p;
     P.frame_flags = (int32_t*)ctx->b_flags.p;
     if (carry) {
         if (ensure(ctx, ctx->b_carry, sizeof(StreamCarry) * (size_t)nstreams)) return -1;
-        A52_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, st));
-        P.carry = (StreamCarry*)ctx->b_carry.p;
+        A52_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, s_run));
     }
     const size_t nblk = (size_t)nframes * 6;
     if (debug) {
@@ -597,37 +616,90 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             if (ensure(ctx, ctx->b_dexp, nblk * 7 * 256) || ensure(ctx, ctx->b_dbap, nblk * 7 * 256)) return -1;
             P.dbg_exp = (uint8_t*)ctx->b_dexp.p;
             P.dbg_bap = (uint8_t*)ctx->b_dbap.p;
-            A52_CUDA(cudaMemsetAsync(P.dbg_exp, 0, nblk * 7 * 256, st));
-            A52_CUDA(cudaMemsetAsync(P.dbg_bap, 0, nblk * 7 * 256, st));
+            A52_CUDA(cudaMemsetAsync(P.dbg_exp, 0, nblk * 7 * 256, s_run));
+            A52_CUDA(cudaMemsetAsync(P.dbg_bap, 0, nblk * 7 * 256, s_run));
         }
         if (debug->coef) {
             if (ensure(ctx, ctx->b_dcoef, nblk * 6 * 256 * 4)) return -1;
             P.dbg_coef = (float*)ctx->b_dcoef.p;
-            A52_CUDA(cudaMemsetAsync(P.dbg_coef, 0, nblk * 6 * 256 * 4, st));
+            A52_CUDA(cudaMemsetAsync(P.dbg_coef, 0, nblk * 6 * 256 * 4, s_run));
         }
         if (debug->info) {
             if (ensure(ctx, ctx->b_dinfo, nblk * 16 * 4)) return -1;
             P.dbg_info = (int32_t*)ctx->b_dinfo.p;
-            A52_CUDA(cudaMemsetAsync(P.dbg_info, 0, nblk * 16 * 4, st));
+            A52_CUDA(cudaMemsetAsync(P.dbg_info, 0, nblk * 16 * 4, s_run));
         }
     }
-    // the staging copies above read pageable host vectors: finish them before they go away
-    A52_CUDA(cudaStreamSynchronize(st));
-    int rc = launch_decode(ctx, P, nframes, maxlen, level, st);
-    if (rc) return rc;
-    A52_CUDA(cudaMemcpyAsync(pcm_out, P.pcm, stride * nframes, cudaMemcpyDeviceToHost, st));
-    if (frame_status) A52_CUDA(cudaMemcpyAsync(frame_status, P.status, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
-    if (frame_flags) A52_CUDA(cudaMemcpyAsync(frame_flags, P.frame_flags, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
-    if (carry) A52_CUDA(cudaMemcpyAsync(carry, P.carry, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, st));
+    // the small staging copies above read pageable host vectors: finish them before they go away
+    A52_CUDA(cudaStreamSynchronize(s_run));
+
+    // chunk plan: contiguous stream ranges; each chunk's bitstream is the byte span of its frames
+    int nchunks = nstreams / 256;
+    if (nchunks > 32) nchunks = 32;
+    if (nchunks < 1) nchunks = 1;
+    std::vector<size_t> cb0(nchunks), cb1(nchunks);
+    size_t span_total = 0;
+    for (int cidx = 0; cidx < nchunks; cidx++) {
+        int s0 = (int)((long long)cidx * nstreams / nchunks), s1 = (int)((long long)(cidx + 1) * nstreams / nchunks);
+        size_t lo = es_bytes, hi = 0;
+        for (uint32_t f = stream_first[s0]; f < stream_first[s1]; f++) {
+            size_t a = (size_t)frame_off[f];
+            size_t b = a + (size_t)maxlen;
+            if (a < lo) lo = a;
+            if (b > hi) hi = b;
+        }
+        if (hi > es_bytes) hi = es_bytes;
+        if (lo > hi) lo = hi;
+        cb0[cidx] = lo & ~(size_t)15;
+        cb1[cidx] = hi;
+        span_total += cb1[cidx] - cb0[cidx];
+    }
+    const bool slice_input = span_total <= es_bytes + es_bytes / 2 + 4096;
+    if (!slice_input) {
+        // frames of different chunks interleave in memory: one copy of everything
+        A52_CUDA(cudaMemcpyAsync(ctx->b_es.p, es, es_bytes, cudaMemcpyHostToDevice, s_in));
+        A52_CUDA(cudaEventRecord(ctx->ev_in[0], s_in));
+    }
+    for (int cidx = 0; cidx < nchunks; cidx++) {
+        int s0 = (int)((long long)cidx * nstreams / nchunks), s1 = (int)((long long)(cidx + 1) * nstreams / nchunks);
+        uint32_t fa = stream_first[s0], fb = stream_first[s1];
+        if (s1 == s0) continue;
+        if (slice_input) {
+            if (cb1[cidx] > cb0[cidx])
+                A52_CUDA(cudaMemcpyAsync((uint8_t*)ctx->b_es.p + cb0[cidx], es + cb0[cidx], cb1[cidx] - cb0[cidx],
+                                         cudaMemcpyHostToDevice, s_in));
+            A52_CUDA(cudaEventRecord(ctx->ev_in[cidx], s_in));
+            A52_CUDA(cudaStreamWaitEvent(s_run, ctx->ev_in[cidx], 0));
+        } else if (cidx == 0) {
+            A52_CUDA(cudaStreamWaitEvent(s_run, ctx->ev_in[0], 0));
+        }
+        DecodeParams Pc = P;
+        Pc.stream_first = (const uint32_t*)ctx->b_first.p + s0;
+        Pc.nstreams = s1 - s0;
+        Pc.carry = carry ? (StreamCarry*)ctx->b_carry.p + s0 : nullptr;
+        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_run, cidx);
+        if (rc) return rc;
+        A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_run));
+        A52_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_run[cidx], 0));
+        if (fb > fa)
+            A52_CUDA(cudaMemcpyAsync((uint8_t*)pcm_out + (size_t)fa * stride, Pc.pcm + (size_t)fa * stride,
+                                     (size_t)(fb - fa) * stride, cudaMemcpyDeviceToHost, s_out));
+    }
+    A52_CUDA(cudaStreamSynchronize(s_run));
+    if (frame_status) A52_CUDA(cudaMemcpyAsync(frame_status, P.status, (size_t)nframes * 4, cudaMemcpyDeviceToHost, s_run));
+    if (frame_flags) A52_CUDA(cudaMemcpyAsync(frame_flags, P.frame_flags, (size_t)nframes * 4, cudaMemcpyDeviceToHost, s_run));
+    if (carry) A52_CUDA(cudaMemcpyAsync(carry, ctx->b_carry.p, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, s_run));
     if (debug) {
         if (P.dbg_exp) {
-            A52_CUDA(cudaMemcpyAsync(debug->exp, P.dbg_exp, nblk * 7 * 256, cudaMemcpyDeviceToHost, st));
-            A52_CUDA(cudaMemcpyAsync(debug->bap, P.dbg_bap, nblk * 7 * 256, cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaMemcpyAsync(debug->exp, P.dbg_exp, nblk * 7 * 256, cudaMemcpyDeviceToHost, s_run));
+            A52_CUDA(cudaMemcpyAsync(debug->bap, P.dbg_bap, nblk * 7 * 256, cudaMemcpyDeviceToHost, s_run));
         }
-        if (P.dbg_coef) A52_CUDA(cudaMemcpyAsync(debug->coef, P.dbg_coef, nblk * 6 * 256 * 4, cudaMemcpyDeviceToHost, st));
-        if (P.dbg_info) A52_CUDA(cudaMemcpyAsync(debug->info, P.dbg_info, nblk * 16 * 4, cudaMemcpyDeviceToHost, st));
+        if (P.dbg_coef) A52_CUDA(cudaMemcpyAsync(debug->coef, P.dbg_coef, nblk * 6 * 256 * 4, cudaMemcpyDeviceToHost, s_run));
+        if (P.dbg_info) A52_CUDA(cudaMemcpyAsync(debug->info, P.dbg_info, nblk * 16 * 4, cudaMemcpyDeviceToHost, s_run));
     }
-    A52_CUDA(cudaStreamSynchronize(st));
+    A52_CUDA(cudaStreamSynchronize(s_run));
+    A52_CUDA(cudaStreamSynchronize(s_out));
+    A52_CUDA(cudaStreamSynchronize(s_in));
     return 0;
 }
 
