@@ -66,6 +66,9 @@ REF_API void ref_ac3enc_get (int what, void * dst)
     case 3: memcpy (dst, encoded_exp, sizeof (encoded_exp)); break;   /* u8 [6][6][256] */
     case 4: memcpy (dst, bap, sizeof (bap)); break;                   /* u8 [6][6][256] */
     case 5: memcpy (dst, exp_samples, sizeof (exp_samples)); break;   /* s8 [6][6] */
+    case 7: memcpy (dst, ac3_window, sizeof (ac3_window)); break;       /* s16 [256] */
+    case 8: { short * q = (short *) dst; memcpy (q, costab, 128); memcpy (q + 64, sintab, 128);
+	      memcpy (q + 128, xcos1, 256); memcpy (q + 256, xsin1, 256); } break;
     case 6: { int * p = (int *) dst; p[0] = ac3enc_state.csnroffst;
 	      p[1] = ac3enc_state.fsnroffst[0]; p[2] = ac3enc_state.frame_size; } break;
     }

@@ -344,3 +344,60 @@ class Oracle:
         dl = np.ascontiguousarray(delay, dtype=np.float32).copy()
         self.lib.ora_imdct(kind, _ptr(d, _fp), _ptr(dl, _fp), bias)
         return d, dl
+
+
+class OracleEnc:
+    """Our CPU restatement of the encoder (oracle/ac3enc_oracle.c), same call shapes as RefAc3Enc."""
+
+    SHAPES = {0: ((6, 6, 256), np.int32), 1: ((6, 6, 256), np.uint8), 2: ((6, 6), np.uint8),
+              3: ((6, 6, 256), np.uint8), 4: ((6, 6, 256), np.uint8), 5: ((6, 6), np.int8), 6: ((4,), np.int32)}
+
+    def __init__(self, path=None):
+        path = path or os.path.join(ORACLE, "liboracle.so")
+        self.lib = L = C.CDLL(path)
+        L.ora_enc_init.restype = C.c_void_p
+        L.ora_enc_init.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ora_enc_free.argtypes = [C.c_void_p]
+        L.ora_enc_frame_bytes.argtypes = [C.c_void_p]
+        L.ora_enc_frame.argtypes = [C.c_void_p, _u8p, C.POINTER(C.c_short), _u8p]
+        L.ora_enc_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ora_enc_window.restype = C.POINTER(C.c_int16)
+        L.ora_enc_window.argtypes = [C.c_void_p]
+        L.ora_enc_stream.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_short), C.c_int, _u8p, _u8p]
+        self.st = None
+
+    def encode_stream(self, pcm, freq, bitrate, chmap=None):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        nch = pcm.shape[1]
+        nframes = pcm.shape[0] // 1536
+        out = np.zeros(nframes * 3840 + 64, np.uint8)
+        cm = np.ascontiguousarray(chmap, dtype=np.uint8) if chmap is not None else None
+        fb = self.lib.ora_enc_stream(freq, bitrate, nch, pcm.ctypes.data_as(C.POINTER(C.c_short)), nframes,
+                                     _ptr(cm, _u8p) if cm is not None else None, _ptr(out, _u8p))
+        if fb <= 0:
+            raise ValueError("encoder rejected config")
+        return fb, out[: nframes * fb].copy()
+
+    def init(self, freq, bitrate, channels):
+        if self.st:
+            self.lib.ora_enc_free(self.st)
+        self.st = self.lib.ora_enc_init(freq, bitrate, channels)
+        return self.lib.ora_enc_frame_bytes(self.st) if self.st else 0
+
+    def frame(self, samples, chmap=None):
+        samples = np.ascontiguousarray(samples, dtype=np.int16)
+        out = np.zeros(3840 + 64, np.uint8)
+        cm = np.ascontiguousarray(chmap, dtype=np.uint8) if chmap is not None else None
+        n = self.lib.ora_enc_frame(self.st, _ptr(out, _u8p), samples.ctypes.data_as(C.POINTER(C.c_short)),
+                                   _ptr(cm, _u8p) if cm is not None else None)
+        return out[:n].copy()
+
+    def get(self, what):
+        sh, dt = self.SHAPES[what]
+        a = np.zeros(sh, dt)
+        self.lib.ora_enc_get(self.st, what, a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def window(self):
+        st = self.st or self.lib.ora_enc_init(48000, 192000, 2)
+        return np.ctypeslib.as_array(self.lib.ora_enc_window(st), shape=(256,)).copy()
