@@ -28,6 +28,9 @@ EXPORTS = [
     "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index",
     "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes",
     "a52_batch_launch_count", "a52_batch_kernel_ms",
+    "AC3_encode_init", "AC3_encode_frame",
+    "ac3_batch_create", "ac3_batch_destroy", "ac3_batch_last_error", "ac3_batch_frame_bytes",
+    "ac3_batch_encode", "ac3_batch_launch_count", "ac3_batch_kernel_ms",
 ]
 
 
@@ -82,6 +85,21 @@ def load_library():
     L.a52_dynrng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.a52_block.argtypes = [C.c_void_p]
     L.a52_free.argtypes = [C.c_void_p]
+    # encoder
+    L.AC3_encode_init.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.AC3_encode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ac3_batch_create.restype = C.c_void_p
+    L.ac3_batch_create.argtypes = [C.c_int]
+    L.ac3_batch_destroy.argtypes = [C.c_void_p]
+    L.ac3_batch_last_error.restype = C.c_char_p
+    L.ac3_batch_last_error.argtypes = [C.c_void_p]
+    L.ac3_batch_frame_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ac3_batch_launch_count.restype = C.c_long
+    L.ac3_batch_launch_count.argtypes = [C.c_void_p]
+    L.ac3_batch_kernel_ms.restype = C.c_double
+    L.ac3_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.ac3_batch_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -196,3 +214,93 @@ class BatchDecoder:
 
     def frame_stride(self, req_flags, out_fmt):
         return self.L.a52_batch_frame_stride(req_flags, out_fmt)
+
+
+class EncCarryStruct(C.Structure):
+    _fields_ = [("last_samples", (C.c_int16 * 256) * 6), ("csnroffst", C.c_int32), ("started", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+class EncDebugStruct(C.Structure):
+    _fields_ = [("coef", C.c_void_p), ("exp_shift", C.c_void_p), ("strategy", C.c_void_p),
+                ("encoded_exp", C.c_void_p), ("bap", C.c_void_p), ("snr", C.c_void_p)]
+
+
+class BatchEncoder:
+    """Batched encoder context bound to one GPU (ac3_batch_t, include/ac3enc_batch.h)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = self.L.ac3_batch_create(device)
+        if not self.ctx:
+            raise RuntimeError("ac3_batch_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
+
+    def close(self):
+        if self.ctx:
+            self.L.ac3_batch_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def frame_bytes(self, freq, bitrate, channels):
+        return self.L.ac3_batch_frame_bytes(freq, bitrate, channels)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("ac3_batch_encode failed (%d): %s" % (rc, self.L.ac3_batch_last_error(self.ctx).decode()))
+
+    def encode_host(self, pcm, freq, bitrate, chmap=None, carry=None, want_debug=False):
+        """pcm: int16 [nstreams, nframes * 1536, channels].  Returns dict(frames [nstreams, nframes, fb], status...)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        ns, nsamp, nch = pcm.shape
+        nfr = nsamp // 1536
+        pcm = np.ascontiguousarray(pcm[:, : nfr * 1536])
+        fb = self.frame_bytes(freq, bitrate, nch)
+        if fb <= 0:
+            raise ValueError("encoder rejected config")
+        out = np.zeros((ns, nfr, fb), np.uint8)
+        status = np.zeros((ns, nfr), np.int32)
+        cm = np.ascontiguousarray(chmap, dtype=np.uint8) if chmap is not None else None
+        cbuf = None
+        if carry is not None:
+            cbuf = (EncCarryStruct * ns)()
+            for i, c in enumerate(carry):
+                if c is not None:
+                    C.memmove(C.byref(cbuf[i]), C.byref(c), C.sizeof(EncCarryStruct))
+        res = {}
+        dbg = None
+        if want_debug:
+            res["coef"] = np.zeros((ns, nfr, 6, 6, 256), np.int32)
+            res["exp_shift"] = np.zeros((ns, nfr, 6, 6), np.int8)
+            res["strategy"] = np.zeros((ns, nfr, 6, 6), np.uint8)
+            res["encoded_exp"] = np.zeros((ns, nfr, 6, 6, 256), np.uint8)
+            res["bap"] = np.zeros((ns, nfr, 6, 6, 256), np.uint8)
+            res["snr"] = np.zeros((ns, nfr, 2), np.int32)
+            dbg = EncDebugStruct(*[res[k].ctypes.data for k in ("coef", "exp_shift", "strategy", "encoded_exp", "bap", "snr")])
+        rc = self.L.ac3_batch_encode(self.ctx, pcm.ctypes.data, ns, nfr, freq, bitrate, nch,
+                                     cm.ctypes.data if cm is not None else None, out.ctypes.data, status.ctypes.data,
+                                     C.byref(cbuf) if cbuf is not None else None,
+                                     C.byref(dbg) if dbg is not None else None, 0, None)
+        self._check(rc)
+        res.update(frames=out, status=status, carry=cbuf, frame_bytes=fb)
+        return res
+
+    def encode_device(self, pcm_ptr, nstreams, nframes, freq, bitrate, channels, out_ptr, status_ptr=0, carry_ptr=0,
+                      chmap=None, stream=0):
+        cm = np.ascontiguousarray(chmap, dtype=np.uint8) if chmap is not None else None
+        rc = self.L.ac3_batch_encode(self.ctx, pcm_ptr, nstreams, nframes, freq, bitrate, channels,
+                                     cm.ctypes.data if cm is not None else None, out_ptr, status_ptr or None,
+                                     carry_ptr or None, None, DEVICE_PTRS, stream or None)
+        self._check(rc)
+
+    def launch_count(self):
+        return self.L.ac3_batch_launch_count(self.ctx)
+
+    def kernel_ms(self):
+        n = C.c_int(0)
+        ms = self.L.ac3_batch_kernel_ms(self.ctx, C.byref(n))
+        return ms, n.value

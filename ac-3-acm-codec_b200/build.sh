@@ -6,4 +6,4 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared \
     -Xptxas -v -Xlinker --version-script="$here/csrc/exports.map" \
-    -o "$here/liba52_b200.so" "$here/csrc/a52_decode.cu" -lcudart "$@"
+    -o "$here/liba52_b200.so" "$here/csrc/a52_decode.cu" "$here/csrc/ac3_encode.cu" -lcudart "$@"

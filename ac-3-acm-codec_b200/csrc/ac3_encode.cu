@@ -1,0 +1,871 @@
+// ac3_encode.cu - batched AC-3 encode for NVIDIA B200 (sm_100a).
+//
+// Bit-exact re-implementation of the reference's integer encoder
+// (reference: src/ac3enc/ac3enc.cpp:1640-1763) as one persistent kernel.  A CTA of
+// six warps owns one PCM stream at a time and walks its frames in order (the
+// reference carries the previous 256 samples per channel and the warm start of the
+// SNR-offset search across frames, ac3enc.cpp:55, 921, 969); warp w is coded channel w
+// for everything that is per channel.  Everything between the PCM load and the frame
+// store lives in shared memory:
+//
+//   E1  window, block-floating normalisation, 512-point fixed-point MDCT (128-point
+//       radix-2 FFT, 16-bit storage, halving butterflies), exponents   (:1673-1722, 485-603)
+//   E2  exponent strategy, run minima, group minima, +-2 delta constraint as two
+//       min-plus warp scans                                            (:617-761, 1725-1749)
+//   E3  masking curve once per exponent set, then the SNR-offset search on per-set
+//       class counts (a probe = bap lookup + ballots, no re-derivation of the curve)
+//                                                                      (:220-421, 764-975)
+//   E4  side information, grouped exponents, quantisation, group codes by shared-memory
+//       atomics, bit packing by absolute bit position, both CRCs by a warp-parallel
+//       chunked CRC                                                    (:1113-1638)
+//
+// Frames are byte-identical to the reference's (tests/test_encoder_gpu.py).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "ac3_tables.h"
+#include "../../include/ac3enc.h"
+#include "../../include/ac3enc_batch.h"
+
+namespace ac3e {
+
+constexpr int kWarps = 6;
+constexpr int kThreads = kWarps * 32;
+constexpr int kFrameWords = 968;         // staged output frame, 32-bit words (3840 bytes max + slack)
+constexpr int kCodes = 1320;             // group codes per block: 3- and 5-level <= 375 each, 11-level <= 562
+
+struct EncTables {
+    int16_t  window[256];
+    int16_t  costab[64], sintab[64], xcos1[128], xsin1[128];
+    uint16_t crc_table[256];
+    uint16_t hth[150];
+    uint8_t  rev[128];
+    uint8_t  masktab[256];
+    uint8_t  latab[256];
+    uint8_t  baptab[64];
+    uint8_t  bndtab[52];
+    uint8_t  plain_bits[16];             // field width of the ungrouped baps, 0 for bap 0, 1, 2, 4
+    uint8_t  width[16];                  // field / group-code width per bap
+    uint8_t  pad_[8];
+};
+
+__device__ EncTables g_enc_tables;
+
+struct EncCarry {                        // == ac3_stream_carry_t
+    int16_t last_samples[6][256];
+    int32_t csnroffst;
+    int32_t started;
+    int32_t reserved[2];
+};
+
+struct EncParams {
+    const int16_t* pcm;
+    uint8_t*  out;
+    int32_t*  status;
+    EncCarry* carry;
+    int*      work_counter;
+    int nstreams, nframes;
+    int nch_all, nch, lfe, acmod, fscod, halfrate, bsid, frmsizecod, frame_words;
+    uint32_t crc_inv;                    // x^-(16 fs58 - 16) mod poly (ac3enc.cpp:1627)
+    uint8_t chmap[8];
+    // optional dumps
+    int32_t* dbg_coef;
+    int8_t*  dbg_shift;
+    uint8_t* dbg_strategy;
+    uint8_t* dbg_enc;
+    uint8_t* dbg_bap;
+    int32_t* dbg_snr;
+};
+
+struct EncShared {
+    int32_t  coef[6][6][256];            // MDCT coefficients; a (block, channel) slot first holds its 512 input samples
+    uint8_t  expo[6][6][256];            // raw exponents, later the baps
+    uint8_t  enc[6][6][256];             // exponents as the decoder will see them (run heads)
+    int16_t  last[6][256];               // previous 256 samples per coded channel
+    union {
+        // E1..E3: one block of interleaved input, FFT scratch, masking curves before the snr offset (run heads)
+        struct { int16_t pcmblk[256 * 6]; uint32_t z[6][128]; int16_t mask[6][6][50]; } e1;
+        // E4: the frame being packed, group-code accumulators and their bit positions
+        struct { uint32_t frame[kFrameWords]; uint32_t codes[kCodes]; uint16_t gpos[kCodes]; } e4;
+    } u;
+    int      cnt[6][6][4];               // per exponent set: 3-, 5-, 11-level mantissas, bits of plain fields
+    uint8_t  strategy[6][6];
+    uint8_t  head[6][6];                 // block holding the exponent set a (block, channel) uses
+    int8_t   exp_shift[6][6];
+    uint32_t exp_pos[6][6];              // bit position of a channel's exponent section in a block
+    uint32_t mant_pos[6];                // bit position of a block's first mantissa
+    int      exp_bits[6];                // per channel: bits of its exponent sections (ac3enc.cpp:760)
+    int      frame_bits;                 // everything but mantissas
+    int      probe_cs, probe_fs, phase, cs, fs, done, failed;
+    uint32_t crc[2];
+};
+
+__device__ __forceinline__ int ilog2(uint32_t v) { return v ? 31 - __clz(v) : 0; }
+
+__device__ __forceinline__ void put_bits_atomic(uint32_t* frame, uint32_t pos, uint32_t n, uint32_t v)
+{
+    // n in 1..16, v < 2^n; big-endian bit order: bit 0 of the frame = msb of word 0
+    if (pos + n > kFrameWords * 32) return;
+    uint32_t wi = pos >> 5, sh = pos & 31;
+    uint64_t x = (uint64_t)v << (64 - n - sh);
+    uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    if (hi) atomicOr(&frame[wi], hi);
+    if (lo) atomicOr(&frame[wi + 1], lo);
+}
+
+struct SerialBits {                      // single-thread bit cursor for the side information
+    uint32_t* frame;
+    uint32_t pos;
+    __device__ __forceinline__ void put(uint32_t n, uint32_t v) { put_bits_atomic(frame, pos, n, v); pos += n; }
+};
+
+__device__ __forceinline__ int sym_quant(int c, int e, int levels)      // ac3enc.cpp:1150-1166
+{
+    int v;
+    if (c >= 0) { v = (levels * (c << e)) >> 24; v = (v + 1) >> 1; v = (levels >> 1) + v; }
+    else { v = (levels * ((-c) << e)) >> 24; v = (v + 1) >> 1; v = (levels >> 1) - v; }
+    return v;
+}
+
+__device__ __forceinline__ int asym_quant(int c, int e, int qbits)       // ac3enc.cpp:1169-1190
+{
+    int lshift = e + qbits - 24, v;
+    v = lshift >= 0 ? c << lshift : c >> (-lshift);
+    v = (v + 1) >> 1;
+    int m = 1 << (qbits - 1);
+    if (v >= m) v = m - 1;
+    return v & ((1 << qbits) - 1);
+}
+
+__device__ __forceinline__ uint32_t mul_poly(uint32_t a, uint32_t b)      // ac3enc.cpp:1513-1524, poly 0x18005
+{
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (a & 1) c ^= b;
+        a >>= 1;
+        b <<= 1;
+        if (b & 0x10000) b ^= 0x18005;
+    }
+    return c;
+}
+
+// CRC-16 (poly 0x8005, init 0) of frame bytes [b0, b1) by one warp: every lane runs the table CRC over
+// an equal chunk (chunks are aligned to the END of the range: leading zero bytes do not change a
+// zero-initialised CRC), then the chunks are folded pairwise: crc(A|B) = crc(A) * x^(8 len B) ^ crc(B).
+__device__ uint32_t warp_crc(const EncTables& T, const uint32_t* frame, int b0, int b1, int lane)
+{
+    const int n = b1 - b0;
+    const int L = (n + 31) >> 5;
+    const int start = b1 - (32 - lane) * L;
+    uint32_t crc = 0;
+    for (int k = 0; k < L; k++) {
+        int idx = start + k;
+        uint32_t byte = (idx >= b0) ? ((frame[idx >> 2] >> (24 - 8 * (idx & 3))) & 0xff) : 0u;
+        crc = (T.crc_table[byte ^ (crc >> 8)] ^ (crc << 8)) & 0xffff;
+    }
+    // m = x^(8 L) mod poly: the register after shifting a one through L zero bytes
+    uint32_t m = 1;
+    for (int k = 0; k < L; k++) m = (T.crc_table[m >> 8] ^ (m << 8)) & 0xffff;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t right = __shfl_down_sync(0xffffffffu, crc, o);
+        if ((lane & (2 * o - 1)) == 0) crc = mul_poly(crc, m) ^ right;
+        m = mul_poly(m, m);
+    }
+    return __shfl_sync(0xffffffffu, crc, 0);
+}
+
+// ---------------------------------------------------------------------------
+// E1: one (block, channel): window, normalise, MDCT-512, exponents.  One warp.
+// ---------------------------------------------------------------------------
+__device__ void e1_transform(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane)
+{
+    int16_t* in = reinterpret_cast<int16_t*>(S.coef[blk][ch]);       // 512 samples live in the coefficient slot
+    uint32_t* z = S.u.e1.z[ch];
+    const int src = P.chmap[ch];
+    // previous 256 samples | new 256 samples, windowed (ac3enc.cpp:1673-1693)
+    uint32_t amax = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int j = lane + 32 * r;
+        const int old = S.last[ch][j];
+        const int cur = S.u.e1.pcmblk[j * P.nch_all + src];
+        S.last[ch][j] = (int16_t)cur;
+        const int a = (int16_t)((old * T.window[j]) >> 15);
+        const int b = (int16_t)((cur * T.window[255 - j]) >> 15);
+        in[j] = (int16_t)a;
+        in[256 + j] = (int16_t)b;
+        amax |= (uint32_t)abs(a) | (uint32_t)abs(b);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) amax |= __shfl_xor_sync(0xffffffffu, amax, o);
+    int sh = 14 - ilog2(amax);                                          // :1697-1700
+    if (sh < 0) sh = 0;
+    if (lane == 0) S.exp_shift[blk][ch] = (int8_t)(sh - 9);
+    __syncwarp();
+    // pre-rotation (:576-589) on the shifted samples; rot[k] = k < 128 ? -in[k + 384] : in[k - 128]
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = lane + 32 * r;
+        auto smp = [&](int k) -> int { return (int)(int16_t)(in[k] << sh); };
+        auto rot = [&](int k) -> int { return k < 128 ? (int)(int16_t)(-smp(k + 384)) : smp(k - 128); };
+        const int re = (rot(2 * i) - rot(511 - 2 * i)) >> 1;
+        const int im = -(rot(256 + 2 * i) - rot(255 - 2 * i)) >> 1;
+        const int bre = -T.xcos1[i], bim = T.xsin1[i];
+        const int xr = (re * bre - im * bim) >> 15, xi = (re * bim + bre * im) >> 15;
+        z[T.rev[i]] = ((uint32_t)(uint16_t)(int16_t)xr) | ((uint32_t)(uint16_t)(int16_t)xi << 16);
+    }
+    __syncwarp();
+    // 128-point FFT (:485-568), 7 halving radix-2 passes, two butterflies per lane and pass
+#pragma unroll 1
+    for (int st = 0; st < 7; st++) {
+        const int half = 1 << st;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int b = lane + 32 * r;
+            const int t = b & (half - 1);
+            const int i0 = ((b >> st) << (st + 1)) + t, i1 = i0 + half;
+            const uint32_t p = z[i0], q = z[i1];
+            const int bx = (int16_t)(p & 0xffff), by = (int16_t)(p >> 16);
+            const int qre = (int16_t)(q & 0xffff), qim = (int16_t)(q >> 16);
+            int ax, ay;
+            if (t == 0) { ax = qre; ay = qim; }
+            else if (st == 1) { ax = qim; ay = -qre; }
+            else {
+                const int l = t * (64 >> st);
+                const int c = T.costab[l], sn = -T.sintab[l];
+                ax = (c * qre - sn * qim) >> 15;
+                ay = (c * qim + qre * sn) >> 15;
+            }
+            z[i0] = ((uint32_t)(uint16_t)(int16_t)((bx + ax) >> 1)) | ((uint32_t)(uint16_t)(int16_t)((by + ay) >> 1) << 16);
+            z[i1] = ((uint32_t)(uint16_t)(int16_t)((bx - ax) >> 1)) | ((uint32_t)(uint16_t)(int16_t)((by - ay) >> 1) << 16);
+        }
+        __syncwarp();
+    }
+    // post-rotation (:594-602) into the coefficient slot (the samples are no longer needed)
+    int32_t* out = S.coef[blk][ch];
+    int o0[4], o1[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = lane + 32 * r;
+        const uint32_t p = z[i];
+        const int re = (int16_t)(p & 0xffff), im = (int16_t)(p >> 16);
+        o1[r] = (re * T.xsin1[i] - im * T.xcos1[i]) >> 15;               // re1 -> out[255 - 2i]
+        o0[r] = (re * T.xcos1[i] + T.xsin1[i] * im) >> 15;               // im1 -> out[2i]
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = lane + 32 * r;
+        out[2 * i] = o0[r];
+        out[255 - 2 * i] = o1[r];
+    }
+    __syncwarp();
+    // exponents (:1707-1722)
+    const int es = sh - 9;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int j = lane + 32 * r;
+        const int a = abs(out[j]);
+        int e = 24;
+        if (a) {
+            e = 23 - ilog2((uint32_t)a) + es;
+            if (e >= 24) { e = 24; out[j] = 0; }
+        }
+        S.expo[blk][ch][j] = (uint8_t)e;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// E2: strategies + exponent sets of one channel.  One warp.  Returns the exponent bits.
+// ---------------------------------------------------------------------------
+__device__ int e2_exponents(EncShared& S, const EncParams& P, int ch, int lane)
+{
+    const bool is_lfe = P.lfe && ch == 5;
+    const int ncoef = is_lfe ? 7 : 223;
+    // new exponents when the L1 distance to the previous block exceeds 1000 over all 256 bins (:617-640)
+    uint32_t newmask = 1;
+    for (int blk = 1; blk < 6; blk++) {
+        int d = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int j = lane + 32 * r;
+            d += abs((int)S.expo[blk][ch][j] - (int)S.expo[blk - 1][ch][j]);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (d > 1000) newmask |= 1u << blk;
+    }
+    int bits = 0;
+    for (int i = 0; i < 6;) {
+        int j = i + 1;
+        while (j < 6 && !((newmask >> j) & 1)) j++;
+        // run [i, j): strategy by run length (:645-668); the LFE only knows new / reuse
+        const int strat = is_lfe ? 1 : (j - i == 1) ? 3 : (j - i <= 3) ? 2 : 1;
+        if (lane == 0) {
+            S.strategy[i][ch] = (uint8_t)strat;
+            for (int k = i; k < j; k++) {
+                if (k > i) S.strategy[k][ch] = 0;
+                S.head[k][ch] = (uint8_t)i;
+            }
+        }
+        // minimum over the run (:1736-1739), coded bins only
+        for (int k = lane; k < ncoef; k += 32) {
+            int m = S.expo[i][ch][k];
+            for (int b = i + 1; b < j; b++) m = min(m, (int)S.expo[b][ch][k]);
+            S.expo[i][ch][k] = (uint8_t)m;
+        }
+        __syncwarp();
+        // group minima, dc <= 15 (:684-726); lane owns values 7 lane .. 7 lane + 6 of e1[0 .. ng]
+        const int gs = strat == 1 ? 1 : strat == 2 ? 2 : 4;
+        const int ng = ((ncoef + gs * 3 - 4) / (3 * gs)) * 3;
+        const uint8_t* ex = S.expo[i][ch];
+        int e1[7];
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const int g = 7 * lane + r;
+            int m = 64;
+            if (g == 0) m = min((int)ex[0], 15);
+            else if (g <= ng) {
+                const int k = 1 + (g - 1) * gs;
+                m = ex[k];
+                for (int q = 1; q < gs; q++) m = min(m, (int)ex[k + q]);
+            }
+            e1[r] = m;
+        }
+        // |delta| <= 2 (:732-748): largest sequence below e1 = forward then backward min-plus sweep
+        {
+            int run = 1 << 20;                                           // min over my values of e - 2 g
+#pragma unroll
+            for (int r = 0; r < 7; r++) run = min(run, e1[r] - 2 * (7 * lane + r));
+            int incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = min(incl, t);
+            }
+            int carry = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) carry = 1 << 20;
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                const int g = 7 * lane + r;
+                carry = min(carry, e1[r] - 2 * g);
+                e1[r] = carry + 2 * g;
+            }
+            run = 1 << 20;                                               // min over my values of e + 2 g
+#pragma unroll
+            for (int r = 0; r < 7; r++)
+                if (7 * lane + r <= ng) run = min(run, e1[r] + 2 * (7 * lane + r));
+            incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_down_sync(0xffffffffu, incl, o);
+                if (lane + o < 32) incl = min(incl, t);
+            }
+            carry = __shfl_down_sync(0xffffffffu, incl, 1);
+            if (lane == 31) carry = 1 << 20;
+#pragma unroll
+            for (int r = 6; r >= 0; r--) {
+                const int g = 7 * lane + r;
+                if (g <= ng) {
+                    carry = min(carry, e1[r] + 2 * g);
+                    e1[r] = carry - 2 * g;
+                }
+            }
+        }
+        // what the decoder will see (:750-758)
+        uint8_t* en = S.enc[i][ch];
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const int g = 7 * lane + r;
+            if (g == 0) en[0] = (uint8_t)e1[r];
+            else if (g <= ng) {
+                const int k = 1 + (g - 1) * gs;
+                for (int q = 0; q < gs; q++) en[k + q] = (uint8_t)e1[r];
+            }
+        }
+        bits += 4 + (ng / 3) * 7;
+        __syncwarp();
+        i = j;
+    }
+    return bits;
+}
+
+// ---------------------------------------------------------------------------
+// E3a: masking curve of one exponent set (everything of ac3enc.cpp:220-383 that does not
+// depend on the snr offset).  Encoder parameters are fixed (:861-869).  One warp.
+// ---------------------------------------------------------------------------
+__device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane, int16_t* psd)
+{
+    const bool is_lfe = P.lfe && ch == 5;
+    const int end = is_lfe ? 7 : 223;
+    const uint8_t* ex = S.enc[blk][ch];
+    const int sdecay = 0x13 >> P.halfrate, fdecay = 0x53 >> P.halfrate, sgain = 0x4d8, dbknee = 0x900, fgain = 0x280;
+    const int bndend = T.masktab[end - 1] + 1;
+    for (int band = lane; band < bndend; band += 32) {
+        const int b0 = T.bndtab[band], b1 = min((int)T.bndtab[band + 1], end);
+        int v = 3072 - (ex[b0] << 7);
+        for (int bin = b0 + 1; bin < b1; bin++) {
+            const int p = 3072 - (ex[bin] << 7);
+            const int adr = min(abs(v - p) >> 1, 255);
+            v = max(v, p) + T.latab[adr];
+        }
+        psd[band] = (int16_t)v;
+    }
+    __syncwarp();
+    int16_t* mk = S.u.e1.mask[blk][ch];
+    if (lane == 0) {
+        auto lc1 = [](int a, int b0, int b1) { return (b0 + 256 == b1) ? 384 : (b0 > b1) ? max(a - 64, 0) : a; };
+        int lowcomp = 0, fast = 0, slow = 0, begin = 7, bin;
+        lowcomp = lc1(lowcomp, psd[0], psd[1]);
+        mk[0] = (int16_t)(psd[0] - fgain - lowcomp);
+        lowcomp = lc1(lowcomp, psd[1], psd[2]);
+        mk[1] = (int16_t)(psd[1] - fgain - lowcomp);
+        for (bin = 2; bin < 7; bin++) {
+            const bool last_lfe = is_lfe && bin == 6;
+            if (!last_lfe) lowcomp = lc1(lowcomp, psd[bin], psd[bin + 1]);
+            fast = psd[bin] - fgain;
+            slow = psd[bin] - sgain;
+            mk[bin] = (int16_t)(fast - lowcomp);
+            if (!last_lfe && psd[bin] <= psd[bin + 1]) { begin = bin + 1; break; }
+        }
+        const int stop = min(bndend, 22);
+        for (bin = begin; bin < stop; bin++) {
+            if (!(is_lfe && bin == 6)) {
+                const int b0 = psd[bin], b1 = psd[bin + 1];
+                if (bin < 7) lowcomp = lc1(lowcomp, b0, b1);
+                else if (bin < 20) lowcomp = (b0 + 256 == b1) ? 320 : (b0 > b1) ? max(lowcomp - 64, 0) : lowcomp;
+                else lowcomp = max(lowcomp - 128, 0);
+            }
+            fast = max(fast - fdecay, psd[bin] - fgain);
+            slow = max(slow - sdecay, psd[bin] - sgain);
+            mk[bin] = (int16_t)max(fast - lowcomp, slow);
+        }
+        for (bin = 22; bin < bndend; bin++) {
+            fast = max(fast - fdecay, psd[bin] - fgain);
+            slow = max(slow - sdecay, psd[bin] - sgain);
+            mk[bin] = (int16_t)max(fast, slow);
+        }
+    }
+    __syncwarp();
+    for (int band = lane; band < bndend; band += 32) {
+        int v1 = mk[band];
+        const int tmp = dbknee - psd[band];
+        if (tmp > 0) v1 += tmp >> 2;
+        mk[band] = (int16_t)max(v1, (int)T.hth[P.fscod * 50 + (band >> P.halfrate)]);
+    }
+    __syncwarp();
+}
+
+// E3b: baps of one exponent set for an snr offset (:393-420) + class counts.  One warp.
+__device__ void e3_probe(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane,
+                         int snroffset, bool store)
+{
+    const bool is_lfe = P.lfe && ch == 5;
+    const int end = is_lfe ? 7 : 223;
+    const uint8_t* ex = S.enc[blk][ch];
+    const int16_t* mk = S.u.e1.mask[blk][ch];
+    uint8_t* bap = S.expo[blk][ch];                                      // raw exponents are dead: baps live there
+    int n1 = 0, n2 = 0, n4 = 0, fixed = 0;
+    for (int i0 = 0; i0 < end; i0 += 32) {
+        const int i = i0 + lane;
+        int b = 0;
+        if (i < end) {
+            int v = mk[T.masktab[i]] - snroffset - 0x1f0;
+            v = (max(v, 0) & 0x1fe0) + 0x1f0;
+            int a = ((3072 - (ex[i] << 7)) - v) >> 5;
+            a = min(max(a, 0), 63);
+            b = T.baptab[a];
+            if (store) bap[i] = (uint8_t)b;
+        }
+        n1 += __popc(__ballot_sync(0xffffffffu, b == 1));
+        n2 += __popc(__ballot_sync(0xffffffffu, b == 2));
+        n4 += __popc(__ballot_sync(0xffffffffu, b == 4));
+        fixed += T.plain_bits[b];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) fixed += __shfl_xor_sync(0xffffffffu, fixed, o);
+    if (lane == 0) {
+        S.cnt[blk][ch][0] = n1;
+        S.cnt[blk][ch][1] = n2;
+        S.cnt[blk][ch][2] = n4;
+        S.cnt[blk][ch][3] = fixed;
+    }
+}
+
+// bits left in the frame for the counts of the last probe (bit_alloc, :813-845)
+__device__ int bits_left(const EncShared& S, const EncParams& P)
+{
+    int used = S.frame_bits;
+    for (int blk = 0; blk < 6; blk++) {
+        int n1 = 0, n2 = 0, n4 = 0;
+        for (int ch = 0; ch < P.nch_all; ch++) {
+            const int* q = S.cnt[S.head[blk][ch]][ch];
+            n1 += q[0]; n2 += q[1]; n4 += q[2]; used += q[3];
+        }
+        used += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
+    }
+    return 16 * P.frame_words - used;
+}
+
+// The search of compute_bit_allocation (:921-967) as a state machine fed with one probe result
+// at a time.  phase 0: csnr down by 4 until it fits; 1: csnr up by 4; 2: csnr up by 1;
+// 3: fsnr up by 4; 4: fsnr up by 1; 5: done.
+__device__ void search_step(EncShared& S, int left)
+{
+    int ph = S.phase;
+    if (ph == 0) {
+        if (left >= 0) { S.cs = S.probe_cs; ph = 1; }
+        else {
+            S.probe_cs -= 4;
+            if (S.probe_cs < 0) { S.failed = 1; S.cs = 0; S.fs = 0; S.phase = 5; S.done = 1; return; }
+            return;
+        }
+    } else if (left >= 0) {
+        S.cs = S.probe_cs;
+        S.fs = S.probe_fs;
+    } else {
+        ph++;
+    }
+    // next candidate of the current phase, falling through exhausted phases
+    for (;;) {
+        if (ph == 1) { if (S.cs + 4 <= 63) { S.probe_cs = S.cs + 4; S.probe_fs = 0; break; } ph = 2; }
+        else if (ph == 2) { if (S.cs + 1 <= 63) { S.probe_cs = S.cs + 1; S.probe_fs = 0; break; } ph = 3; }
+        else if (ph == 3) { if (S.fs + 4 <= 15) { S.probe_cs = S.cs; S.probe_fs = S.fs + 4; break; } ph = 4; }
+        else if (ph == 4) { if (S.fs + 1 <= 15) { S.probe_cs = S.cs; S.probe_fs = S.fs + 1; break; } ph = 5; }
+        else { S.done = 1; break; }
+    }
+    S.phase = ph;
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 3)
+ac3_encode_kernel(const EncParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    EncTables& T = *reinterpret_cast<EncTables*>(smem_raw);
+    EncShared& S = *reinterpret_cast<EncShared*>(smem_raw + ((sizeof(EncTables) + 15) & ~(size_t)15));
+    __shared__ int s_stream;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_enc_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+        for (int i = tid; i < (int)(sizeof(EncTables) / 4); i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int nbytes = P.frame_words * 2;
+    const bool active = warp < P.nch_all;                              // warp = coded channel
+
+    for (;;) {
+        if (tid == 0) s_stream = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int s = s_stream;
+        if (s >= P.nstreams) break;
+        // carry in
+        for (int i = tid; i < 6 * 256; i += kThreads)
+            S.last[i >> 8][i & 255] = (P.carry && P.carry[s].started) ? P.carry[s].last_samples[i >> 8][i & 255] : 0;
+        if (tid == 0) S.cs = (P.carry && P.carry[s].started) ? P.carry[s].csnroffst : 40;      // :1092
+        __syncthreads();
+
+        for (int f = 0; f < P.nframes; f++) {
+            const size_t fidx = (size_t)s * P.nframes + f;
+            const int16_t* pcm = P.pcm + fidx * 1536 * P.nch_all;
+            // ================= E1 =================
+            for (int blk = 0; blk < 6; blk++) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(pcm + (size_t)blk * 256 * P.nch_all);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(S.u.e1.pcmblk);
+                for (int i = tid; i < 128 * P.nch_all; i += kThreads) dst[i] = src[i];
+                __syncthreads();
+                if (active) e1_transform(S, T, P, blk, warp, lane);
+                __syncthreads();
+            }
+            if (P.dbg_coef) {
+                for (int i = tid; i < 6 * 6 * 256; i += kThreads) {
+                    const int ch = (i >> 8) % 6;
+                    P.dbg_coef[fidx * 9216 + i] = ch < P.nch_all ? (&S.coef[0][0][0])[i] : 0;
+                }
+                if (tid < 36) P.dbg_shift[fidx * 36 + tid] = (tid % 6) < P.nch_all ? (&S.exp_shift[0][0])[tid] : 0;
+            }
+            // ================= E2 =================
+            if (active) {
+                const int bits = e2_exponents(S, P, warp, lane);
+                if (lane == 0) S.exp_bits[warp] = bits;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // everything but mantissas (:880-916)
+                static const int inc[8] = {0, 0, 2, 2, 2, 4, 2, 4};
+                int fb = 65 + inc[P.acmod];
+                for (int ch = 0; ch < P.nch_all; ch++) fb += S.exp_bits[ch];
+                for (int blk = 0; blk < 6; blk++) {
+                    fb += P.nch * 2 + 2;
+                    if (P.acmod == 2) fb++;
+                    fb += 2 * P.nch;
+                    if (P.lfe) fb++;
+                    for (int ch = 0; ch < P.nch; ch++)
+                        if (S.strategy[blk][ch]) fb += 6 + 2;
+                    fb += 4;
+                }
+                fb += 1 + 2 * 4 + 3 + 6 + P.nch_all * (4 + 3) + 2 + 16;
+                S.frame_bits = fb;
+                S.probe_cs = S.cs;                                       // warm start (:921)
+                S.probe_fs = 0;
+                S.fs = 0;
+                S.phase = 0;
+                S.done = 0;
+                S.failed = 0;
+            }
+            // ================= E3 =================
+            if (active) {
+                int16_t* psd = reinterpret_cast<int16_t*>(S.u.e1.z[warp]);      // scratch: 50 band values
+                for (int blk = 0; blk < 6; blk++)
+                    if (S.head[blk][warp] == blk) e3_mask(S, T, P, blk, warp, lane, psd);
+            }
+            __syncthreads();
+            for (;;) {
+                const int snro = (((S.probe_cs - 15) << 4) + S.probe_fs) << 2;
+                if (active)
+                    for (int blk = 0; blk < 6; blk++)
+                        if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, snro, false);
+                __syncthreads();
+                if (tid == 0) search_step(S, bits_left(S, P));
+                __syncthreads();
+                if (S.done) break;
+            }
+            {
+                // the accepted allocation (or, after a failed search, all-zero baps)
+                const int snro = (((S.cs - 15) << 4) + S.fs) << 2;
+                if (active)
+                    for (int blk = 0; blk < 6; blk++)
+                        if (S.head[blk][warp] == blk) {
+                            if (S.failed) {
+                                for (int i = lane; i < 256; i += 32) S.expo[blk][warp][i] = 0;
+                                if (lane < 4) S.cnt[blk][warp][lane] = 0;
+                            } else {
+                                e3_probe(S, T, P, blk, warp, lane, snro, true);
+                            }
+                        }
+            }
+            __syncthreads();
+            if (P.dbg_bap) {
+                for (int i = tid; i < 6 * 6 * 256; i += kThreads) {
+                    const int blk = i / 1536, ch = (i >> 8) % 6, k = i & 255;
+                    const bool ok = ch < P.nch_all && k < ((P.lfe && ch == 5) ? 7 : 223);
+                    const int h = ok ? S.head[blk][ch] : 0;
+                    P.dbg_bap[fidx * 9216 + i] = ok ? S.expo[h][ch][k] : 0;
+                    P.dbg_enc[fidx * 9216 + i] = ok ? S.enc[h][ch][k] : 0;
+                }
+                if (tid < 36) P.dbg_strategy[fidx * 36 + tid] = (tid % 6) < P.nch_all ? (&S.strategy[0][0])[tid] : 0;
+                if (tid == 0) { P.dbg_snr[fidx * 2] = S.cs; P.dbg_snr[fidx * 2 + 1] = S.fs; }
+            }
+            // ================= E4 =================
+            uint32_t* frame = S.u.e4.frame;
+            for (int i = tid; i < kFrameWords; i += kThreads) frame[i] = 0;
+            for (int i = tid; i < kCodes; i += kThreads) S.u.e4.codes[i] = 0;
+            __syncthreads();
+            if (tid == 0) {
+                // side information, serial (:1113-1147, 1210-1259, 1316-1337); sections written by the
+                // warps are skipped over and their positions recorded
+                SerialBits w{frame, 0};
+                w.put(16, 0x0b77);
+                w.put(16, 0);
+                w.put(2, P.fscod);
+                w.put(6, P.frmsizecod);
+                w.put(5, P.bsid);
+                w.put(3, 0);
+                w.put(3, P.acmod);
+                if ((P.acmod & 1) && P.acmod != 1) w.put(2, 1);
+                if (P.acmod & 4) w.put(2, 1);
+                if (P.acmod == 2) w.put(2, 0);
+                w.put(1, P.lfe);
+                w.put(5, 31);
+                w.put(4, 0);
+                w.put(1, 1);
+                w.put(3, 0);
+                for (int blk = 0; blk < 6; blk++) {
+                    w.put(P.nch, 0);                                     // blksw
+                    w.put(P.nch, (1u << P.nch) - 1);                     // dithflag
+                    w.put(1, 0);                                         // dynrnge
+                    if (blk == 0) w.put(2, 2); else w.put(1, 0);         // cplstre [cplinu]
+                    if (P.acmod == 2) { if (blk == 0) w.put(5, 16); else w.put(1, 0); }
+                    for (int ch = 0; ch < P.nch; ch++) w.put(2, S.strategy[blk][ch]);
+                    if (P.lfe) w.put(1, S.strategy[blk][5]);
+                    for (int ch = 0; ch < P.nch; ch++)
+                        if (S.strategy[blk][ch]) w.put(6, 50);
+                    for (int ch = 0; ch < P.nch_all; ch++) {
+                        const int st = S.strategy[blk][ch];
+                        if (!st) continue;
+                        const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
+                        const int ng = (((P.lfe && ch == 5) ? 7 : 223) + gs * 3 - 4) / (3 * gs);
+                        S.exp_pos[blk][ch] = w.pos;
+                        w.pos += 4 + 7 * ng + ((P.lfe && ch == 5) ? 0 : 2);
+                    }
+                    w.put(1, blk == 0);
+                    if (blk == 0) w.put(11, (2u << 9) | (1u << 7) | (1u << 5) | (2u << 3) | 4u);
+                    w.put(1, blk == 0);
+                    if (blk == 0) {
+                        w.put(6, S.cs);
+                        for (int ch = 0; ch < P.nch_all; ch++) { w.put(4, S.fs); w.put(3, 4); }
+                    }
+                    w.put(2, 0);
+                    S.mant_pos[blk] = w.pos;
+                    int n1 = 0, n2 = 0, n4 = 0;
+                    for (int ch = 0; ch < P.nch_all; ch++) {
+                        const int* q = S.cnt[S.head[blk][ch]][ch];
+                        n1 += q[0]; n2 += q[1]; n4 += q[2]; w.pos += q[3];
+                    }
+                    w.pos += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
+                }
+            }
+            __syncthreads();
+            for (int blk = 0; blk < 6; blk++) {
+                if (active) {
+                    const int ch = warp;
+                    const bool is_lfe = P.lfe && ch == 5;
+                    const int ncoef = is_lfe ? 7 : 223;
+                    const int h = S.head[blk][ch];
+                    const uint8_t* en = S.enc[h][ch];
+                    // grouped exponents (:1261-1314): lanes = groups
+                    const int st = S.strategy[blk][ch];
+                    if (st) {
+                        const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
+                        const int ng = (ncoef + gs * 3 - 4) / (3 * gs);
+                        const uint32_t p0 = S.exp_pos[blk][ch];
+                        if (lane == 0) put_bits_atomic(frame, p0, 4, en[0]);
+                        for (int g = lane; g < ng; g += 32) {
+                            const int k = 1 + 3 * g * gs;
+                            const int ea = g ? en[k - gs] : en[0];
+                            const int d0 = en[k] - ea + 2, d1 = en[k + gs] - en[k] + 2, d2 = en[k + 2 * gs] - en[k + gs] + 2;
+                            put_bits_atomic(frame, p0 + 4 + 7 * g, 7, (uint32_t)((d0 * 5 + d1) * 5 + d2));
+                        }
+                    }
+                    // mantissas (:1346-1501): occurrence numbers of the grouped classes run across channels
+                    int N1 = 0, N2 = 0, N4 = 0, fixed_before = 0;
+                    for (int c = 0; c < ch; c++) {
+                        const int* q = S.cnt[S.head[blk][c]][c];
+                        N1 += q[0]; N2 += q[1]; N4 += q[2]; fixed_before += q[3];
+                    }
+                    uint32_t pos0 = S.mant_pos[blk] + fixed_before + 5 * ((N1 + 2) / 3) + 7 * ((N2 + 2) / 3) + 7 * ((N4 + 1) / 2);
+                    const uint8_t* bap = S.expo[h][ch];
+                    const int gexp = S.exp_shift[blk][ch];
+                    for (int i0 = 0; i0 < ncoef; i0 += 32) {
+                        const int i = i0 + lane;
+                        int b = 0, c = 0, e = 0;
+                        if (i < ncoef) { b = bap[i]; c = S.coef[blk][ch][i]; e = en[i] - gexp; }
+                        const uint32_t m1 = __ballot_sync(0xffffffffu, b == 1);
+                        const uint32_t m2 = __ballot_sync(0xffffffffu, b == 2);
+                        const uint32_t m4 = __ballot_sync(0xffffffffu, b == 4);
+                        const uint32_t lt = (1u << lane) - 1;
+                        int x = 0, per = 1, cls = -1;
+                        if (b == 1) { x = N1 + __popc(m1 & lt); per = 3; cls = 0; }
+                        else if (b == 2) { x = N2 + __popc(m2 & lt); per = 3; cls = 1; }
+                        else if (b == 4) { x = N4 + __popc(m4 & lt); per = 2; cls = 2; }
+                        const int g = x / per, digit = x - g * per;
+                        int width = (cls >= 0 && digit) ? 0 : T.width[b];
+                        // inclusive scan of the widths
+                        int incl = width;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            int t = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        const uint32_t pos = pos0 + incl - width;
+                        pos0 += __shfl_sync(0xffffffffu, incl, 31);
+                        N1 += __popc(m1); N2 += __popc(m2); N4 += __popc(m4);
+                        if (b == 0) continue;
+                        if (cls >= 0) {
+                            const int levels = cls == 0 ? 3 : cls == 1 ? 5 : 11;
+                            const int v = sym_quant(c, e, levels);
+                            const int wgt = cls == 2 ? (digit ? 1 : 11)
+                                                     : (digit == 0 ? levels * levels : digit == 1 ? levels : 1);
+                            const int gi = (cls == 0 ? 0 : cls == 1 ? 376 : 752) + g;
+                            atomicAdd(&S.u.e4.codes[gi], (uint32_t)(wgt * v));
+                            if (digit == 0) S.u.e4.gpos[gi] = (uint16_t)min(pos, 65535u);
+                        } else {
+                            int v;
+                            if (b == 3) v = sym_quant(c, e, 7);
+                            else if (b == 5) v = sym_quant(c, e, 15);
+                            else if (b == 14) v = asym_quant(c, e, 14);
+                            else if (b == 15) v = asym_quant(c, e, 16);
+                            else v = asym_quant(c, e, b - 1);
+                            put_bits_atomic(frame, pos, T.width[b], (uint32_t)v);
+                        }
+                    }
+                }
+                __syncthreads();
+                {
+                    // group codes of the block
+                    int n1 = 0, n2 = 0, n4 = 0;
+                    for (int c = 0; c < P.nch_all; c++) {
+                        const int* q = S.cnt[S.head[blk][c]][c];
+                        n1 += q[0]; n2 += q[1]; n4 += q[2];
+                    }
+                    const int g1 = (n1 + 2) / 3, g2 = (n2 + 2) / 3, g4 = (n4 + 1) / 2;
+                    for (int i = tid; i < g1 + g2 + g4; i += kThreads) {
+                        const int gi = i < g1 ? i : i < g1 + g2 ? 376 + (i - g1) : 752 + (i - g1 - g2);
+                        put_bits_atomic(frame, S.u.e4.gpos[gi], i < g1 ? 5 : 7, S.u.e4.codes[gi]);
+                        S.u.e4.codes[gi] = 0;
+                    }
+                }
+                __syncthreads();
+            }
+            // frame end (:1599-1638): crc1 over the first 5/8 through the inverse polynomial trick,
+            // crc2 over the rest, stored over the last two bytes whatever spilled into them
+            {
+                const int fs58 = (P.frame_words >> 1) + (P.frame_words >> 3);
+                if (tid == 0) {
+                    // bytes past the payload that belong to the crc2 field are excluded below; clear the
+                    // field first so that payload overflow (stereo bit-accounting slip, :889) is dropped
+                    const int k = nbytes - 2;
+                    frame[k >> 2] &= ~(0xffffu << (16 - 8 * (k & 3)));
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t c1 = warp_crc(T, frame, 4, 2 * fs58, lane);
+                    if (lane == 0) S.crc[0] = mul_poly(P.crc_inv, c1);
+                } else if (warp == 1) {
+                    uint32_t c2 = warp_crc(T, frame, 2 * fs58, nbytes - 2, lane);
+                    if (lane == 0) S.crc[1] = c2;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    frame[0] |= S.crc[0] & 0xffff;                           // bytes 2, 3
+                    const int k = nbytes - 2;
+                    frame[k >> 2] |= (S.crc[1] & 0xffff) << (16 - 8 * (k & 3));
+                }
+                __syncthreads();
+            }
+            // store (big-endian bytes): frames start at even offsets, so 16-bit stores
+            {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(P.out + fidx * nbytes);
+                for (int i = tid; i < P.frame_words; i += kThreads) {
+                    const uint32_t wv = frame[i >> 1];
+                    const uint32_t h = (i & 1) ? (wv & 0xffff) : (wv >> 16);
+                    dst[i] = (uint16_t)(((h & 0xff) << 8) | (h >> 8));
+                }
+                if (tid == 0 && P.status) P.status[fidx] = S.failed ? AC3_ST_NO_FIT : AC3_ST_OK;
+            }
+            __syncthreads();
+        }   // frames
+
+        if (P.carry) {
+            for (int i = tid; i < 6 * 256; i += kThreads) P.carry[s].last_samples[i >> 8][i & 255] = S.last[i >> 8][i & 255];
+            if (tid == 0) { P.carry[s].csnroffst = S.cs; P.carry[s].started = 1; }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ac3e
+
+#include "ac3_encode_host.inl"

@@ -1,0 +1,352 @@
+// ac3_encode_host.inl - host side of the encoder: tables, context, the C ABI of
+// include/ac3enc_batch.h and the drop-in AC3_encode_* API of include/ac3enc.h.
+// Included at the end of ac3_encode.cu.
+
+namespace ac3e {
+
+static const int h_freqs[3] = {48000, 44100, 32000};
+
+static int16_t h_fix15(float a)             // ac3enc.cpp:427-439
+{
+    int v = (int)(a * (float)(1 << 15));
+    if (v < -32767) v = -32767; else if (v > 32767) v = 32767;
+    return (int16_t)v;
+}
+
+static void build_enc_tables(EncTables* T)
+{
+    memset(T, 0, sizeof(*T));
+    // KBD (alpha = 5) window in Q15, truncated (ac3tab.h:14-47 holds the same values as literals)
+    {
+        double sum = 0, cum[256];
+        for (int i = 0; i < 256; i++) {
+            double x = i * (256 - i) * (5 * M_PI / 256) * (5 * M_PI / 256), b = 1;
+            for (int k = 100; k > 0; k--) b = b * x / (k * k) + 1;
+            sum += b;
+            cum[i] = sum;
+        }
+        sum++;
+        for (int i = 0; i < 256; i++) {
+            int v = (int)floor(sqrt(cum[i] / sum) * 32768.0);
+            T->window[i] = (int16_t)(v > 32767 ? 32767 : v);
+        }
+    }
+    // fft / mdct twiddles, float arithmetic exactly as the reference writes it (ac3enc.cpp:441-459, 1098-1102)
+    for (int i = 0; i < 64; i++) {
+        float alpha = (float)(2 * M_PI * (float)i / (float)128);
+        T->costab[i] = h_fix15((float)cos(alpha));
+        T->sintab[i] = h_fix15((float)sin(alpha));
+    }
+    for (int i = 0; i < 128; i++) {
+        int m = 0;
+        for (int j = 0; j < 7; j++) m |= ((i >> j) & 1) << (6 - j);
+        T->rev[i] = (uint8_t)m;
+        float alpha = (float)(2 * M_PI * (i + 1.0 / 8.0) / (float)512);
+        T->xcos1[i] = h_fix15((float)-cos(alpha));
+        T->xsin1[i] = h_fix15((float)-sin(alpha));
+    }
+    for (int i = 0; i < 256; i++) {          // ac3enc.cpp:998-1016
+        unsigned c = (unsigned)i << 8;
+        for (int j = 0; j < 8; j++) c = (c & 0x8000) ? (((c << 1) & 0xffff) ^ 0x8005) : (c << 1);
+        T->crc_table[i] = (uint16_t)c;
+        T->masktab[i] = ac3_masktab[i];
+        T->latab[i] = ac3_latab[i];
+    }
+    for (int i = 0; i < 150; i++) T->hth[i] = ac3_hth[i];
+    for (int i = 0; i < 64; i++) T->baptab[i] = ac3_baptab[i];
+    for (int i = 0; i < 51; i++) T->bndtab[i] = ac3_bndtab[i];
+    T->bndtab[51] = 253;
+    for (int b = 0; b < 16; b++) {
+        T->width[b] = ac3_bap_bits[b];
+        T->plain_bits[b] = (b == 0 || b == 1 || b == 2 || b == 4) ? 0 : ac3_bap_bits[b];
+    }
+}
+
+struct EncConfig {
+    int nch_all, nch, lfe, acmod, fscod, halfrate, bsid, frmsizecod, frame_words;
+};
+
+static bool enc_config(int freq, int bitrate, int channels, EncConfig* c)    // ac3enc.cpp:1019-1077
+{
+    static const uint8_t acmod_defs[6] = {1, 2, 3, 6, 7, 7};
+    if (channels < 1 || channels > 6) return false;
+    c->acmod = acmod_defs[channels - 1];
+    c->lfe = channels == 6;
+    c->nch_all = channels;
+    c->nch = channels > 5 ? 5 : channels;
+    bool found = false;
+    for (int i = 0; i < 3 && !found; i++)
+        for (int j = 0; j < 3; j++)
+            if ((h_freqs[j] >> i) == freq) { c->halfrate = i; c->fscod = j; found = true; break; }
+    if (!found) return false;
+    c->bsid = 8 + c->halfrate;
+    bitrate /= 1000;
+    int i;
+    for (i = 0; i < 19; i++)
+        if ((ac3_bitrate_kbps[i] >> c->halfrate) == bitrate) break;
+    if (i == 19) return false;
+    c->frmsizecod = i << 1;
+    c->frame_words = (bitrate * 1000 * 1536) / (freq * 16);
+    return c->frame_words > 0;
+}
+
+static unsigned h_mul_poly(unsigned a, unsigned b, unsigned poly)
+{
+    unsigned c = 0;
+    while (a) { if (a & 1) c ^= b; a >>= 1; b <<= 1; if (b & 0x10000) b ^= poly; }
+    return c;
+}
+static unsigned h_pow_poly(unsigned a, unsigned n, unsigned poly)
+{
+    unsigned r = 1;
+    while (n) { if (n & 1) r = h_mul_poly(r, a, poly); a = h_mul_poly(a, a, poly); n >>= 1; }
+    return r;
+}
+
+}  // namespace ac3e
+
+struct ac3_batch_s {
+    int device = 0;
+    int num_sms = 0;
+    int* d_counter = nullptr;
+    char err[256] = {0};
+    long launches = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Buf { void* p = nullptr; size_t cap = 0; } b_pcm, b_out, b_status, b_carry, b_coef, b_shift, b_strat, b_enc, b_bap, b_snr;
+};
+
+#define AC3_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            snprintf(ctx->err, sizeof(ctx->err), "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+static int ac3_ensure(ac3_batch_t* ctx, ac3_batch_s::Buf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t cap = bytes + bytes / 8 + 256;
+    AC3_CUDA(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return 0;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+ac3_batch_t* ac3_batch_create(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    ac3_batch_t* ctx = new (std::nothrow) ac3_batch_s();
+    if (!ctx) return nullptr;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
+    ctx->num_sms = prop.multiProcessorCount;
+    ac3e::EncTables* T = new ac3e::EncTables;
+    ac3e::build_enc_tables(T);
+    bool ok = cudaMemcpyToSymbol(ac3e::g_enc_tables, T, sizeof(*T)) == cudaSuccess;
+    delete T;
+    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ac3e::ac3_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(ac3e::EncShared) + sizeof(ac3e::EncTables) + 32)) == cudaSuccess;
+    if (!ok) { ac3_batch_destroy(ctx); return nullptr; }
+    return ctx;
+}
+
+void ac3_batch_destroy(ac3_batch_t* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ac3_batch_s::Buf* bufs[] = {&ctx->b_pcm, &ctx->b_out, &ctx->b_status, &ctx->b_carry, &ctx->b_coef,
+                                &ctx->b_shift, &ctx->b_strat, &ctx->b_enc, &ctx->b_bap, &ctx->b_snr};
+    for (auto* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+const char* ac3_batch_last_error(ac3_batch_t* ctx) { return ctx ? ctx->err : "no context"; }
+
+int ac3_batch_frame_bytes(int freq, int bitrate, int channels)
+{
+    ac3e::EncConfig c;
+    return ac3e::enc_config(freq, bitrate, channels, &c) ? c.frame_words * 2 : 0;
+}
+
+long ac3_batch_launch_count(ac3_batch_t* ctx) { return ctx->launches; }
+
+double ac3_batch_kernel_ms(ac3_batch_t* ctx, int* nlaunches)
+{
+    double total = 0;
+    int n = 0;
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0;
+        cudaEventSynchronize(ctx->ev_pool[i + 1]);
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) { total += ms; n++; }
+    }
+    ctx->ev_used = 0;
+    if (nlaunches) *nlaunches = n;
+    return n ? total / n : 0.0;
+}
+
+int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nframes, int freq, int bitrate,
+                     int channels, const uint8_t* chmap, uint8_t* out, int32_t* status, ac3_stream_carry_t* carry,
+                     const ac3_batch_debug_t* debug, int mem_flags, void* cuda_stream)
+{
+    using namespace ac3e;
+    if (!ctx) return -1;
+    ctx->err[0] = 0;
+    EncConfig c;
+    if (nstreams < 0 || nframes < 0 || !enc_config(freq, bitrate, channels, &c)) {
+        snprintf(ctx->err, sizeof(ctx->err), "bad argument (configuration rejected as by AC3_encode_init)");
+        return -3;
+    }
+    if (nstreams == 0 || nframes == 0) return 0;
+    AC3_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t total = (size_t)nstreams * nframes;
+    const size_t pcm_bytes = total * 1536 * channels * 2, out_bytes = total * c.frame_words * 2;
+
+    EncParams P;
+    memset(&P, 0, sizeof(P));
+    P.nstreams = nstreams;
+    P.nframes = nframes;
+    P.nch_all = c.nch_all; P.nch = c.nch; P.lfe = c.lfe; P.acmod = c.acmod; P.fscod = c.fscod;
+    P.halfrate = c.halfrate; P.bsid = c.bsid; P.frmsizecod = c.frmsizecod; P.frame_words = c.frame_words;
+    const int fs58 = (c.frame_words >> 1) + (c.frame_words >> 3);
+    P.crc_inv = h_pow_poly(0x18005 >> 1, (unsigned)(16 * fs58 - 16), 0x18005);
+    for (int i = 0; i < 6; i++) P.chmap[i] = chmap ? chmap[i < channels ? i : 0] : (uint8_t)i;
+    for (int i = 0; i < channels; i++)
+        if (P.chmap[i] >= channels) {
+            snprintf(ctx->err, sizeof(ctx->err), "bad channel map");
+            return -3;
+        }
+    P.work_counter = ctx->d_counter;
+    const bool dev = (mem_flags & AC3_BATCH_DEVICE_PTRS) != 0;
+    if (dev) {
+        P.pcm = pcm; P.out = out; P.status = status; P.carry = (EncCarry*)carry;
+        if (debug) {
+            P.dbg_coef = debug->coef; P.dbg_shift = debug->exp_shift; P.dbg_strategy = debug->strategy;
+            P.dbg_enc = debug->encoded_exp; P.dbg_bap = debug->bap; P.dbg_snr = debug->snr;
+        }
+    } else {
+        if (ac3_ensure(ctx, ctx->b_pcm, pcm_bytes) || ac3_ensure(ctx, ctx->b_out, out_bytes) ||
+            ac3_ensure(ctx, ctx->b_status, total * 4)) return -1;
+        AC3_CUDA(cudaMemcpyAsync(ctx->b_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+        P.pcm = (const int16_t*)ctx->b_pcm.p;
+        P.out = (uint8_t*)ctx->b_out.p;
+        P.status = (int32_t*)ctx->b_status.p;
+        if (carry) {
+            if (ac3_ensure(ctx, ctx->b_carry, sizeof(EncCarry) * (size_t)nstreams)) return -1;
+            AC3_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, st));
+            P.carry = (EncCarry*)ctx->b_carry.p;
+        }
+        if (debug && debug->coef) {
+            if (ac3_ensure(ctx, ctx->b_coef, total * 9216 * 4) || ac3_ensure(ctx, ctx->b_shift, total * 36) ||
+                ac3_ensure(ctx, ctx->b_strat, total * 36) || ac3_ensure(ctx, ctx->b_enc, total * 9216) ||
+                ac3_ensure(ctx, ctx->b_bap, total * 9216) || ac3_ensure(ctx, ctx->b_snr, total * 8)) return -1;
+            P.dbg_coef = (int32_t*)ctx->b_coef.p; P.dbg_shift = (int8_t*)ctx->b_shift.p;
+            P.dbg_strategy = (uint8_t*)ctx->b_strat.p; P.dbg_enc = (uint8_t*)ctx->b_enc.p;
+            P.dbg_bap = (uint8_t*)ctx->b_bap.p; P.dbg_snr = (int32_t*)ctx->b_snr.p;
+        }
+    }
+    // all six dump pointers travel together
+    if (!(P.dbg_coef && P.dbg_shift && P.dbg_strategy && P.dbg_enc && P.dbg_bap && P.dbg_snr))
+        P.dbg_coef = nullptr, P.dbg_shift = nullptr, P.dbg_strategy = nullptr, P.dbg_enc = nullptr,
+        P.dbg_bap = nullptr, P.dbg_snr = nullptr;
+
+    const size_t smem = ((sizeof(EncTables) + 15) & ~(size_t)15) + sizeof(EncShared);
+    int occ = 0;
+    AC3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ac3_encode_kernel, kThreads, smem));
+    if (occ < 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "encode kernel does not fit: %zu bytes of shared memory", smem);
+        return -2;
+    }
+    int grid = ctx->num_sms * occ;
+    if (grid > nstreams) grid = nstreams;
+    AC3_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+        if (ctx->ev_pool.size() < 8192) {
+            cudaEvent_t a, b;
+            AC3_CUDA(cudaEventCreate(&a));
+            AC3_CUDA(cudaEventCreate(&b));
+            ctx->ev_pool.push_back(a);
+            ctx->ev_pool.push_back(b);
+        } else ctx->ev_used = 0;
+    }
+    cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used], e1 = ctx->ev_pool[ctx->ev_used + 1];
+    ctx->ev_used += 2;
+    AC3_CUDA(cudaEventRecord(e0, st));
+    ac3_encode_kernel<<<grid, kThreads, smem, st>>>(P);
+    AC3_CUDA(cudaEventRecord(e1, st));
+    AC3_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (dev) return 0;
+
+    AC3_CUDA(cudaMemcpyAsync(out, P.out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (status) AC3_CUDA(cudaMemcpyAsync(status, P.status, total * 4, cudaMemcpyDeviceToHost, st));
+    if (carry) AC3_CUDA(cudaMemcpyAsync(carry, P.carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, st));
+    if (P.dbg_coef && debug) {
+        AC3_CUDA(cudaMemcpyAsync(debug->coef, P.dbg_coef, total * 9216 * 4, cudaMemcpyDeviceToHost, st));
+        AC3_CUDA(cudaMemcpyAsync(debug->exp_shift, P.dbg_shift, total * 36, cudaMemcpyDeviceToHost, st));
+        AC3_CUDA(cudaMemcpyAsync(debug->strategy, P.dbg_strategy, total * 36, cudaMemcpyDeviceToHost, st));
+        AC3_CUDA(cudaMemcpyAsync(debug->encoded_exp, P.dbg_enc, total * 9216, cudaMemcpyDeviceToHost, st));
+        AC3_CUDA(cudaMemcpyAsync(debug->bap, P.dbg_bap, total * 9216, cudaMemcpyDeviceToHost, st));
+        AC3_CUDA(cudaMemcpyAsync(debug->snr, P.dbg_snr, total * 8, cudaMemcpyDeviceToHost, st));
+    }
+    AC3_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ===========================================================================
+// drop-in encoder API (include/ac3enc.h): a process-wide singleton like the reference's
+// (static AC3EncodeContext ac3enc_state, ac3enc.cpp:78)
+// ===========================================================================
+static struct {
+    ac3_batch_t* ctx;
+    int freq, bitrate, channels, frame_bytes;
+    ac3_stream_carry_t carry;
+} g_enc1;
+
+int AC3_encode_init(int freq, int bitrate, int channels)
+{
+    int fb = ac3_batch_frame_bytes(freq, bitrate, channels);
+    if (!fb) return 0;
+    if (!g_enc1.ctx) {
+        int dev = 0;
+        const char* e = getenv("A52_B200_DEVICE");
+        if (e) dev = atoi(e);
+        g_enc1.ctx = ac3_batch_create(dev);
+        if (!g_enc1.ctx) return 0;          // no CPU fallback by design
+    }
+    g_enc1.freq = freq;
+    g_enc1.bitrate = bitrate;
+    g_enc1.channels = channels;
+    g_enc1.frame_bytes = fb;
+    // the reference keeps last_samples across re-initialisation but resets the snr warm start (:1092);
+    // a fresh stream here starts from silence like a freshly loaded codec
+    memset(&g_enc1.carry, 0, sizeof(g_enc1.carry));
+    return fb;
+}
+
+int AC3_encode_frame(unsigned char* dst, short* samples, unsigned char* chmap)
+{
+    if (!g_enc1.ctx) return 0;
+    int rc = ac3_batch_encode(g_enc1.ctx, samples, 1, 1, g_enc1.freq, g_enc1.bitrate, g_enc1.channels, chmap, dst,
+                              nullptr, &g_enc1.carry, nullptr, 0, nullptr);
+    return rc ? 0 : g_enc1.frame_bytes;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,73 @@
+/* include/ac3enc_batch.h - batched AC-3 encode entry points of the B200 engine (C ABI).
+ *
+ * One call encodes nstreams independent PCM streams of nframes frames each; a group of GPU
+ * threads walks the frames of one stream in order (the reference encoder carries 256 samples per
+ * channel and the warm start of its SNR-offset search from frame to frame, ac3enc.cpp:55, 921,
+ * 969), streams in parallel.  Per frame the arithmetic is the reference's integer encoder
+ * (ac3enc.cpp:1640-1763): frames are byte-identical to AC3_encode_frame's.
+ *
+ * Pointers are host pointers unless AC3_BATCH_DEVICE_PTRS is set in mem_flags.
+ */
+#ifndef AC3ENC_BATCH_H
+#define AC3ENC_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ac3_batch_s ac3_batch_t;
+
+#define AC3_BATCH_DEVICE_PTRS 1
+
+#define AC3_ST_OK            0
+#define AC3_ST_NO_FIT        1   /* no SNR offset fits the frame (the reference prints "Yack" and emits an
+				    undecodable frame, ac3enc.cpp:930-933); here: a valid frame of zero mantissas */
+
+/* per-stream carry between calls (optional) */
+typedef struct {
+    int16_t last_samples[6][256];   /* previous 256 samples of every coded channel (ac3enc.cpp:55) */
+    int32_t csnroffst;              /* warm start of the search; 0 in a fresh record means "40" (:1092) */
+    int32_t started;                /* 0: fresh stream */
+    int32_t reserved[2];
+} ac3_stream_carry_t;
+
+/* optional intermediate dumps for parity testing; any pointer may be NULL.  Layouts per frame:
+ * coef int32 [6 blocks][6 ch][256], exp_shift int8 [6][6], strategy uint8 [6][6],
+ * encoded_exp uint8 [6][6][256], bap uint8 [6][6][256], snr int32 [2] (csnroffst, fsnroffst) */
+typedef struct {
+    int32_t * coef;
+    int8_t *  exp_shift;
+    uint8_t * strategy;
+    uint8_t * encoded_exp;
+    uint8_t * bap;
+    int32_t * snr;
+} ac3_batch_debug_t;
+
+ac3_batch_t * ac3_batch_create (int device);
+void ac3_batch_destroy (ac3_batch_t * ctx);
+const char * ac3_batch_last_error (ac3_batch_t * ctx);
+
+/* frame size in bytes for a configuration, 0 if the reference encoder would reject it
+ * (AC3_encode_init, ac3enc.cpp:1019-1077) */
+int ac3_batch_frame_bytes (int freq, int bitrate, int channels);
+
+/* pcm   int16 [nstreams][nframes][1536][channels] (interleaved, as AC3_encode_frame takes it)
+ * chmap channels entries or NULL (identity)
+ * out   uint8 [nstreams][nframes][frame_bytes]
+ * status int32 [nstreams][nframes] or NULL; carry [nstreams] in/out or NULL
+ * Returns 0, or negative on a CUDA / argument error. */
+int ac3_batch_encode (ac3_batch_t * ctx, const int16_t * pcm, int nstreams, int nframes,
+		      int freq, int bitrate, int channels, const uint8_t * chmap,
+		      uint8_t * out, int32_t * status, ac3_stream_carry_t * carry,
+		      const ac3_batch_debug_t * debug, int mem_flags, void * cuda_stream);
+
+long ac3_batch_launch_count (ac3_batch_t * ctx);
+double ac3_batch_kernel_ms (ac3_batch_t * ctx, int * nlaunches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AC3ENC_BATCH_H */

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_functions():
     names = set()
-    for h in ("a52.h", "a52_batch.h", "ac3enc.h"):
+    for h in ("a52.h", "a52_batch.h", "ac3enc.h", "ac3enc_batch.h"):
         p = os.path.join(ROOT, "include", h)
         if not os.path.exists(p):
             continue
@@ -72,6 +72,16 @@ def test_frame_indexer_resync(engine, oracle, c2):
     assert len(engine.index_frames(fr[:1791])) == 0          # truncated single frame
 
 
+def test_encoder_frame_bytes(engine):
+    L = engine.load_library()
+    # AC3_encode_init's acceptance rules (ac3enc.cpp:1019-1077), host side only
+    assert L.ac3_batch_frame_bytes(48000, 448000, 6) == 1792 and L.ac3_batch_frame_bytes(48000, 192000, 2) == 768
+    assert L.ac3_batch_frame_bytes(44100, 320000, 5) == 2 * (320000 * 1536 // (44100 * 16))
+    assert L.ac3_batch_frame_bytes(24000, 64000, 2) == 512
+    for bad in ((48000, 448000, 7), (48000, 448000, 0), (47999, 448000, 2), (48000, 449000, 2)):
+        assert L.ac3_batch_frame_bytes(*bad) == 0
+
+
 def test_frame_stride(engine):
     L = engine.load_library()
     for flags, nout in [(2, 2), (7 | 16, 6), (1, 1), (10 | 32, 2), (6 | 16, 5)]:
@@ -86,5 +96,9 @@ def test_no_cpu_fallback_without_gpu(engine):
     L = engine.load_library()
     assert not L.a52_init(0)                       # NULL: no device, no decode
     assert not L.a52_batch_create(0)
+    assert not L.ac3_batch_create(0)
+    assert L.AC3_encode_init(48000, 448000, 6) == 0
+    with pytest.raises(RuntimeError):
+        engine.BatchEncoder(0)
     with pytest.raises(RuntimeError):
         engine.BatchDecoder(0)
