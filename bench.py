@@ -32,6 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ENC_CPU_FRAMES = 32                 # frames per "stream" of the CPU encode sample
 FRAME_BYTES = 1792                  # 5.1 @ 448 kb/s, 48 kHz (parse.c:119)
 FRAME_SECONDS = 1536 / 48000.0
 PCM_BYTES = 1536 * 2 * 4            # float32 stereo per frame
@@ -39,6 +40,8 @@ ALGO_BYTES_PER_FRAME = FRAME_BYTES + PCM_BYTES      # 14080 (SURVEY.md section 8
 A52_STEREO, A52_ADJUST_LEVEL = 2, 32
 REQ_FLAGS = A52_STEREO | A52_ADJUST_LEVEL
 METRIC = "decoded audio-sec/sec, 5.1 448k AC-3, batched streams"
+METRIC_ENC = "encoded audio-sec/sec, 5.1 448k AC-3, batched streams"
+ENC_ALGO_BYTES_PER_FRAME = 1536 * 6 * 2 + 1792      # int16 5.1 PCM in + frame out
 UNIT = "audio-s/s"
 
 
@@ -81,8 +84,40 @@ def _cpu_work(nstreams):
     return frames, time.perf_counter() - t0
 
 
+def _cpu_init_enc(kind):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refbind
+    from synth import synth_pcm
+    _cpu["enc"] = refbind.RefAc3Enc() if kind == "reference" else refbind.OracleEnc()
+    _cpu["pcm"] = np.ascontiguousarray(synth_pcm(2, 0, 6, 1536 * ENC_CPU_FRAMES))
+    _cpu["outbuf"] = np.zeros(ENC_CPU_FRAMES * 3840 + 64, np.uint8)
+
+
+def _cpu_work_enc(nstreams):
+    import ctypes as C
+    e = _cpu["enc"]
+    fn = e.lib.ref_ac3enc_stream if hasattr(e.lib, "ref_ac3enc_stream") else e.lib.ora_enc_stream
+    pcm, out = _cpu["pcm"], _cpu["outbuf"]
+    t0 = time.perf_counter()
+    for _ in range(nstreams):
+        fb = fn(48000, 448000, 6, pcm.ctypes.data_as(C.POINTER(C.c_short)), ENC_CPU_FRAMES, None,
+                out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert fb == 1792
+    return nstreams * ENC_CPU_FRAMES, time.perf_counter() - t0
+
+
 class CpuArm:
-    def __init__(self):
+    def __init__(self, workload="decode"):
+        self.workload = workload
+        self._init_common()
+        if workload == "encode":
+            self.pool = self.mp.get_context("fork").Pool(self.cores, initializer=_cpu_init_enc, initargs=(self.kind,))
+            self.work = _cpu_work_enc
+            self.pool.map(self.work, [1] * self.cores)
+            return
+        self._init_decode()
+
+    def _init_common(self):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import refbind
         self.kind = "reference" if refbind.have_ref() else "port"
@@ -91,12 +126,16 @@ class CpuArm:
         except AttributeError:
             self.cores = os.cpu_count() or 1
         import multiprocessing as mp
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
+        self.mp = mp
+        self.work = _cpu_work
+
+    def _init_decode(self):
+        self.pool = self.mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
         self.pool.map(_cpu_work, [1] * self.cores)               # warm: page in, tables
 
     def run(self, streams_per_core):
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_work, [streams_per_core] * self.cores, chunksize=1)
+        res = self.pool.map(self.work, [streams_per_core] * self.cores, chunksize=1)
         wall = time.perf_counter() - t0
         frames = sum(r[0] for r in res)
         return frames * FRAME_SECONDS, wall
@@ -116,7 +155,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    arm = CpuArm()
+    arm = CpuArm(args.workload)
     k = arm.calibrate(2.0)                                   # ~2 s of CPU work per core per step
     for _ in range(args.warmup):
         arm.run(k)
@@ -127,9 +166,12 @@ def run_reference(args):
         t_total += w
     arm.close()
     v = a_total / t_total
-    sample = "%d streams x 313 frames per core per step (%d cores), in memory, stereo float out" % (k, arm.cores)
+    if args.workload == "encode":
+        sample = "%d x %d frames of 5.1 PCM per core per step (%d cores), in memory" % (k, ENC_CPU_FRAMES, arm.cores)
+    else:
+        sample = "%d streams x 313 frames per core per step (%d cores), in memory, stereo float out" % (k, arm.cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC_ENC if args.workload == "encode" else METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
@@ -142,6 +184,12 @@ def run_reference(args):
 
 
 def workload_config(args):
+    if args.workload == "encode":
+        return {"workload": "5.1 48 kHz int16 PCM -> 448 kbps AC-3 encode, %d independent %.1f s streams per GPU "
+                            "(BASELINE.json configs[3])" % (args.streams, args.frames * FRAME_SECONDS),
+                "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "frame_bytes": FRAME_BYTES,
+                "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2"
+                % (args.streams * args.frames * ENC_ALGO_BYTES_PER_FRAME / 1e9)}
     return {"workload": "5.1 48 kHz 448 kbps decode, %d independent %.1f s streams per GPU, stereo downmix, "
                         "float32 PCM (BASELINE.json configs[1])" % (args.streams, args.frames * FRAME_SECONDS),
             "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "frame_bytes": FRAME_BYTES,
@@ -326,6 +374,131 @@ def run_gpu(args):
     return 0
 
 
+def run_gpu_encode(args):
+    """Config 4: batched encode.  Same contract as the decode line (value = device resident, e2e = host buffers)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        arm = CpuArm("encode")
+        k = arm.calibrate(args.cpu_seconds)
+        a, w = arm.run(k)
+        arm.close()
+        cpu_baseline = {"value": a / w, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                        "sample": "%d x %d frames of 5.1 PCM per core (%d cores, %.1f s wall), in memory"
+                                  % (k, ENC_CPU_FRAMES, arm.cores, w)}
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    eng = ge.load_engine()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the encode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import importlib
+    shard = importlib.import_module("ac3_acm_codec_b200.shard")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import synth_pcm
+    S, F = args.streams, args.frames
+    dev = torch.device("cuda", local)
+    base = torch.from_numpy(np.stack([synth_pcm(2, s, 6, 1536 * 64) for s in range(4)]).reshape(4, 64, 1536 * 6)).to(dev)
+    fidx = (torch.arange(F, device=dev)[None, :] + 7 * torch.arange(S, device=dev)[:, None]) % 64
+    pcm = base[(torch.arange(S, device=dev) % 4)[:, None], fidx].contiguous()          # [S, F, 1536*6] int16
+    out = torch.zeros((S, F, FRAME_BYTES), dtype=torch.uint8, device=dev)
+    status = torch.zeros((S, F), dtype=torch.int32, device=dev)
+    enc = eng.BatchEncoder(local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        enc.encode_device(pcm.data_ptr(), S, F, 48000, 448000, 6, out.data_ptr(), status_ptr=status.data_ptr(),
+                          stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    assert int((status != 0).sum().item()) == 0
+    enc.kernel_ms()
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.25)
+    l0 = enc.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1))
+    launches = enc.launch_count() - l0
+    kms, kn = enc.kernel_ms()
+    clocks = sampler.window(t0, t1) if sampler else None
+    nframes = S * F
+    value = nframes * FRAME_SECONDS * world * args.steps / (ms / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except ImportError:
+            avail = 64 << 30
+        s2 = S
+        while s2 > 64 and s2 * F * ENC_ALGO_BYTES_PER_FRAME > avail // (3 * max(world, 1)):
+            s2 //= 2
+        pcm_h = pcm[:s2].cpu().pin_memory()
+        out_h = torch.zeros((s2, F, FRAME_BYTES), dtype=torch.uint8).pin_memory()
+        st_h = torch.zeros((s2, F), dtype=torch.int32).pin_memory()
+
+        def hstep():
+            rc = enc.L.ac3_batch_encode(enc.ctx, pcm_h.data_ptr(), s2, F, 48000, 448000, 6, None, out_h.data_ptr(),
+                                        st_h.data_ptr(), None, None, 0, None)
+            assert rc == 0
+        hstep()
+        barrier()
+        n = max(1, min(args.steps, args.e2e_steps))
+        tt = time.perf_counter()
+        for _ in range(n):
+            hstep()
+        barrier()
+        wall = shard.max_over_ranks(time.perf_counter() - tt)
+        e2e = {"value": s2 * F * FRAME_SECONDS * world * n / wall, "unit": UNIT,
+               "h2d_bytes_per_step": int(pcm_h.numel() * 2), "d2h_bytes_per_step": int(out_h.numel() + st_h.numel() * 4),
+               "streams_per_gpu": s2, "steps": n, "ms_per_step": 1e3 * wall / n,
+               "api": "ac3_batch_encode (host pointers, pinned)"}
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        peak, peak_src = 6650.0, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            if peaks.get("hbm_gbs"):
+                peak, peak_src = float(peaks["hbm_gbs"]), "measured"
+        except (OSError, ValueError):
+            pass
+        achieved = nframes * ENC_ALGO_BYTES_PER_FRAME / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+        print(json.dumps({
+            "metric": METRIC_ENC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16/int32 fixed point", "data": "synthetic", "config": workload_config(args),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "ac3_encode_kernel", "kernel_ms": kms,
+                         "kernel_launches_timed": kn, "algorithmic_bytes_per_launch": nframes * ENC_ALGO_BYTES_PER_FRAME},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_e2e(args, eng, dec, corpus, shard, barrier, world):
     import torch
     S, F = args.streams, args.frames
@@ -381,9 +554,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="decode", choices=["decode", "encode"],
+                    help="decode = BASELINE.json configs[1] (the headline metric); encode = configs[3]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "encode":
+        return run_gpu_encode(args)
     return run_gpu(args)
 
 
