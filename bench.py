@@ -354,7 +354,8 @@ def run_gpu(args):
         achieved = nframes * ALGO_BYTES_PER_FRAME / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            per_frame = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_frame")
+            traffic = per_frame * nframes if per_frame else None     # ncu dram bytes per frame x frames per launch
         except (OSError, ValueError):
             pass
         line = {
