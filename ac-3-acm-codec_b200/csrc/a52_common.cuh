@@ -87,6 +87,7 @@ struct DecodeParams {
     int             fbuf_bytes;      // bytes of the staged-frame buffer (multiple of 16)
     int             warp_bytes;      // shared-memory bytes per warp
     int             nplanes;         // coefficient planes per warp: 5, or 6 when the LFE is requested
+    int             group_threads;   // threads walking one stream: 32 (warp kernel) or 64 (pair kernel)
     // optional dumps
     uint8_t*        dbg_exp;
     uint8_t*        dbg_bap;

@@ -616,12 +616,12 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         bool same = (ns == c->plan_nseg);
         for (int k = 0; k < ns; k++) same = same && (c->seg[k].count == c->plan_count[k]);
         if (!same) {
-            uint32_t K = (flat + 31) >> 5;
+            uint32_t K = (flat + P.group_threads - 1) / P.group_threads;
             if (K < 1) K = 1;
             for (;; K++) {
                 uint32_t lanes = 0;
                 for (int k = 0; k < ns; k++) lanes += (c->seg[k].count + K - 1) / K;
-                if (lanes <= 32) break;
+                if (lanes <= (uint32_t)P.group_threads) break;
             }
             uint32_t l0 = 0;
             for (int k = 0; k < ns; k++) {
@@ -726,8 +726,15 @@ __device__ __forceinline__ void alloc_range(const GroupCtl* c, int a, int& start
 //   3. masking curve   lanes = (array, band)
 //   4. bap lookup      lanes = bins
 // psd / mask scratch: int16 [7][50] each.
+struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+struct PairSync {                        // two warps of one stream: named barrier, 64 threads
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+};
+
+template <int NT, class Sync>
 __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t todo, const uint8_t* exp_all,
-                                   uint8_t* bap_all, int16_t* psd_all, int16_t* mask_all, int lane)
+                                   uint8_t* bap_all, int16_t* psd_all, int16_t* mask_all, int lane, Sync sync)
 {
     // compact list of the arrays to do, 3 bits each
     uint32_t act = 0;
@@ -736,7 +743,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
     const int half = c->halfrate;
 
     // ---- 1a. single-bin bands (0..27) ----
-    for (int t = lane; t < na * 28; t += 32) {
+    for (int t = lane; t < na * 28; t += NT) {
         const int j = t / 28, band = t - j * 28;
         const int a = (act >> (3 * j)) & 7;
         int start, end;
@@ -748,7 +755,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
     for (int cls = 0; cls < 4; cls++) {
         const int fb = (cls == 0) ? 28 : (cls == 1) ? 35 : (cls == 2) ? 41 : 45;
         const int nb = (cls == 0) ? 7 : (cls == 1) ? 6 : (cls == 2) ? 4 : 5;
-        for (int t0 = 0; t0 < na * nb; t0 += 32) {
+        for (int t0 = 0; t0 < na * nb; t0 += NT) {
             const int t = t0 + lane;
             int b0 = 0, b1 = 0, a = 0, band = 0;
             if (t < na * nb) {
@@ -772,7 +779,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
             }
         }
     }
-    __syncwarp();
+    sync();
 
     // ---- 2. excitation (serial recurrences), result left in mask[] ----
     if (lane < na) {
@@ -827,7 +834,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
             mask[band] = max(fastleak, slowleak);
         }
     }
-    __syncwarp();
+    sync();
 
     // ---- 3. masking curve, delta, snr offset (per band) ----
     {
@@ -836,7 +843,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
         const int floorv = c_floor[bai & 7];
         const int csnr = c->csnroffst;
         const uint16_t* hth = T.hth + c->fscod * 50;
-        for (int t = lane; t < na * 50; t += 32) {
+        for (int t = lane; t < na * 50; t += NT) {
             const int j = t / 50, band = t - j * 50;
             const int a = (act >> (3 * j)) & 7;
             int start, end;
@@ -856,7 +863,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
             mask_all[a * 50 + band] = (int16_t)(v + floorv);
         }
     }
-    __syncwarp();
+    sync();
 
     // ---- 4. pointer lookup per bin ----
     for (int j = 0; j < na; j++) {
@@ -866,7 +873,7 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
         const uint8_t* e = exp_all + a * 256;
         const int16_t* mask = mask_all + a * 50;
         uint8_t* bap = bap_all + a * 256;
-        for (int bin = start + lane; bin < end; bin += 32) {
+        for (int bin = start + lane; bin < end; bin += NT) {
             const int p = 3072 - (e[bin] << 7);
             int q = (p - mask[T.masktab[bin]]) >> 5;
             q = min(max(q, 0), 63);
@@ -947,13 +954,13 @@ __device__ __forceinline__ uint32_t peek_nz(const uint32_t* w, uint32_t pos, uin
 }
 
 // 3-, 5- and 11-level groups: one lane per group code (parse.c:368-421)
-template <int PER, int WBITS, int QSTRIDE>
+template <int PER, int WBITS, int QSTRIDE, int NT = 32>
 __device__ __forceinline__ void unpack_groups(const WarpPtrs& G, const uint32_t* W, uint32_t base, uint32_t n,
                                               const int16_t* qtab, int lane)
 {
     uint32_t* planeU = reinterpret_cast<uint32_t*>(G.plane);
     const uint32_t ng = (n + PER - 1) / PER;
-    for (uint32_t g = lane; g < ng; g += 32) {
+    for (uint32_t g = lane; g < ng; g += NT) {
         const uint32_t k0 = g * PER;
         uint32_t slot[PER], d[PER];
 #pragma unroll
@@ -972,7 +979,7 @@ __device__ __forceinline__ void unpack_groups(const WarpPtrs& G, const uint32_t*
 }
 
 // coefficient-domain downmix: out[o] = sum over coded channels of wg[o][ch] * in[ch]
-template <int NM>
+template <int NM, int NT = 32>
 __device__ __forceinline__ void mix_planes(float* plane, const GroupCtl* c, int lane)
 {
     float wg[NM][5];
@@ -981,7 +988,7 @@ __device__ __forceinline__ void mix_planes(float* plane, const GroupCtl* c, int 
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) wg[o][ch] = c->wt[o][ch] * c->gain[ch];
 #pragma unroll 2
-    for (int bin = lane; bin < 256; bin += 32) {
+    for (int bin = lane; bin < 256; bin += NT) {
         float in[5], acc[NM];
 #pragma unroll
         for (int ch = 0; ch < 5; ch++) in[ch] = plane[ch * 256 + bin];       // planes past nfchans are zero
@@ -1339,7 +1346,7 @@ a52_decode_kernel(const DecodeParams P)
                     } else {
                         // psd / mask scratch lives in the work-list area (not in use before the locate stage)
                         int16_t* scratch = reinterpret_cast<int16_t*>(G.list);
-                        bit_allocate_block(T, c, c->do_alloc, G.exp, G.bap, scratch, scratch + 7 * 50, lane);
+                        bit_allocate_block<32>(T, c, c->do_alloc, G.exp, G.bap, scratch, scratch + 7 * 50, lane, WarpSync());
                     }
                     __syncwarp();
                 }
@@ -1787,6 +1794,541 @@ a52_decode_kernel(const DecodeParams P)
             }
         }
         __syncwarp();
+    }
+}
+
+
+// ===========================================================================
+// The pair kernel: TWO warps (64 threads) walk one stream.  Same stages as the warp kernel
+// above; the two warps split every lane loop, meet at a 64-thread named barrier, keep the
+// overlap tails in shared memory and exchange scan totals through the control block.  For the
+// same shared memory per stream this doubles the resident warps of an SM.
+// ===========================================================================
+struct PairPtrs : WarpPtrs {
+    float*    delay;   // [nplanes][128] overlap-add tails
+    uint32_t* xch;     // [2][8] scan totals of the two warps
+};
+
+__host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
+{
+    return warp_smem_bytes(fbuf_bytes, nplanes) + nplanes * 128 * 4 + 64;
+}
+
+__device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes)
+{
+    PairPtrs g;
+    static_cast<WarpPtrs&>(g) = carve(base, fbuf_bytes, nplanes);
+    uint8_t* p = reinterpret_cast<uint8_t*>(g.mbar) + 16;
+    g.delay = reinterpret_cast<float*>(p);   p += nplanes * 128 * 4;
+    g.xch = reinterpret_cast<uint32_t*>(p);
+    return g;
+}
+
+constexpr int kMaxPairsPerCta = 12;
+
+__global__ void __launch_bounds__(kMaxPairsPerCta * 64, 1)
+a52_decode_pair_kernel(const DecodeParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    Tables& T = *reinterpret_cast<Tables*>(smem);
+    const int tid = threadIdx.x;
+    const int pair = tid >> 6, gt = tid & 63, w = gt >> 5, lane = tid & 31;
+    constexpr int NT = 64;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+        for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    PairPtrs G = carve_pair(smem + align16((int)sizeof(Tables)) + pair * P.warp_bytes, P.fbuf_bytes, P.nplanes);
+    GroupCtl* c = G.ctl;
+    uint32_t* const W = G.fbuf;
+    uint32_t* const planeU = reinterpret_cast<uint32_t*>(G.plane);
+    const PairSync sync{pair + 1};
+    if (gt == 0) {
+        mbar_init(G.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = gt; i < (int)(sizeof(GroupCtl) / 4); i += NT) reinterpret_cast<uint32_t*>(c)[i] = 0;
+    for (int i = gt; i < 7 * 256 * 2 / 4; i += NT) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
+    __syncthreads();
+    uint32_t tab_base;
+    asm volatile("mov.u32 %0, %1;" : "=r"(tab_base) : "r"(smem_u32(&T)));
+    uint32_t phase = 0;
+    const int ndelay = P.nplanes;            // tails: planes 0..4 main, 5 LFE
+
+    for (;;) {
+        if (gt == 0) c->stream = atomicAdd(P.work_counter, 1);
+        sync();
+        const int s = c->stream;
+        if (s >= P.nstreams) break;
+        const uint32_t f0 = P.stream_first[s], f1 = P.stream_first[s + 1];
+        uint32_t dither_index = 0;
+        if (P.carry) {
+            dither_index = P.carry[s].dither_index % kDitherPeriod;
+            if (gt == 0) c->per_channel = (P.carry[s].per_channel != 0);
+            for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = P.carry[s].delay[i >> 7][i & 127];
+        } else {
+            if (gt == 0) c->per_channel = 0;
+            for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = 0.f;
+        }
+        if (gt == 0 && f0 < f1) issue_frame_load(P, G, f0);
+        sync();
+
+        for (uint32_t f = f0; f < f1; f++) {
+            const uint64_t off = P.frame_off[f];
+            bool next_issued = false;
+            mbar_wait(G.mbar, phase);
+            phase ^= 1;
+            for (int i = gt; i < P.fbuf_bytes / 4; i += NT) W[i] = __byte_perm(W[i], 0, 0x0123);
+            sync();
+            if (gt == 0) {
+                uint32_t base_bit = (uint32_t)(off & 15) * 8;
+                uint32_t avail = P.fbuf_bytes - 16 - (uint32_t)(off & 15);
+                {
+                    uint64_t nxt = P.frame_off[f + 1];
+                    uint64_t end = (nxt > off) ? nxt : P.es_bytes;
+                    if (end - off < avail) avail = (uint32_t)(end - off);
+                }
+                c->base_bit = base_bit;
+                int st = parse_frame_header(c, W, base_bit, P, avail);
+                c->frame_ok = (st == 0);
+                c->err = st;
+                if (P.frame_flags) P.frame_flags[f] = st ? 0 : c->output;
+            }
+            sync();
+            int frame_status = c->err;
+            const bool frame_ok = c->frame_ok;
+            uint8_t* out_frame = P.pcm + (size_t)f * P.frame_stride;
+            if (frame_ok) {
+                uint32_t lim = c->limit_bit;
+                for (uint32_t i = (lim >> 5) + gt; i < (uint32_t)P.fbuf_bytes / 4; i += NT) {
+                    if (i == (lim >> 5)) {
+                        uint32_t keep = lim & 31;
+                        W[i] = keep ? (W[i] & (0xffffffffu << (32 - keep))) : 0;
+                    } else W[i] = 0;
+                }
+                sync();
+            }
+
+            int blk = 0;
+            for (; blk < 6 && frame_ok; blk++) {
+                // dither states of this block's first rows (row r of the zero list goes to warp r & 1);
+                // requested early so that the L2 latency hides behind the side information
+                uint32_t ring = P.dither_seq[(dither_index + 1 + 32 * w + lane) % kDitherPeriod];
+                // ================= P =================
+                if (gt == 0) c->err = parse_block(c, W, P);
+                sync();
+                if (c->err) break;
+                const int nfchans = c->nfchans;
+                const uint32_t chincpl = c->chincpl;
+                const uint32_t limit = c->limit_bit;
+
+                // ================= E =================
+                {
+                    int bad = 0, k = 0;
+                    for (int a = 0; a < 7; a++) {
+                        if (!c->expstr[a]) continue;
+                        if ((k++ & 1) != w) continue;
+                        uint8_t* e = G.exp + a * 256;
+                        int dst = (a == 6) ? c->cplstrtmant : 1;
+                        if (a != 6 && lane == 0) e[0] = c->exp_abs[a];
+                        bad |= decode_exponents(W, limit, e + dst, c->expstr[a], c->exp_ngrp[a],
+                                                c->exp_pos[a], c->exp_abs[a], lane);
+                    }
+                    if (bad && lane == 0) c->err = 1;
+                    sync();
+                    if (c->err) break;
+                }
+
+                // ================= B =================
+                if (c->do_alloc) {
+                    if (c->zero_alloc) {
+                        for (int a = 0; a < 7; a++)
+                            if ((c->do_alloc >> a) & 1) reinterpret_cast<uint32_t*>(G.bap + a * 256)[gt] = 0;
+                    } else {
+                        int16_t* scratch = reinterpret_cast<int16_t*>(G.list);
+                        bit_allocate_block<NT>(T, c, c->do_alloc, G.exp, G.bap, scratch, scratch + 7 * 50, gt, sync);
+                    }
+                    sync();
+                }
+
+                // ================= L =================
+                for (int i = gt; i < P.nplanes * 256 / 4; i += NT)
+                    reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
+                const uint32_t K = c->plan_K;
+                const uint32_t cpl_dith = chincpl & c->dithflag;
+                const uint32_t ncpl_dith = __popc(cpl_dith);
+                const int nseg = c->nseg;
+                uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
+                bool mute = false;
+                {
+                    int sgi = -1;
+                    for (int k = 0; k < nseg; k++)
+                        if (gt >= c->plan_lane0[k] && gt < c->plan_lane0[k + 1]) sgi = k;
+                    if (sgi >= 0) {
+                        const Segment sg = c->seg[sgi];
+                        const uint32_t o = (gt - c->plan_lane0[sgi]) * K;
+                        run_idx = sg.arr * 256 + sg.start + o;
+                        run_slot = sg.plane * 256 + sg.start + o;
+                        run_n = min(K, (uint32_t)sg.count - o);
+                        zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : ((c->dithflag >> sg.arr) & 1u);
+                        mute = (sg.arr == 5) && !c->out_lfe;
+                    }
+                }
+                uint32_t cnt = 0, fz = 0;
+                const uint32_t cnt_lut_addr = tab_base + (uint32_t)offsetof(Tables, cnt_lut);
+#pragma unroll 4
+                for (uint32_t k = 0; k < K; k++) {
+                    const uint32_t b = (k < run_n) ? (uint32_t)G.bap[run_idx + k] : 16u;
+                    const uint2 l = lds_v2(cnt_lut_addr + b * 8);
+                    cnt += l.x;
+                    fz += l.y;
+                }
+                const uint32_t fixed = fz & 0xffff;
+                const uint32_t nz = (fz >> 16) * (zmode == 2 ? ncpl_dith : zmode);
+                const uint32_t n1 = cnt & 0xff, n2 = (cnt >> 8) & 0xff, n4 = (cnt >> 16) & 0xff, np = cnt >> 24;
+                const uint32_t pa = mute ? 0u : (n1 | (n2 << 16)), pb = mute ? 0u : (n4 | (np << 16));
+                uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
+                uint32_t iz = warp_incl_scan(nz, lane);
+                if (lane == 31) { G.xch[w * 8 + 0] = ia; G.xch[w * 8 + 1] = ib; G.xch[w * 8 + 2] = iz; }
+                sync();
+                const uint32_t ta = G.xch[0] + G.xch[8], tb = G.xch[1] + G.xch[9], tz = G.xch[2] + G.xch[10];
+                if (w) { ia += G.xch[0]; ib += G.xch[1]; iz += G.xch[2]; }
+                const uint32_t e1 = (ia - pa) & 0xffff, e2 = (ia - pa) >> 16;
+                const uint32_t e4 = (ib - pb) & 0xffff, ep = (ib - pb) >> 16, ez = iz - nz;
+                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
+                const uint32_t p1 = e1 % 3, p2 = e2 % 3, p4 = e4 & 1;
+                const uint32_t s1 = (p1 + n1 + 2) / 3 - (p1 != 0);
+                const uint32_t s2 = (p2 + n2 + 2) / 3 - (p2 != 0);
+                const uint32_t s4 = (p4 + n4 + 1) / 2 - (p4 != 0);
+                const uint32_t mybits = fixed + 5 * s1 + 7 * (s2 + s4);
+                uint32_t ibits = warp_incl_scan(mybits, lane);
+                if (lane == 31) G.xch[w * 8 + 3] = ibits;
+                sync();
+                const uint32_t mant_bits = G.xch[3] + G.xch[11];
+                if (w) ibits += G.xch[3];
+                const uint32_t bitpos = c->bitpos;
+                const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
+                {
+                    uint32_t pos = min(bitpos + ibits - mybits, limit);
+                    const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
+                    const uint32_t base_z = LZ + ez;
+                    const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);
+                    uint32_t run_a = 0, run_z = 0;
+                    const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
+                    const uint32_t zrow = (zmode == 1) ? 16u : 0u;
+                    const uint32_t emit_bit = mute ? 0u : 0x1000000u;
+                    uint32_t b = G.bap[run_idx], e = G.exp[run_idx];
+                    uint4 L = lds_v4(lut_addr + (run_n ? (b + zrow) : 0u) * 16);
+                    for (uint32_t k = 0; k < K; k++) {
+                        const bool valid = k < run_n;
+                        const uint32_t slot = run_slot + k;
+                        const uint32_t bn = G.bap[run_idx + k + 1], en = G.exp[run_idx + k + 1];
+                        const uint4 Ln = lds_v4(lut_addr + ((k + 1 < run_n) ? (bn + zrow) : 0u) * 16);
+                        if (zmode == 2 && b == 0 && valid) {
+                            uint32_t m = cpl_dith;
+                            while (m) {
+                                const uint32_t ch = __ffs(m) - 1;
+                                m &= m - 1;
+                                const uint32_t s2 = ch * 256 + (slot & 255);
+                                G.list[base_z + run_z] = (uint16_t)s2;
+                                run_z++;
+                                planeU[s2] = e;
+                            }
+                        } else {
+                            const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
+                            const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
+                            const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
+                            const uint32_t per = prmt(L.w, 0, 0x4442);
+                            const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
+                            run_a += L.x;
+                            run_z += L.w >> 24;
+                            if (L.y & emit_bit) {
+                                G.list[li] = (uint16_t)slot;
+                                planeU[slot] = make_desc(e, b, pos);
+                            }
+                            pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
+                        }
+                        b = bn;
+                        e = en;
+                        L = Ln;
+                    }
+                }
+                sync();
+                if (gt == 0) c->bitpos = bitpos + mant_bits;
+
+                // ================= U =================
+                if (tz) {
+                    // rows of 32 zeros alternate between the warps; a warp's states advance 64 steps per own row
+                    for (uint32_t r0 = 32 * w; r0 < tz; r0 += 64) {
+                        const uint32_t k = r0 + lane;
+                        if (k < tz) {
+                            const uint32_t slot = G.list[LZ + k];
+                            const uint32_t e = planeU[slot];
+                            const int dv = (3 * (int)(int16_t)ring) >> 2;
+                            G.plane[slot] = (float)dv * pow2neg(15 + e);
+                        }
+                        ring = lfsr_jump32(tab_base, lfsr_jump32(tab_base, ring));
+                    }
+                    dither_index = (dither_index + tz) % kDitherPeriod;
+                }
+                if (t1) unpack_groups<3, 5, 32, NT>(G, W, 0, t1, &T.q1[0][0], gt);
+                if (t2) unpack_groups<3, 7, 128, NT>(G, W, L2, t2, &T.q2[0][0], gt);
+                if (t4) unpack_groups<2, 7, 128, NT>(G, W, L4, t4, &T.q4[0][0], gt);
+                for (uint32_t k = gt; k < tp; k += NT) {
+                    const uint32_t slot = G.list[LP + k];
+                    const uint32_t d = planeU[slot];
+                    const uint32_t b = (d >> 5) & 15;
+                    const uint32_t wbits = T.bap_bits[b];
+                    const uint32_t raw = peek_nz(W, (d >> 10) & 0x7fff, wbits);
+                    int q = ((int)(raw << (32 - wbits))) >> 16;
+                    if (b <= 5) q = T.q35[(b & 4) * 2 + raw];
+                    G.plane[slot] = (float)q * pow2neg(15 + (d & 31));
+                }
+                sync();
+                if (blk == 5 && f + 1 < f1) {
+                    if (gt == 0) issue_frame_load(P, G, f + 1);
+                    next_issued = true;
+                }
+
+                const bool unif = c->uniform_path;
+                if (!unif) {
+                    for (int ch = 0; ch < nfchans; ch++) {
+                        const float g1 = c->gain[ch];
+                        const int end = c->endmant[ch];
+                        for (int bin = gt; bin < end; bin += NT) G.plane[ch * 256 + bin] *= g1;
+                    }
+                }
+                if (c->out_lfe && gt < 7) G.plane[5 * 256 + gt] *= c->gain[5];
+                sync();
+                if (chincpl) {
+                    const int first = __ffs(chincpl) - 1;
+                    for (int bin = c->cplstrtmant + gt; bin < c->cplendmant; bin += NT) {
+                        int sub = (bin - c->cplstrtmant) / 12;
+                        int bnd = sub - __popc(c->cplbndstrc & ((1u << sub) - 1));
+                        bool zero_bap = (G.bap[6 * 256 + bin] == 0);
+                        float cv = G.plane[first * 256 + bin];
+                        for (int ch = nfchans - 1; ch >= 0; ch--) {
+                            if (!((chincpl >> ch) & 1)) continue;
+                            float co = unif ? c->cplco[ch][bnd] : c->cplco[ch][bnd] * c->gain[ch];
+                            float src = zero_bap ? G.plane[ch * 256 + bin] : cv;
+                            G.plane[ch * 256 + bin] = src * co;
+                        }
+                    }
+                    sync();
+                }
+                if (c->acmod == 2 && c->rematflg) {
+                    int end = min(c->endmant[0], c->endmant[1]);
+                    for (int bin = 13 + gt; bin < end; bin += NT) {
+                        int band = (bin >= 61) ? 3 : (bin >= 37) ? 2 : (bin >= 25) ? 1 : 0;
+                        if ((c->rematflg >> band) & 1) {
+                            float a = G.plane[bin], b = G.plane[256 + bin];
+                            G.plane[bin] = a + b;
+                            G.plane[256 + bin] = a - b;
+                        }
+                    }
+                    sync();
+                }
+                if (P.dbg_exp) {
+                    size_t o = ((size_t)f * 6 + blk) * 7 * 256;
+                    for (int i = gt; i < 7 * 256; i += NT) {
+                        P.dbg_exp[o + i] = G.exp[i];
+                        P.dbg_bap[o + i] = G.bap[i];
+                    }
+                }
+                if (P.dbg_coef) {
+                    size_t o = ((size_t)f * 6 + blk) * 6 * 256;
+                    for (int i = gt; i < 6 * 256; i += NT) {
+                        int pl = i >> 8;
+                        bool live = (pl < nfchans) || (pl == 5 && c->out_lfe);
+                        float v = live ? G.plane[i] : 0.f;
+                        if (unif && pl < 5) v *= c->gain[pl];
+                        P.dbg_coef[o + i] = v;
+                    }
+                }
+                if (P.dbg_info && gt == 0) {
+                    int32_t* o = P.dbg_info + ((size_t)f * 6 + blk) * 16;
+                    for (int i = 0; i < 5; i++) o[i] = c->endmant[i];
+                    o[5] = c->cplstrtmant; o[6] = c->cplendmant; o[7] = c->chincpl;
+                    o[8] = P.dither_seq[dither_index]; o[9] = c->acmod; o[10] = c->lfeon;
+                    o[11] = c->output;
+                    o[12] = c->blksw | (c->uniform_path << 8) | ((c->clev == 0.f) << 9) | ((c->slev == 0.f) << 10);
+                    o[13] = c->ncplbnd; o[14] = c->rematflg;
+                    o[15] = c->csnroffst;
+                }
+
+                // ================= M =================
+                const int nmain = c->nout;
+                const bool uniform = c->uniform_path;
+                const int lfe_on = c->out_lfe;
+                if (uniform) {
+                    switch (nmain) {
+                    case 1: mix_planes<1, NT>(G.plane, c, gt); break;
+                    case 2: mix_planes<2, NT>(G.plane, c, gt); break;
+                    case 3: mix_planes<3, NT>(G.plane, c, gt); break;
+                    default: mix_planes<4, NT>(G.plane, c, gt); break;
+                    }
+                    sync();
+                }
+
+                // ================= T: planes alternate between the warps =================
+                {
+                    const int ntr = uniform ? nmain : nfchans;
+                    int job = 0;
+                    for (int pl = 0; pl < 6; pl++) {
+                        if (pl < 5 ? (pl >= ntr) : !lfe_on) continue;
+                        if (!uniform && pl < 5 && c->gain[pl] == 0.f) continue;
+                        if ((job++ & 1) != w) continue;
+                        bool shortblk = (pl < 5) && ((c->blksw >> (uniform ? 0 : pl)) & 1);
+                        if (shortblk) imdct256_warp(T, G.plane + pl * 256, lane);
+                        else imdct512_warp(T, G.plane + pl * 256, lane);
+                    }
+                }
+                sync();
+
+                // ================= O =================
+                // thread q = gt owns positions p = 2q, 2q+1 (and their mirrors 254-p, 255-p) of every plane
+                {
+                    const int nout = nmain + lfe_on;
+                    const float bias = P.bias;
+                    const bool identity = c->identity_mix;
+                    const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
+                    const float2* win2 = reinterpret_cast<const float2*>(T.window);
+                    float2* delay2 = reinterpret_cast<float2*>(G.delay);
+                    const int q = gt;
+                    if (uniform && c->per_channel) {
+                        // a52_downmix on the per-channel tails; zero-gain channels are left out
+                        float2 d[5], m[5];
+#pragma unroll
+                        for (int ch = 0; ch < 5; ch++)
+                            d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? delay2[ch * 64 + q] : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int o = 0; o < 5; o++) {
+                            float ax = 0.f, ay = 0.f;
+#pragma unroll
+                            for (int ch = 0; ch < 5; ch++) { ax = fmaf(c->wt[o][ch], d[ch].x, ax); ay = fmaf(c->wt[o][ch], d[ch].y, ay); }
+                            m[o] = make_float2(ax, ay);
+                        }
+#pragma unroll
+                        for (int o = 0; o < 5; o++)
+                            if (o < nmain) delay2[o * 64 + q] = m[o];
+                    } else if (!uniform && !c->per_channel) {
+                        // a52_upmix: downmixed tails go back to the coded channels they belong to
+                        const MixEntry mx = c_mix[c->acmod * 11 + (c->output & M_MASK)];
+                        float2 m[5];
+#pragma unroll
+                        for (int o = 0; o < 5; o++) m[o] = delay2[o * 64 + q];
+#pragma unroll
+                        for (int ch = 0; ch < 5; ch++) {
+                            if (ch < nfchans) {
+                                float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+                                for (int o = 0; o < 5; o++)
+                                    if (mx.up[ch] == o) v = m[o];
+                                delay2[ch * 64 + q] = v;
+                            }
+                        }
+                    }
+                    const float2 wl = win2[q], wh = win2[127 - q];      // (w[p], w[p+1]), (w[254-p], w[255-p])
+                    float y[6][4];                                       // [output][p, p+1, 254-p, 255-p]
+#pragma unroll
+                    for (int o = 0; o < 6; o++)
+#pragma unroll
+                        for (int r = 0; r < 4; r++) y[o][r] = 0.f;
+#pragma unroll
+                    for (int pl = 0; pl < 6; pl++) {
+                        const bool is_lfe = (pl == 5);
+                        bool live;
+                        if (is_lfe) live = lfe_on;
+                        else if (uniform) live = pl < nmain;
+                        else live = pl < nfchans && c->gain[pl] != 0.f;
+                        if (!live) continue;
+                        const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
+                        const float2 D = delay2[pl * 64 + q];
+                        const float a0 = D.x * wh.y - U.x * wl.x;        // sample p
+                        const float a1 = D.y * wh.x - U.y * wl.y;        // sample p + 1
+                        const float b0 = D.x * wl.x + U.x * wh.y;        // sample 255 - p
+                        const float b1 = D.y * wl.y + U.y * wh.x;        // sample 254 - p
+                        delay2[pl * 64 + q] = V;
+                        if (is_lfe) {
+                            y[0][0] = a0; y[0][1] = a1; y[0][2] = b1; y[0][3] = b0;
+                        } else if (uniform || identity) {
+#pragma unroll
+                            for (int oo = 0; oo < 6; oo++)
+                                if (oo == pl + lfe_on) { y[oo][0] = a0; y[oo][1] = a1; y[oo][2] = b1; y[oo][3] = b0; }
+                        } else {
+#pragma unroll
+                            for (int o = 0; o < 5; o++) {
+                                const float wgt = c->wt[o][pl];
+#pragma unroll
+                                for (int oo = 0; oo < 6; oo++)
+                                    if (o < nmain && oo == o + lfe_on) {
+                                        y[oo][0] = fmaf(wgt, a0, y[oo][0]);
+                                        y[oo][1] = fmaf(wgt, a1, y[oo][1]);
+                                        y[oo][2] = fmaf(wgt, b1, y[oo][2]);
+                                        y[oo][3] = fmaf(wgt, b0, y[oo][3]);
+                                    }
+                            }
+                        }
+                    }
+                    const int p = 2 * q;
+                    if (P.out_fmt == 1 && nout == 2) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
+                        dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
+                        dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+                    } else {
+#pragma unroll
+                        for (int oc = 0; oc < 6; oc++) {
+                            if (oc >= nout) continue;
+                            const float v0 = y[oc][0], v1 = y[oc][1], v2 = y[oc][2], v3 = y[oc][3];
+                            if (P.out_fmt == 0) {
+                                float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
+                                *reinterpret_cast<float2*>(dst + p) = make_float2(v0 + bias, v1 + bias);
+                                *reinterpret_cast<float2*>(dst + 254 - p) = make_float2(v2 + bias, v3 + bias);
+                            } else if (P.out_fmt == 1) {
+                                float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
+                                dst[p * nout + oc] = v0 + bias;
+                                dst[(p + 1) * nout + oc] = v1 + bias;
+                                dst[(254 - p) * nout + oc] = v2 + bias;
+                                dst[(255 - p) * nout + oc] = v3 + bias;
+                            } else {
+                                int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
+                                dst[p * nout + oc] = (int16_t)min(max(__float2int_rn(v0 * 32768.f), -32768), 32767);
+                                dst[(p + 1) * nout + oc] = (int16_t)min(max(__float2int_rn(v1 * 32768.f), -32768), 32767);
+                                dst[(254 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v2 * 32768.f), -32768), 32767);
+                                dst[(255 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v3 * 32768.f), -32768), 32767);
+                            }
+                        }
+                    }
+                }
+                sync();
+                if (gt == 0) c->per_channel = uniform ? 0 : 1;
+                sync();
+            }   // blocks
+
+            if (frame_ok && blk < 6) frame_status = 16 + blk;
+            if (frame_status) {
+                int nout = frame_ok ? (c->nout + c->out_lfe) : P.nout_req;
+                int ssz = (P.out_fmt == 2) ? 2 : 4;
+                size_t from = (size_t)blk * 256 * nout * ssz;
+                size_t to = (size_t)6 * 256 * nout * ssz;
+                for (size_t i = from + gt * 4; i < to; i += NT * 4)
+                    *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
+            }
+            if (gt == 0 && P.status) P.status[f] = frame_status;
+            sync();
+            if (!next_issued && f + 1 < f1 && gt == 0) issue_frame_load(P, G, f + 1);
+            sync();
+        }   // frames
+
+        if (P.carry) {
+            for (int i = gt; i < ndelay * 128; i += NT) P.carry[s].delay[i >> 7][i & 127] = G.delay[i];
+            if (gt == 0) {
+                P.carry[s].dither_index = dither_index;
+                P.carry[s].per_channel = c->per_channel;
+            }
+        }
+        sync();
     }
 }
 

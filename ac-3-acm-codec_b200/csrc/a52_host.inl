@@ -302,6 +302,7 @@ struct a52_batch_s {
     int device = 0;
     int num_sms = 0;
     int warps_per_cta = 0;         // 0 = as many as fit
+    int pair_kernel = 1;           // two warps per stream (default) or one
     int max_frame_hint = 0;
     uint16_t* d_dither = nullptr;
     int* d_counter = nullptr;      // [0..31] work counters (one per pipelined chunk), [63] max frame length
@@ -357,6 +358,8 @@ a52_batch_t* a52_batch_create(int device)
     ctx->num_sms = prop.multiProcessorCount;
     const char* g = getenv("A52_B200_WARPS_PER_CTA");
     if (g) ctx->warps_per_cta = atoi(g);
+    const char* pk = getenv("A52_B200_PAIR");
+    if (pk) ctx->pair_kernel = atoi(pk) != 0;
 
     // constant tables
     a52::Tables* T = new a52::Tables;
@@ -377,6 +380,8 @@ a52_batch_t* a52_batch_create(int device)
     ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(a52::a52_decode_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024) == cudaSuccess;
     if (!ok) {
         a52_batch_destroy(ctx);
@@ -471,14 +476,17 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     if (max_frame_bytes > 3840) max_frame_bytes = 3840;
     P.fbuf_bytes = align16(max_frame_bytes + 15) + 16 + 16;
     P.nplanes = (P.req_flags & M_LFE) ? 6 : 5;
-    P.warp_bytes = warp_smem_bytes(P.fbuf_bytes, P.nplanes);
+    const bool pair = ctx->pair_kernel != 0;
+    P.group_threads = pair ? 64 : 32;
+    P.warp_bytes = pair ? pair_smem_bytes(P.fbuf_bytes, P.nplanes) : warp_smem_bytes(P.fbuf_bytes, P.nplanes);
     P.dither_seq = ctx->d_dither;
     P.work_counter = ctx->d_counter + counter_slot;
     const int tables = align16((int)sizeof(Tables));
     int fit = (227 * 1024 - tables) / P.warp_bytes;
-    if (fit > kMaxWarpsPerCta) fit = kMaxWarpsPerCta;
+    const int fit_max = pair ? kMaxPairsPerCta : kMaxWarpsPerCta;
+    if (fit > fit_max) fit = fit_max;
     if (fit < 1) {
-        snprintf(ctx->err, sizeof(ctx->err), "decode kernel does not fit: %d bytes of shared memory per warp", P.warp_bytes);
+        snprintf(ctx->err, sizeof(ctx->err), "decode kernel does not fit: %d bytes of shared memory per stream", P.warp_bytes);
         return -2;
     }
     int G = fit;
@@ -486,7 +494,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     // small batches: spread the streams over all SMs
     int per_sm = (P.nstreams + ctx->num_sms - 1) / ctx->num_sms;
     if (per_sm < G) G = per_sm < 1 ? 1 : per_sm;
-    const int threads = G * 32;
+    const int threads = G * P.group_threads;
     const size_t smem = (size_t)tables + (size_t)G * P.warp_bytes;
     int grid = (P.nstreams + G - 1) / G;
     if (grid > ctx->num_sms) grid = ctx->num_sms;
@@ -507,7 +515,8 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used], e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
     A52_CUDA(cudaEventRecord(e0, st));
-    a52_decode_kernel<<<grid, threads, smem, st>>>(P);
+    if (pair) a52_decode_pair_kernel<<<grid, threads, smem, st>>>(P);
+    else a52_decode_kernel<<<grid, threads, smem, st>>>(P);
     A52_CUDA(cudaEventRecord(e1, st));
     A52_CUDA(cudaGetLastError());
     ctx->launches++;
