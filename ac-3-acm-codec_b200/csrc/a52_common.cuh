@@ -36,6 +36,7 @@ struct __align__(16) Tables {
     uint16_t jump_hi[256];     // dither generator advanced 32 steps: contribution of the high byte
     uint16_t jump_lo[256];     //                                      and of the low byte
     uint2    cnt_lut[18];      // per bap: x = n1 | n2 << 8 | n4 << 16 | nplain << 24, y = plain field bits | zero << 16
+    uint32_t cnt_lut32[20];    // per bap: 5-bit counters n1 | n2 << 5 | n4 << 10 | zero << 15, plain field bits << 20
     uint4    emit_lut[32];     // per bap (+16: bap-0 mantissas of this run are dithered), see build_tables()
     uint16_t hth[3 * 50];
     uint8_t  masktab[256];

@@ -616,9 +616,9 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         bool same = (ns == c->plan_nseg);
         for (int k = 0; k < ns; k++) same = same && (c->seg[k].count == c->plan_count[k]);
         if (!same) {
-            uint32_t K = (flat + P.group_threads - 1) / P.group_threads;
-            if (K < 1) K = 1;
-            for (;; K++) {
+            // K odd: consecutive lanes then write their descriptors to different shared-memory banks
+            uint32_t K = ((flat + P.group_threads - 1) / P.group_threads) | 1;
+            for (;; K += 2) {
                 uint32_t lanes = 0;
                 for (int k = 0; k < ns; k++) lanes += (c->seg[k].count + K - 1) / K;
                 if (lanes <= (uint32_t)P.group_threads) break;
@@ -1975,18 +1975,33 @@ a52_decode_pair_kernel(const DecodeParams P)
                         mute = (sg.arr == 5) && !c->out_lfe;
                     }
                 }
-                uint32_t cnt = 0, fz = 0;
-                const uint32_t cnt_lut_addr = tab_base + (uint32_t)offsetof(Tables, cnt_lut);
-#pragma unroll 4
-                for (uint32_t k = 0; k < K; k++) {
-                    const uint32_t b = (k < run_n) ? (uint32_t)G.bap[run_idx + k] : 16u;
-                    const uint2 l = lds_v2(cnt_lut_addr + b * 8);
-                    cnt += l.x;
-                    fz += l.y;
+                // pass 1: class counts of my run.  The bap bytes are fetched a 32-bit word at a time (runs
+                // start at any byte: each word is funnelled together with its predecessor); one 32-bit LUT
+                // word per bap carries 5-bit counters (3-, 5-, 11-level, zero) and the plain field bits.
+                const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
+                const uint32_t* expw = reinterpret_cast<const uint32_t*>(G.exp);
+                const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
+                uint32_t cnt = 0;
+                {
+                    const uint32_t lut32 = tab_base + (uint32_t)offsetof(Tables, cnt_lut32);
+                    uint32_t wlo = bapw[wi0];
+                    for (uint32_t k = 0, j = 1; k < K; k += 4, j++) {
+                        const uint32_t whi = bapw[wi0 + j];
+                        const uint32_t v = __funnelshift_r(wlo, whi, bsh);
+                        wlo = whi;
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const uint32_t b = (k + t < run_n) ? ((v >> (8 * t)) & 0xff) : 16u;
+                            uint32_t l;
+                            asm("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(lut32 + b * 4));
+                            cnt += l;
+                        }
+                    }
                 }
-                const uint32_t fixed = fz & 0xffff;
-                const uint32_t nz = (fz >> 16) * (zmode == 2 ? ncpl_dith : zmode);
-                const uint32_t n1 = cnt & 0xff, n2 = (cnt >> 8) & 0xff, n4 = (cnt >> 16) & 0xff, np = cnt >> 24;
+                const uint32_t n1 = cnt & 31, n2 = (cnt >> 5) & 31, n4 = (cnt >> 10) & 31, n0 = (cnt >> 15) & 31;
+                const uint32_t fixed = cnt >> 20;
+                const uint32_t np = run_n - n1 - n2 - n4 - n0;
+                const uint32_t nz = n0 * (zmode == 2 ? ncpl_dith : zmode);
                 const uint32_t pa = mute ? 0u : (n1 | (n2 << 16)), pb = mute ? 0u : (n4 | (np << 16));
                 uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
                 uint32_t iz = warp_incl_scan(nz, lane);
@@ -2018,12 +2033,25 @@ a52_decode_pair_kernel(const DecodeParams P)
                     const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
                     const uint32_t zrow = (zmode == 1) ? 16u : 0u;
                     const uint32_t emit_bit = mute ? 0u : 0x1000000u;
-                    uint32_t b = G.bap[run_idx], e = G.exp[run_idx];
+                    // bap / exponent bytes four at a time (funnelled words, as in pass 1), one mantissa ahead
+                    uint32_t bw_lo = bapw[wi0], ew_lo = expw[wi0];
+                    uint32_t bw_hi = bapw[wi0 + 1], ew_hi = expw[wi0 + 1];
+                    uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
+                    uint32_t b = bv & 0xff, e = ev & 0xff;
                     uint4 L = lds_v4(lut_addr + (run_n ? (b + zrow) : 0u) * 16);
                     for (uint32_t k = 0; k < K; k++) {
                         const bool valid = k < run_n;
                         const uint32_t slot = run_slot + k;
-                        const uint32_t bn = G.bap[run_idx + k + 1], en = G.exp[run_idx + k + 1];
+                        // next mantissa's bytes: byte (k + 1) & 3 of the current funnelled words
+                        if (((k + 1) & 3) == 0) {
+                            const uint32_t j = ((k + 1) >> 2) + 1;
+                            bw_lo = bw_hi; ew_lo = ew_hi;
+                            bw_hi = bapw[wi0 + j]; ew_hi = expw[wi0 + j];
+                            bv = __funnelshift_r(bw_lo, bw_hi, bsh);
+                            ev = __funnelshift_r(ew_lo, ew_hi, bsh);
+                        }
+                        const uint32_t sh8 = 8 * ((k + 1) & 3);
+                        const uint32_t bn = (bv >> sh8) & 0xff, en = (ev >> sh8) & 0xff;
                         const uint4 Ln = lds_v4(lut_addr + ((k + 1 < run_n) ? (bn + zrow) : 0u) * 16);
                         if (zmode == 2 && b == 0 && valid) {
                             uint32_t m = cpl_dith;

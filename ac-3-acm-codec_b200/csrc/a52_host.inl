@@ -242,6 +242,8 @@ static void build_tables(Tables* T)
         else if (b != 0) { x = 1u << 24; y = ac3_bap_bits[b]; }
         else y = 1u << 16;
         T->cnt_lut[b] = make_uint2(x, y);
+        T->cnt_lut32[b] = (b == 1 ? 1u : 0u) | (b == 2 ? 1u << 5 : 0u) | (b == 4 ? 1u << 10 : 0u) | (b == 0 ? 1u << 15 : 0u) |
+                          ((b != 0 && b != 1 && b != 2 && b != 4) ? (uint32_t)ac3_bap_bits[b] << 20 : 0u);
     }
     // emit_lut: how pass 2 of the locate stage treats a mantissa of a given bap.
     //   classes: 0 = 3-level groups, 1 = 5-level, 2 = 11-level, 3 = plain fields, 4 = dithered zero
