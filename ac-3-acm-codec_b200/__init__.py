@@ -26,7 +26,7 @@ _NFCH = [2, 1, 2, 3, 3, 4, 4, 5, 1, 1, 2]
 EXPORTS = [
     "a52_init", "a52_samples", "a52_syncinfo", "a52_frame", "a52_dynrng", "a52_block", "a52_free",
     "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index",
-    "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes",
+    "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes", "a52_batch_set_max_stream_frames",
     "a52_batch_launch_count", "a52_batch_kernel_ms",
     "AC3_encode_init", "AC3_encode_frame",
     "ac3_batch_create", "ac3_batch_destroy", "ac3_batch_last_error", "ac3_batch_frame_bytes",
@@ -68,6 +68,7 @@ def load_library():
     L.a52_batch_frame_stride.restype = C.c_size_t
     L.a52_batch_frame_stride.argtypes = [C.c_int, C.c_int]
     L.a52_batch_set_max_frame_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.a52_batch_set_max_stream_frames.argtypes = [C.c_void_p, C.c_int]
     L.a52_batch_launch_count.restype = C.c_long
     L.a52_batch_launch_count.argtypes = [C.c_void_p]
     L.a52_batch_kernel_ms.restype = C.c_double
@@ -203,6 +204,9 @@ class BatchDecoder:
 
     def set_max_frame_bytes(self, n):
         self.L.a52_batch_set_max_frame_bytes(self.ctx, n)
+
+    def set_max_stream_frames(self, n):
+        self.L.a52_batch_set_max_stream_frames(self.ctx, n)
 
     def launch_count(self):
         return self.L.a52_batch_launch_count(self.ctx)

@@ -89,6 +89,10 @@ struct DecodeParams {
     int             warp_bytes;      // shared-memory bytes per warp
     int             nplanes;         // coefficient planes per warp: 5, or 6 when the LFE is requested
     int             group_threads;   // threads walking one stream: 32 (warp kernel) or 64 (pair kernel)
+    int             slice_frames;    // pair kernel: frames per work unit
+    int             nslices;         // pair kernel: work units per stream (1 = whole streams)
+    int             carry_init;      // carry[] holds the caller's initial state (else streams start fresh)
+    int*            slice_done;      // [nstreams] slices completed per stream
     // optional dumps
     uint8_t*        dbg_exp;
     uint8_t*        dbg_bap;

@@ -1856,17 +1856,37 @@ a52_decode_pair_kernel(const DecodeParams P)
     uint32_t phase = 0;
     const int ndelay = P.nplanes;            // tails: planes 0..4 main, 5 LFE
 
+    // Work units are SLICES of streams (P.slice_frames frames), handed out slice-major from one ticket
+    // counter: all first slices, then all second slices, ...  A slice starts from the carry record its
+    // predecessor left in global memory; the predecessor holds a smaller ticket, so it is already running
+    // on some resident CTA (the grid never exceeds the SM count) and the wait below cannot deadlock.
+    // Slicing keeps the last wave of a batch short: the tail of a launch is one slice, not one stream.
+    const uint32_t nunits = (uint32_t)P.nstreams * (uint32_t)P.nslices;
     for (;;) {
         if (gt == 0) c->stream = atomicAdd(P.work_counter, 1);
         sync();
-        const int s = c->stream;
-        if (s >= P.nstreams) break;
-        const uint32_t f0 = P.stream_first[s], f1 = P.stream_first[s + 1];
+        const uint32_t ticket = (uint32_t)c->stream;
+        if (ticket >= nunits) break;
+        const uint32_t slice = ticket / (uint32_t)P.nstreams;
+        const int s = (int)(ticket - slice * (uint32_t)P.nstreams);
+        const uint32_t fs0 = P.stream_first[s], fs1 = P.stream_first[s + 1];
+        uint32_t f0 = fs0 + slice * (uint32_t)P.slice_frames;
+        if (f0 > fs1) f0 = fs1;
+        const uint32_t f1 = (P.nslices > 1 && fs1 - f0 > (uint32_t)P.slice_frames) ? f0 + P.slice_frames : fs1;
+        if (slice > 0) {
+            if (gt == 0) {
+                volatile int* done = P.slice_done + s;
+                while (*done < (int)slice) __nanosleep(200);
+                __threadfence();
+            }
+            sync();
+        }
+        const bool have_state = P.carry && (slice > 0 || P.carry_init);
         uint32_t dither_index = 0;
-        if (P.carry) {
-            dither_index = P.carry[s].dither_index % kDitherPeriod;
-            if (gt == 0) c->per_channel = (P.carry[s].per_channel != 0);
-            for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = P.carry[s].delay[i >> 7][i & 127];
+        if (have_state) {
+            dither_index = __ldcg(&P.carry[s].dither_index) % kDitherPeriod;
+            if (gt == 0) c->per_channel = (__ldcg(&P.carry[s].per_channel) != 0);
+            for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = __ldcg(&P.carry[s].delay[i >> 7][i & 127]);
         } else {
             if (gt == 0) c->per_channel = 0;
             for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = 0.f;
@@ -2355,6 +2375,11 @@ a52_decode_pair_kernel(const DecodeParams P)
                 P.carry[s].dither_index = dither_index;
                 P.carry[s].per_channel = c->per_channel;
             }
+        }
+        if (P.nslices > 1) {
+            __threadfence();
+            sync();
+            if (gt == 0) atomicExch(P.slice_done + s, (int)slice + 1);
         }
         sync();
     }

@@ -295,6 +295,15 @@ __global__ void a52_maxlen_kernel(const uint8_t* es, const uint64_t* off, int nf
     if ((threadIdx.x & 31) == 0 && len) atomicMax(out, len);
 }
 
+// longest stream (frames) of a device-resident batch
+__global__ void a52_maxstream_kernel(const uint32_t* first, int nstreams, int* out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (i < nstreams) ? (int)(first[i + 1] - first[i]) : 0;
+    for (int o = 16; o; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+    if ((threadIdx.x & 31) == 0 && n) atomicMax(out, n);
+}
+
 }  // namespace a52
 
 // ---------------------------------------------------------------------------
@@ -306,6 +315,8 @@ struct a52_batch_s {
     int warps_per_cta = 0;         // 0 = as many as fit
     int pair_kernel = 1;           // two warps per stream (default) or one
     int max_frame_hint = 0;
+    int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
+    int slice_frames = 32;         // pair kernel: frames per work unit
     uint16_t* d_dither = nullptr;
     int* d_counter = nullptr;      // [0..31] work counters (one per pipelined chunk), [63] max frame length
     cudaStream_t s_in = nullptr, s_out = nullptr, s_run = nullptr;   // host-mode pipeline: H2D, D2H, kernels
@@ -320,7 +331,7 @@ struct a52_batch_s {
     float mode_level = 0;
     // host-mode scratch
     struct Buf { void* p = nullptr; size_t cap = 0; } b_es, b_off, b_first, b_pcm, b_status, b_flags,
-        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo;
+        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo, b_slice, b_done;
 };
 
 #define A52_CUDA(call)                                                                       \
@@ -362,6 +373,8 @@ a52_batch_t* a52_batch_create(int device)
     if (g) ctx->warps_per_cta = atoi(g);
     const char* pk = getenv("A52_B200_PAIR");
     if (pk) ctx->pair_kernel = atoi(pk) != 0;
+    const char* sf = getenv("A52_B200_SLICE_FRAMES");
+    if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
 
     // constant tables
     a52::Tables* T = new a52::Tables;
@@ -398,7 +411,7 @@ void a52_batch_destroy(a52_batch_t* ctx)
     cudaSetDevice(ctx->device);
     a52_batch_s::Buf* bufs[] = {&ctx->b_es, &ctx->b_off, &ctx->b_first, &ctx->b_pcm, &ctx->b_status,
                                 &ctx->b_flags, &ctx->b_carry, &ctx->b_dexp, &ctx->b_dbap, &ctx->b_dcoef,
-                                &ctx->b_dinfo};
+                                &ctx->b_dinfo, &ctx->b_slice, &ctx->b_done};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_dither) cudaFree(ctx->d_dither);
@@ -440,6 +453,8 @@ size_t a52_batch_frame_stride(int req_flags, int out_fmt)
 
 void a52_batch_set_max_frame_bytes(a52_batch_t* ctx, int nbytes) { ctx->max_frame_hint = nbytes; }
 
+void a52_batch_set_max_stream_frames(a52_batch_t* ctx, int nframes) { ctx->max_stream_hint = nframes; }
+
 long a52_batch_launch_count(a52_batch_t* ctx) { return ctx->launches; }
 
 double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
@@ -461,9 +476,24 @@ double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
 }
 
 static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int max_frame_bytes,
-                         float level, cudaStream_t st, int counter_slot = 0)
+                         float level, cudaStream_t st, int counter_slot = 0, int max_stream_frames = 0)
 {
     using namespace a52;
+    // work units of the pair kernel: slices of streams (see a52_decode_pair_kernel)
+    P.slice_frames = ctx->slice_frames;
+    P.nslices = 1;
+    P.carry_init = P.carry != nullptr;
+    P.slice_done = nullptr;
+    if (ctx->pair_kernel && max_stream_frames > ctx->slice_frames) {
+        P.nslices = (max_stream_frames + ctx->slice_frames - 1) / ctx->slice_frames;
+        if (ensure(ctx, ctx->b_done, (size_t)P.nstreams * sizeof(int))) return -1;
+        A52_CUDA(cudaMemsetAsync(ctx->b_done.p, 0, (size_t)P.nstreams * sizeof(int), st));
+        P.slice_done = (int*)ctx->b_done.p;
+        if (!P.carry) {
+            if (ensure(ctx, ctx->b_slice, (size_t)P.nstreams * sizeof(StreamCarry))) return -1;
+            P.carry = (StreamCarry*)ctx->b_slice.p;
+        }
+    }
     // per-request constants
     if (ctx->mode_flags != P.req_flags || ctx->mode_level != level) {
         ModeEntry tab[9 * 16];
@@ -568,6 +598,14 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         P.frame_flags = frame_flags;
         P.carry = (StreamCarry*)carry;
         if (debug) { P.dbg_exp = debug->exp; P.dbg_bap = debug->bap; P.dbg_coef = debug->coef; P.dbg_info = debug->info; }
+        int maxstream = ctx->max_stream_hint;
+        if (maxstream <= 0 && ctx->pair_kernel) {
+            A52_CUDA(cudaMemsetAsync(ctx->d_counter + 62, 0, sizeof(int), st));
+            a52_maxstream_kernel<<<(nstreams + 255) / 256, 256, 0, st>>>(stream_first, nstreams, ctx->d_counter + 62);
+            A52_CUDA(cudaMemcpyAsync(&maxstream, ctx->d_counter + 62, sizeof(int), cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaStreamSynchronize(st));
+            ctx->launches++;
+        }
         int maxlen = ctx->max_frame_hint;
         if (maxlen <= 0) {
             A52_CUDA(cudaMemsetAsync(ctx->d_counter + 63, 0, sizeof(int), st));
@@ -576,7 +614,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             A52_CUDA(cudaStreamSynchronize(st));
             ctx->launches++;
         }
-        return launch_decode(ctx, P, nframes, maxlen, level, st);
+        return launch_decode(ctx, P, nframes, maxlen, level, st, 0, maxstream);
     }
 
     // ---- host pointers: stage in, decode, stage out (synchronous for the caller) ----
@@ -688,7 +726,12 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         Pc.stream_first = (const uint32_t*)ctx->b_first.p + s0;
         Pc.nstreams = s1 - s0;
         Pc.carry = carry ? (StreamCarry*)ctx->b_carry.p + s0 : nullptr;
-        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_run, cidx);
+        int chunk_max = 0;
+        for (int q = s0; q < s1; q++) {
+            int n = (int)(stream_first[q + 1] - stream_first[q]);
+            if (n > chunk_max) chunk_max = n;
+        }
+        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_run, cidx, chunk_max);
         if (rc) return rc;
         A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_run));
         A52_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_run[cidx], 0));

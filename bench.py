@@ -291,6 +291,7 @@ def run_gpu(args):
 
     dec = eng.BatchDecoder(local)
     dec.set_max_frame_bytes(FRAME_BYTES)
+    dec.set_max_stream_frames(F)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():

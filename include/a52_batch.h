@@ -110,6 +110,10 @@ int a52_batch_decode (a52_batch_t * ctx,
  * device-pointer calls need no length pre-pass; 0 = derive it (default). */
 void a52_batch_set_max_frame_bytes (a52_batch_t * ctx, int nbytes);
 
+/* Optional: frames of the longest stream in the next batches, so that device-pointer calls need no
+ * pre-pass to plan the work units (slices of streams); 0 = derive it (default). */
+void a52_batch_set_max_stream_frames (a52_batch_t * ctx, int nframes);
+
 /* number of kernel launches issued by this context so far (bench bookkeeping) */
 long a52_batch_launch_count (a52_batch_t * ctx);
 /* average device time (ms) of the decode kernel over the launches since the

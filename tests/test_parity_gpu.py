@@ -249,6 +249,32 @@ def test_carry_split_equals_one_call(decoder, engine, oracle, c2):
     assert (got.view(np.uint32) == whole["pcm"].view(np.uint32)).all()
 
 
+def test_time_slicing_is_bit_identical(engine, c2):
+    """The kernel hands out slices of streams as work units (carry through global memory between
+    slices): any slice length must give the same bits as whole-stream units."""
+    import os
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    counts = [16, 5, 11, 1, 16, 7]
+    chunks, off, first, pos = [], [], [0], 0
+    for s, n in enumerate(counts):
+        fr = c2["frames"][s % 4, :n].reshape(-1)
+        chunks.append(fr)
+        off += [pos + 1792 * k for k in range(n)]
+        pos += len(fr)
+        first.append(first[-1] + n)
+    es = np.concatenate(chunks)
+    outs = []
+    for sl in ("1000", "3", "1"):
+        os.environ["A52_B200_SLICE_FRAMES"] = sl
+        dec = engine.BatchDecoder(0)
+        c0 = [engine.CarryStruct() for _ in counts] if sl == "3" else None
+        outs.append(dec.decode_host(es, np.array(off, np.uint64), np.array(first, np.uint32), flags, carry=c0)["pcm"])
+        dec.close()
+    del os.environ["A52_B200_SLICE_FRAMES"]
+    assert (outs[0].view(np.uint32) == outs[1].view(np.uint32)).all()
+    assert (outs[0].view(np.uint32) == outs[2].view(np.uint32)).all()
+
+
 def test_corrupted_frames_status_and_isolation(decoder, engine, oracle):
     """Same per-frame error returns as liba52; a bad frame does not poison other streams."""
     rng = np.random.RandomState(11)
