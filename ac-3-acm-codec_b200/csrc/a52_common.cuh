@@ -11,7 +11,6 @@
 
 namespace a52 {
 
-constexpr int kMaxWarpsPerCta = 16;  // one warp walks one stream; a CTA is just a bag of warps
 constexpr int kDitherPeriod = 65535;
 
 // output mode ids == liba52's A52_* flag values (include/a52.h)
@@ -35,7 +34,6 @@ struct __align__(16) Tables {
     uint16_t dither_lut[256];  // CRC-16/0xA011 byte step (tables.h:213-246)
     uint16_t jump_hi[256];     // dither generator advanced 32 steps: contribution of the high byte
     uint16_t jump_lo[256];     //                                      and of the low byte
-    uint2    cnt_lut[18];      // per bap: x = n1 | n2 << 8 | n4 << 16 | nplain << 24, y = plain field bits | zero << 16
     uint32_t cnt_lut32[20];    // per bap: 5-bit counters n1 | n2 << 5 | n4 << 10 | zero << 15, plain field bits << 20
     uint4    emit_lut[32];     // per bap (+16: bap-0 mantissas of this run are dithered), see build_tables()
     uint16_t hth[3 * 50];
@@ -88,7 +86,7 @@ struct DecodeParams {
     int             fbuf_bytes;      // bytes of the staged-frame buffer (multiple of 16)
     int             warp_bytes;      // shared-memory bytes per warp
     int             nplanes;         // coefficient planes per warp: 5, or 6 when the LFE is requested
-    int             group_threads;   // threads walking one stream: 32 (warp kernel) or 64 (pair kernel)
+    int             group_threads;   // threads walking one stream (64: a pair of warps)
     int             slice_frames;    // pair kernel: frames per work unit
     int             nslices;         // pair kernel: work units per stream (1 = whole streams)
     int             carry_init;      // carry[] holds the caller's initial state (else streams start fresh)

@@ -1,10 +1,11 @@
 // a52_decode.cu - batched AC-3 (ATSC A/52) decode for NVIDIA B200 (sm_100a).
 //
-// One persistent kernel decodes thousands of independent AC-3 streams.  One
-// WARP owns one stream at a time and walks its sync frames in order;
-// everything between the staged bitstream and the PCM store lives in that
-// warp's slice of shared memory and in registers, so the only CTA-wide
-// synchronisation is the one after the table load:
+// One persistent kernel decodes thousands of independent AC-3 streams.  A PAIR
+// of warps (64 threads) owns a slice of one stream at a time and walks its
+// sync frames in order; everything between the staged bitstream and the PCM
+// store lives in that pair's part of shared memory and in registers, so the
+// only CTA-wide synchronisation is the one after the table load (pairs meet
+// at their own named barrier):
 //
 //   stage   frame bytes  : TMA bulk copy (cp.async.bulk + mbarrier); the next frame is
 //                          requested as soon as the last block's mantissas are out
@@ -21,10 +22,10 @@
 //   imdct   512 / 2x256 transform: pre-twiddle, radix-4 FFT in shared memory,
 //           post-twiddle                        (imdct.c:258-345)
 //   ola     KBD window + overlap-add + PCM store (imdct.c:276-292); the overlap tails
-//           stay in registers from block to block and frame to frame
+//           stay in shared memory from block to block and frame to frame
 //
 // The dither generator position and the overlap tails enter and leave the call
-// through a52_stream_carry_t, so frames never wait on another warp.
+// (and pass from one slice of a stream to the next) through a52_stream_carry_t.
 //
 // Integer stages are bit-exact with liba52; the float transform uses a
 // different FFT factorisation (tolerance 1e-5 relative RMS, measured ~1e-7).
@@ -1196,613 +1197,12 @@ __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const Wa
     tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
 }
 
-static_assert(sizeof(GroupCtl) <= 1200, "GroupCtl grew: check the shared-memory budget per warp");
-
-__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
-a52_decode_kernel(const DecodeParams P)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    Tables& T = *reinterpret_cast<Tables*>(smem);
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    // tables: global -> shared, whole CTA
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
-        for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    WarpPtrs G = carve(smem + align16((int)sizeof(Tables)) + warp * P.warp_bytes, P.fbuf_bytes, P.nplanes);
-    GroupCtl* c = G.ctl;
-    uint32_t* const W = G.fbuf;
-    uint32_t* const planeU = reinterpret_cast<uint32_t*>(G.plane);
-    if (lane == 0) {
-        mbar_init(G.mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // zero persistent decoder state once (liba52 leaves it uninitialised; valid streams never read it)
-    for (int i = lane; i < (int)(sizeof(GroupCtl) / 4); i += 32) reinterpret_cast<uint32_t*>(c)[i] = 0;
-    for (int i = lane; i < 7 * 256 * 2 / 4; i += 32) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
-    __syncthreads();
-
-    // 32-bit shared address of the tables, made opaque so that it lives in a register instead of
-    // being rebuilt from the shared-window base inside the hot loops
-    uint32_t tab_base;
-    asm volatile("mov.u32 %0, %1;" : "=r"(tab_base) : "r"(smem_u32(&T)));
-    uint32_t phase = 0;
-    // overlap-add tails: dly[plane][r] <-> position p(r) = 64 (r >> 1) + 2 lane + (r & 1)
-    float dly[6][4];
-
-    for (;;) {
-        // ---- claim a stream ----
-        int s = 0;
-        if (lane == 0) s = atomicAdd(P.work_counter, 1);
-        s = __shfl_sync(0xffffffffu, s, 0);
-        if (s >= P.nstreams) break;
-        const uint32_t f0 = P.stream_first[s], f1 = P.stream_first[s + 1];
-
-        // carry in
-        uint32_t dither_index = 0;
-#pragma unroll
-        for (int o = 0; o < 6; o++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) dly[o][r] = 0.f;
-        if (P.carry) {
-            dither_index = P.carry[s].dither_index % kDitherPeriod;
-            if (lane == 0) c->per_channel = (P.carry[s].per_channel != 0);
-#pragma unroll
-            for (int o = 0; o < 6; o++)
-#pragma unroll
-                for (int jj = 0; jj < 2; jj++) {
-                    float2 v = reinterpret_cast<const float2*>(P.carry[s].delay[o])[32 * jj + lane];
-                    dly[o][2 * jj] = v.x;
-                    dly[o][2 * jj + 1] = v.y;
-                }
-        } else if (lane == 0) {
-            c->per_channel = 0;
-        }
-        // the next 32 dither generator states: ring (lane j) = state after dither_index + 1 + j steps
-        uint32_t ring = P.dither_seq[(dither_index + 1 + lane) % kDitherPeriod];
-
-        if (lane == 0 && f0 < f1) issue_frame_load(P, G, f0);
-        __syncwarp();
-
-        for (uint32_t f = f0; f < f1; f++) {
-            const uint64_t off = P.frame_off[f];
-            bool next_issued = false;
-            mbar_wait(G.mbar, phase);
-            phase ^= 1;
-            // big-endian bytes -> native words
-            for (int i = lane; i < P.fbuf_bytes / 4; i += 32) W[i] = __byte_perm(W[i], 0, 0x0123);
-            __syncwarp();
-
-            if (lane == 0) {
-                uint32_t base_bit = (uint32_t)(off & 15) * 8;
-                uint32_t avail = P.fbuf_bytes - 16 - (uint32_t)(off & 15);
-                // a frame never extends past the start of the next one / the end of the buffer
-                {
-                    uint64_t nxt = P.frame_off[f + 1];
-                    uint64_t end = (nxt > off) ? nxt : P.es_bytes;
-                    if (end - off < avail) avail = (uint32_t)(end - off);
-                }
-                c->base_bit = base_bit;
-                int st = parse_frame_header(c, W, base_bit, P, avail);
-                c->frame_ok = (st == 0);
-                c->err = st;
-                if (P.frame_flags) P.frame_flags[f] = st ? 0 : c->output;
-            }
-            __syncwarp();
-            int frame_status = c->err;            // 0, 1 (sync) or 2 (frame)
-            const bool frame_ok = c->frame_ok;
-            uint8_t* out_frame = P.pcm + (size_t)f * P.frame_stride;
-
-            if (frame_ok) {
-                // zero the bits past the frame end so that overruns read zeros
-                uint32_t lim = c->limit_bit;
-                for (uint32_t i = (lim >> 5) + lane; i < (uint32_t)P.fbuf_bytes / 4; i += 32) {
-                    if (i == (lim >> 5)) {
-                        uint32_t keep = lim & 31;
-                        W[i] = keep ? (W[i] & (0xffffffffu << (32 - keep))) : 0;
-                    } else W[i] = 0;
-                }
-                __syncwarp();
-            }
-
-            int blk = 0;
-            for (; blk < 6 && frame_ok; blk++) {
-                // ================= P: side info =================
-                if (lane == 0) c->err = parse_block(c, W, P);
-                __syncwarp();
-                if (c->err) break;
-                const int nfchans = c->nfchans;
-                const uint32_t chincpl = c->chincpl;
-                const uint32_t limit = c->limit_bit;
-
-                // ================= E: exponents =================
-                {
-                    int bad = 0;
-                    for (int a = 0; a < 7; a++) {
-                        if (!c->expstr[a]) continue;
-                        uint8_t* e = G.exp + a * 256;
-                        int dst = (a == 6) ? c->cplstrtmant : 1;
-                        if (a != 6 && lane == 0) e[0] = c->exp_abs[a];
-                        bad |= decode_exponents(W, limit, e + dst, c->expstr[a], c->exp_ngrp[a],
-                                                c->exp_pos[a], c->exp_abs[a], lane);
-                    }
-                    __syncwarp();
-                    if (bad) {
-                        if (lane == 0) c->err = 1;
-                        __syncwarp();
-                        break;
-                    }
-                }
-
-                // ================= B: bit allocation =================
-                if (c->do_alloc) {
-                    if (c->zero_alloc) {
-                        for (int a = 0; a < 7; a++)
-                            if ((c->do_alloc >> a) & 1)
-                                for (int i = lane; i < 64; i += 32) reinterpret_cast<uint32_t*>(G.bap + a * 256)[i] = 0;
-                    } else {
-                        // psd / mask scratch lives in the work-list area (not in use before the locate stage)
-                        int16_t* scratch = reinterpret_cast<int16_t*>(G.list);
-                        bit_allocate_block<32>(T, c, c->do_alloc, G.exp, G.bap, scratch, scratch + 7 * 50, lane, WarpSync());
-                    }
-                    __syncwarp();
-                }
-
-                // ================= L: locate =================
-                // planes start as zeros: bins past the coded range and undithered bap-0 bins stay zero
-                for (int i = lane; i < P.nplanes * 256 / 4; i += 32)
-                    reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
-                const uint32_t K = c->plan_K;
-                const uint32_t cpl_dith = chincpl & c->dithflag;
-                const uint32_t ncpl_dith = __popc(cpl_dith);
-                const int nseg = c->nseg;
-                // my run: n mantissas of segment sgi starting at offset o
-                uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
-                bool mute = false;          // LFE mantissas when the LFE is not an output: skipped, not stored
-                {
-                    int sgi = -1;
-                    for (int k = 0; k < nseg; k++)
-                        if (lane >= c->plan_lane0[k] && lane < c->plan_lane0[k + 1]) sgi = k;
-                    if (sgi >= 0) {
-                        const Segment sg = c->seg[sgi];
-                        const uint32_t o = (lane - c->plan_lane0[sgi]) * K;
-                        run_idx = sg.arr * 256 + sg.start + o;       // addresses exp[] (and bap[] = exp[] + 7*256)
-                        run_slot = sg.plane * 256 + sg.start + o;
-                        run_n = min(K, (uint32_t)sg.count - o);
-                        zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : ((c->dithflag >> sg.arr) & 1u);
-                        mute = (sg.arr == 5) && !c->out_lfe;
-                    }
-                }
-                // pass 1: class counts of my run (lock step; bins past my run read the all-zero LUT row)
-                uint32_t cnt = 0, fz = 0;
-                const uint32_t cnt_lut_addr = tab_base + (uint32_t)offsetof(Tables, cnt_lut);
-#pragma unroll 4
-                for (uint32_t k = 0; k < K; k++) {
-                    const uint32_t b = (k < run_n) ? (uint32_t)G.bap[run_idx + k] : 16u;
-                    const uint2 l = lds_v2(cnt_lut_addr + b * 8);
-                    cnt += l.x;
-                    fz += l.y;                                        // plain field bits | zero count << 16
-                }
-                const uint32_t fixed = fz & 0xffff;
-                const uint32_t nz = (fz >> 16) * (zmode == 2 ? ncpl_dith : zmode);
-                const uint32_t n1 = cnt & 0xff, n2 = (cnt >> 8) & 0xff, n4 = (cnt >> 16) & 0xff, np = cnt >> 24;
-                // (the LFE comes last in coded order, so leaving a muted run out of the list cursors
-                // only shortens the lists)
-                const uint32_t pa = mute ? 0u : (n1 | (n2 << 16)), pb = mute ? 0u : (n4 | (np << 16));
-                const uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
-                const uint32_t iz = warp_incl_scan(nz, lane);
-                const uint32_t ta = __shfl_sync(0xffffffffu, ia, 31), tb = __shfl_sync(0xffffffffu, ib, 31);
-                const uint32_t tz = __shfl_sync(0xffffffffu, iz, 31);
-                const uint32_t e1 = (ia - pa) & 0xffff, e2 = (ia - pa) >> 16;
-                const uint32_t e4 = (ib - pb) & 0xffff, ep = (ib - pb) >> 16, ez = iz - nz;
-                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
-                const uint32_t p1 = e1 % 3, p2 = e2 % 3, p4 = e4 & 1;
-                // group codes started inside my run
-                const uint32_t s1 = (p1 + n1 + 2) / 3 - (p1 != 0);
-                const uint32_t s2 = (p2 + n2 + 2) / 3 - (p2 != 0);
-                const uint32_t s4 = (p4 + n4 + 1) / 2 - (p4 != 0);
-                const uint32_t mybits = fixed + 5 * s1 + 7 * (s2 + s4);
-                const uint32_t ibits = warp_incl_scan(mybits, lane);
-                const uint32_t mant_bits = __shfl_sync(0xffffffffu, ibits, 31);
-                const uint32_t bitpos = c->bitpos;
-                // list layout: [class 1 | class 2 | class 4 | plain | dithered zeros]
-                const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
-
-                // pass 2: descriptors + work lists, branch-free: the class of a bap selects, through
-                // emit_lut, which list cursor moves and whether the mantissa starts a new field.
-                {
-                    uint32_t pos = min(bitpos + ibits - mybits, limit);
-                    const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
-                    const uint32_t base_z = LZ + ez;
-                    const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);   // group phase at my first mantissa
-                    uint32_t run_a = 0, run_z = 0;                         // entries emitted so far, a byte per class
-                    const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
-                    const uint32_t zrow = (zmode == 1) ? 16u : 0u;
-                    const uint32_t emit_bit = mute ? 0u : 0x1000000u;
-                    // software pipeline: the bap / exponent bytes of mantissa k+1 and its LUT row are
-                    // fetched before the stores of mantissa k (the compiler cannot hoist them itself:
-                    // byte loads may alias the list / descriptor stores)
-                    uint32_t b = G.bap[run_idx], e = G.exp[run_idx];
-                    uint4 L = lds_v4(lut_addr + (run_n ? (b + zrow) : 0u) * 16);
-                    for (uint32_t k = 0; k < K; k++) {
-                        const bool valid = k < run_n;
-                        const uint32_t slot = run_slot + k;
-                        const uint32_t bn = G.bap[run_idx + k + 1], en = G.exp[run_idx + k + 1];
-                        const uint4 Ln = lds_v4(lut_addr + ((k + 1 < run_n) ? (bn + zrow) : 0u) * 16);
-                        if (zmode == 2 && b == 0 && valid) {
-                            // one dither value per coupled channel, channel order (parse.c:466-481)
-                            uint32_t m = cpl_dith;
-                            while (m) {
-                                const uint32_t ch = __ffs(m) - 1;
-                                m &= m - 1;
-                                const uint32_t s2 = ch * 256 + (slot & 255);
-                                G.list[base_z + run_z] = (uint16_t)s2;
-                                run_z++;
-                                planeU[s2] = e;
-                            }
-                        } else {
-                            // bins past my run take the row of an undithered zero: nothing moves
-                            // x: cursor increment (classes 1, 2, 4, plain); y: base selector A | width << 16 |
-                            // emit << 24; z: base selector B | 256/period << 16; w: count selector |
-                            // period << 16 | zero-list increment << 24
-                            const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
-                            const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
-                            // starts a field / group code when (phase0 + occurrences so far) % period == 0
-                            const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
-                            const uint32_t per = prmt(L.w, 0, 0x4442);
-                            const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
-                            run_a += L.x;
-                            run_z += L.w >> 24;
-                            if (L.y & emit_bit) {
-                                G.list[li] = (uint16_t)slot;
-                                planeU[slot] = make_desc(e, b, pos);
-                            }
-                            pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
-                        }
-                        b = bn;
-                        e = en;
-                        L = Ln;
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) c->bitpos = bitpos + mant_bits;
-
-                // ================= U: unpack + dequantise, class by class =================
-                // dithered zeros: zero number k of the block takes the generator state dither_index + 1 + k
-                if (tz) {
-                    uint32_t ring_prev = ring;
-                    for (uint32_t r0 = 0; r0 < tz; r0 += 32) {
-                        const uint32_t k = r0 + lane;
-                        if (k < tz) {
-                            const uint32_t slot = G.list[LZ + k];
-                            const uint32_t e = planeU[slot];
-                            const int dv = (3 * (int)(int16_t)ring) >> 2;
-                            G.plane[slot] = (float)dv * pow2neg(15 + e);
-                        }
-                        ring_prev = ring;
-                        ring = lfsr_jump32(tab_base, ring);
-                    }
-                    const uint32_t back = (32 - (tz & 31)) & 31;
-                    const uint32_t a = __shfl_sync(0xffffffffu, ring, (lane - back) & 31);
-                    const uint32_t b = __shfl_sync(0xffffffffu, ring_prev, (lane - back) & 31);
-                    ring = ((uint32_t)lane >= back) ? a : b;
-                    dither_index = (dither_index + tz) % kDitherPeriod;
-                }
-                if (t1) unpack_groups<3, 5, 32>(G, W, 0, t1, &T.q1[0][0], lane);
-                if (t2) unpack_groups<3, 7, 128>(G, W, L2, t2, &T.q2[0][0], lane);
-                if (t4) unpack_groups<2, 7, 128>(G, W, L4, t4, &T.q4[0][0], lane);
-                for (uint32_t k = lane; k < tp; k += 32) {
-                    const uint32_t slot = G.list[LP + k];
-                    const uint32_t d = planeU[slot];
-                    const uint32_t b = (d >> 5) & 15;
-                    const uint32_t wbits = T.bap_bits[b];
-                    const uint32_t raw = peek_nz(W, (d >> 10) & 0x7fff, wbits);
-                    // 7- and 15-level fields go through tables, wider ones are two's complement
-                    int q = ((int)(raw << (32 - wbits))) >> 16;
-                    if (b <= 5) q = T.q35[(b & 4) * 2 + raw];     // q3 at [0..7], q5 at [8..23]
-                    G.plane[slot] = (float)q * pow2neg(15 + (d & 31));
-                }
-                __syncwarp();
-                // the staged frame is no longer needed after the last block's mantissas: fetch the next one
-                if (blk == 5 && f + 1 < f1) {
-                    if (lane == 0) issue_frame_load(P, G, f + 1);
-                    next_issued = true;
-                }
-
-                const bool unif = c->uniform_path;
-                // channel gains (downmix.c:162-330 folded into dequantisation by liba52, parse.c:347-348)
-                if (!unif) {
-                    for (int ch = 0; ch < nfchans; ch++) {
-                        const float g1 = c->gain[ch];
-                        const int end = c->endmant[ch];
-                        for (int bin = lane; bin < end; bin += 32) G.plane[ch * 256 + bin] *= g1;
-                    }
-                }
-                if (c->out_lfe && lane < 7) G.plane[5 * 256 + lane] *= c->gain[5];
-                __syncwarp();
-
-                // ================= C: coupling fan-out (parse.c:435-556) =================
-                if (chincpl) {
-                    const int first = __ffs(chincpl) - 1;
-                    for (int bin = c->cplstrtmant + lane; bin < c->cplendmant; bin += 32) {
-                        int sub = (bin - c->cplstrtmant) / 12;
-                        int bnd = sub - __popc(c->cplbndstrc & ((1u << sub) - 1));
-                        bool zero_bap = (G.bap[6 * 256 + bin] == 0);
-                        float cv = G.plane[first * 256 + bin];
-                        for (int ch = nfchans - 1; ch >= 0; ch--) {
-                            if (!((chincpl >> ch) & 1)) continue;
-                            // channel gain: here when channels are transformed one by one, in the mix
-                            // weights otherwise (parse.c:456-457: cplco * coeff[ch])
-                            float co = unif ? c->cplco[ch][bnd] : c->cplco[ch][bnd] * c->gain[ch];
-                            float src = zero_bap ? G.plane[ch * 256 + bin] : cv;
-                            G.plane[ch * 256 + bin] = src * co;
-                        }
-                    }
-                    __syncwarp();
-                }
-
-                // ================= rematrix (parse.c:837-865) =================
-                if (c->acmod == 2 && c->rematflg) {
-                    int end = min(c->endmant[0], c->endmant[1]);
-                    for (int bin = 13 + lane; bin < end; bin += 32) {
-                        int band = (bin >= 61) ? 3 : (bin >= 37) ? 2 : (bin >= 25) ? 1 : 0;
-                        if ((c->rematflg >> band) & 1) {
-                            float a = G.plane[bin], b = G.plane[256 + bin];
-                            G.plane[bin] = a + b;
-                            G.plane[256 + bin] = a - b;
-                        }
-                    }
-                    __syncwarp();
-                }
-
-                // ---- optional dumps ----
-                if (P.dbg_exp) {
-                    size_t o = ((size_t)f * 6 + blk) * 7 * 256;
-                    for (int i = lane; i < 7 * 256; i += 32) {
-                        P.dbg_exp[o + i] = G.exp[i];
-                        P.dbg_bap[o + i] = G.bap[i];
-                    }
-                }
-                if (P.dbg_coef) {
-                    size_t o = ((size_t)f * 6 + blk) * 6 * 256;
-                    for (int i = lane; i < 6 * 256; i += 32) {
-                        int pl = i >> 8;
-                        bool live = (pl < nfchans) || (pl == 5 && c->out_lfe);
-                        float v = live ? G.plane[i] : 0.f;
-                        if (unif && pl < 5) v *= c->gain[pl];
-                        P.dbg_coef[o + i] = v;
-                    }
-                }
-                if (P.dbg_info && lane == 0) {
-                    int32_t* o = P.dbg_info + ((size_t)f * 6 + blk) * 16;
-                    for (int i = 0; i < 5; i++) o[i] = c->endmant[i];
-                    o[5] = c->cplstrtmant; o[6] = c->cplendmant; o[7] = c->chincpl;
-                    o[8] = P.dither_seq[dither_index]; o[9] = c->acmod; o[10] = c->lfeon;
-                    o[11] = c->output;
-                    o[12] = c->blksw | (c->uniform_path << 8) | ((c->clev == 0.f) << 9) | ((c->slev == 0.f) << 10);
-                    o[13] = c->ncplbnd; o[14] = c->rematflg;
-                    o[15] = c->csnroffst;
-                }
-
-                // ================= M: coefficient-domain mix =================
-                const int nmain = c->nout;
-                const bool uniform = c->uniform_path;
-                const int lfe_on = c->out_lfe;
-                if (uniform) {
-                    switch (nmain) {
-                    case 1: mix_planes<1>(G.plane, c, lane); break;
-                    case 2: mix_planes<2>(G.plane, c, lane); break;
-                    case 3: mix_planes<3>(G.plane, c, lane); break;
-                    default: mix_planes<4>(G.plane, c, lane); break;
-                    }
-                    __syncwarp();
-                }
-
-                // ================= T: transforms =================
-                {
-                    const int ntr = uniform ? nmain : nfchans;
-                    for (int pl = 0; pl < 6; pl++) {
-                        if (pl < 5 ? (pl >= ntr) : !lfe_on) continue;
-                        if (!uniform && pl < 5 && c->gain[pl] == 0.f) continue;     // parse.c:897-909
-                        bool shortblk = (pl < 5) && ((c->blksw >> (uniform ? 0 : pl)) & 1);
-                        if (shortblk) imdct256_warp(T, G.plane + pl * 256, lane);
-                        else imdct512_warp(T, G.plane + pl * 256, lane);
-                    }
-                }
-                __syncwarp();
-
-                // ================= O: window + overlap-add (+ time-domain mix) + store ========
-                // The tails follow liba52's state machine (parse.c:881-937): after a block that mixed
-                // coefficients they hold the downmixed tail (planes 0..nout-1); after a block that
-                // transformed every coded channel they hold per-channel tails (planes 0..nfchans-1).
-                // Switching representation = a52_downmix / a52_upmix on the delay (downmix.c:480-685);
-                // a channel whose gain is zero keeps its tail untouched and unheard (parse.c:897-909).
-                {
-                    const int nout = nmain + lfe_on;
-                    const float bias = P.bias;
-                    const bool identity = c->identity_mix;
-                    const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
-                    const float2* win2 = reinterpret_cast<const float2*>(T.window);
-                    // y[oc][r]: r = 0,1 -> samples p, p+1 ; r = 2,3 -> samples 254-p, 255-p  (per jj)
-                    float y[2][6][4];
-#pragma unroll
-                    for (int jj = 0; jj < 2; jj++)
-#pragma unroll
-                        for (int o = 0; o < 6; o++)
-#pragma unroll
-                            for (int r = 0; r < 4; r++) y[jj][o][r] = 0.f;
-
-                    if (uniform && c->per_channel) {
-                        // a52_downmix on the per-channel tails; zero-gain channels are left out
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            float d[5], m[5];
-#pragma unroll
-                            for (int ch = 0; ch < 5; ch++)
-                                d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? dly[ch][r] : 0.f;
-#pragma unroll
-                            for (int o = 0; o < 5; o++) {
-                                float acc = 0.f;
-#pragma unroll
-                                for (int ch = 0; ch < 5; ch++) acc = fmaf(c->wt[o][ch], d[ch], acc);
-                                m[o] = acc;
-                            }
-#pragma unroll
-                            for (int o = 0; o < 5; o++)
-                                if (o < nmain) dly[o][r] = m[o];
-                        }
-                    } else if (!uniform && !c->per_channel) {
-                        // a52_upmix: downmixed tails go back to the coded channels they belong to
-                        const MixEntry mx = c_mix[c->acmod * 11 + (c->output & M_MASK)];
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            float m[5];
-#pragma unroll
-                            for (int o = 0; o < 5; o++) m[o] = dly[o][r];
-#pragma unroll
-                            for (int ch = 0; ch < 5; ch++) {
-                                if (ch < nfchans) {
-                                    float v = 0.f;
-#pragma unroll
-                                    for (int o = 0; o < 5; o++)
-                                        if (mx.up[ch] == o) v = m[o];
-                                    dly[ch][r] = v;
-                                }
-                            }
-                        }
-                    }
-
-#pragma unroll
-                    for (int pl = 0; pl < 6; pl++) {
-                        const bool is_lfe = (pl == 5);
-                        bool live;
-                        if (is_lfe) live = lfe_on;
-                        else if (uniform) live = pl < nmain;
-                        else live = pl < nfchans && c->gain[pl] != 0.f;
-                        if (!live) continue;
-#pragma unroll
-                        for (int jj = 0; jj < 2; jj++) {
-                            const int q = 32 * jj + lane;                    // float2 index: p = 2 q
-                            const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
-                            const float2 wl = win2[q], wh = win2[127 - q];  // (w[p], w[p+1]), (w[254-p], w[255-p])
-                            const float D0 = dly[pl][2 * jj], D1 = dly[pl][2 * jj + 1];
-                            const float a0 = D0 * wh.y - U.x * wl.x;        // sample p
-                            const float a1 = D1 * wh.x - U.y * wl.y;        // sample p + 1
-                            const float b0 = D0 * wl.x + U.x * wh.y;        // sample 255 - p
-                            const float b1 = D1 * wl.y + U.y * wh.x;        // sample 254 - p
-                            dly[pl][2 * jj] = V.x;
-                            dly[pl][2 * jj + 1] = V.y;
-                            if (is_lfe) {
-                                y[jj][0][0] = a0; y[jj][0][1] = a1; y[jj][0][2] = b1; y[jj][0][3] = b0;
-                            } else if (uniform || identity) {
-#pragma unroll
-                                for (int o = 0; o < 5; o++) {
-                                    if (o == pl) {
-#pragma unroll
-                                        for (int oo = 0; oo < 6; oo++)
-                                            if (oo == o + lfe_on) {
-                                                y[jj][oo][0] = a0; y[jj][oo][1] = a1; y[jj][oo][2] = b1; y[jj][oo][3] = b0;
-                                            }
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int o = 0; o < 5; o++) {
-                                    const float wgt = c->wt[o][pl];
-#pragma unroll
-                                    for (int oo = 0; oo < 6; oo++)
-                                        if (o < nmain && oo == o + lfe_on) {
-                                            y[jj][oo][0] = fmaf(wgt, a0, y[jj][oo][0]);
-                                            y[jj][oo][1] = fmaf(wgt, a1, y[jj][oo][1]);
-                                            y[jj][oo][2] = fmaf(wgt, b1, y[jj][oo][2]);
-                                            y[jj][oo][3] = fmaf(wgt, b0, y[jj][oo][3]);
-                                        }
-                                }
-                            }
-                        }
-                    }
-
-                    // stores: samples (p, p+1) and (254-p, 255-p), p = 2 (32 jj + lane)
-#pragma unroll
-                    for (int jj = 0; jj < 2; jj++) {
-                        const int p = 2 * (32 * jj + lane);
-                        if (P.out_fmt == 1 && nout == 2) {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
-                            dst[p >> 1] = make_float4(y[jj][0][0] + bias, y[jj][1][0] + bias, y[jj][0][1] + bias, y[jj][1][1] + bias);
-                            dst[(254 - p) >> 1] = make_float4(y[jj][0][2] + bias, y[jj][1][2] + bias, y[jj][0][3] + bias, y[jj][1][3] + bias);
-                        } else {
-#pragma unroll
-                            for (int oc = 0; oc < 6; oc++) {
-                                if (oc >= nout) continue;
-                                const float v0 = y[jj][oc][0], v1 = y[jj][oc][1], v2 = y[jj][oc][2], v3 = y[jj][oc][3];
-                                if (P.out_fmt == 0) {
-                                    float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
-                                    *reinterpret_cast<float2*>(dst + p) = make_float2(v0 + bias, v1 + bias);
-                                    *reinterpret_cast<float2*>(dst + 254 - p) = make_float2(v2 + bias, v3 + bias);
-                                } else if (P.out_fmt == 1) {
-                                    float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
-                                    dst[p * nout + oc] = v0 + bias;
-                                    dst[(p + 1) * nout + oc] = v1 + bias;
-                                    dst[(254 - p) * nout + oc] = v2 + bias;
-                                    dst[(255 - p) * nout + oc] = v3 + bias;
-                                } else {
-                                    int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
-                                    dst[p * nout + oc] = (int16_t)min(max(__float2int_rn(v0 * 32768.f), -32768), 32767);
-                                    dst[(p + 1) * nout + oc] = (int16_t)min(max(__float2int_rn(v1 * 32768.f), -32768), 32767);
-                                    dst[(254 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v2 * 32768.f), -32768), 32767);
-                                    dst[(255 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v3 * 32768.f), -32768), 32767);
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) c->per_channel = uniform ? 0 : 1;
-                __syncwarp();
-            }   // blocks
-
-            if (frame_ok && blk < 6) frame_status = 16 + blk;     // A52_ST_BAD_BLOCK + block
-            if (frame_status) {
-                // silence for everything not produced
-                int nout = frame_ok ? (c->nout + c->out_lfe) : P.nout_req;
-                int ssz = (P.out_fmt == 2) ? 2 : 4;
-                size_t from = (size_t)blk * 256 * nout * ssz;
-                size_t to = (size_t)6 * 256 * nout * ssz;
-                for (size_t i = from + lane * 4; i < to; i += 32 * 4)
-                    *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
-            }
-            if (lane == 0 && P.status) P.status[f] = frame_status;
-            __syncwarp();
-            if (!next_issued && f + 1 < f1 && lane == 0) issue_frame_load(P, G, f + 1);
-            __syncwarp();
-        }   // frames
-
-        // carry out
-        if (P.carry) {
-#pragma unroll
-            for (int o = 0; o < 6; o++)
-#pragma unroll
-                for (int jj = 0; jj < 2; jj++)
-                    reinterpret_cast<float2*>(P.carry[s].delay[o])[32 * jj + lane] =
-                        make_float2(dly[o][2 * jj], dly[o][2 * jj + 1]);
-            if (lane == 0) {
-                P.carry[s].dither_index = dither_index;
-                P.carry[s].per_channel = c->per_channel;
-            }
-        }
-        __syncwarp();
-    }
-}
-
+static_assert(sizeof(GroupCtl) <= 1200, "GroupCtl grew: check the shared-memory budget per stream");
 
 // ===========================================================================
-// The pair kernel: TWO warps (64 threads) walk one stream.  Same stages as the warp kernel
-// above; the two warps split every lane loop, meet at a 64-thread named barrier, keep the
-// overlap tails in shared memory and exchange scan totals through the control block.  For the
-// same shared memory per stream this doubles the resident warps of an SM.
+// The decode kernel: TWO warps (64 threads, a "pair") walk one stream.  The two warps split every
+// lane loop, meet at a 64-thread named barrier, keep the overlap tails in shared memory and
+// exchange scan totals through a few words of shared memory.
 // ===========================================================================
 struct PairPtrs : WarpPtrs {
     float*    delay;   // [nplanes][128] overlap-add tails

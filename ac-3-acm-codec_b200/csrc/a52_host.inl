@@ -235,13 +235,6 @@ static void build_tables(Tables* T)
         T->jump_lo[v] = lo;
     }
     for (int b = 0; b < 16; b++) {
-        uint32_t x = 0, y = 0;
-        if (b == 1) x = 1;
-        else if (b == 2) x = 1u << 8;
-        else if (b == 4) x = 1u << 16;
-        else if (b != 0) { x = 1u << 24; y = ac3_bap_bits[b]; }
-        else y = 1u << 16;
-        T->cnt_lut[b] = make_uint2(x, y);
         T->cnt_lut32[b] = (b == 1 ? 1u : 0u) | (b == 2 ? 1u << 5 : 0u) | (b == 4 ? 1u << 10 : 0u) | (b == 0 ? 1u << 15 : 0u) |
                           ((b != 0 && b != 1 && b != 2 && b != 4) ? (uint32_t)ac3_bap_bits[b] << 20 : 0u);
     }
@@ -313,7 +306,7 @@ struct a52_batch_s {
     int device = 0;
     int num_sms = 0;
     int warps_per_cta = 0;         // 0 = as many as fit
-    int pair_kernel = 1;           // two warps per stream (default) or one
+    int pair_kernel = 1;           // (kept for the launch arithmetic: two warps per stream)
     int max_frame_hint = 0;
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
@@ -371,8 +364,6 @@ a52_batch_t* a52_batch_create(int device)
     ctx->num_sms = prop.multiProcessorCount;
     const char* g = getenv("A52_B200_WARPS_PER_CTA");
     if (g) ctx->warps_per_cta = atoi(g);
-    const char* pk = getenv("A52_B200_PAIR");
-    if (pk) ctx->pair_kernel = atoi(pk) != 0;
     const char* sf = getenv("A52_B200_SLICE_FRAMES");
     if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
 
@@ -394,8 +385,6 @@ a52_batch_t* a52_batch_create(int device)
     ok = ok && cudaMalloc(&ctx->d_dither, seq.size() * 2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    227 * 1024) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(a52::a52_decode_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024) == cudaSuccess;
     if (!ok) {
@@ -515,7 +504,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.work_counter = ctx->d_counter + counter_slot;
     const int tables = align16((int)sizeof(Tables));
     int fit = (227 * 1024 - tables) / P.warp_bytes;
-    const int fit_max = pair ? kMaxPairsPerCta : kMaxWarpsPerCta;
+    const int fit_max = kMaxPairsPerCta;
     if (fit > fit_max) fit = fit_max;
     if (fit < 1) {
         snprintf(ctx->err, sizeof(ctx->err), "decode kernel does not fit: %d bytes of shared memory per stream", P.warp_bytes);
@@ -547,8 +536,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used], e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
     A52_CUDA(cudaEventRecord(e0, st));
-    if (pair) a52_decode_pair_kernel<<<grid, threads, smem, st>>>(P);
-    else a52_decode_kernel<<<grid, threads, smem, st>>>(P);
+    a52_decode_pair_kernel<<<grid, threads, smem, st>>>(P);
     A52_CUDA(cudaEventRecord(e1, st));
     A52_CUDA(cudaGetLastError());
     ctx->launches++;
