@@ -1031,6 +1031,14 @@ __device__ __forceinline__ void bfly4(float2& x0, float2& x1, float2& x2, float2
     x3 = csub(t1, t3);
 }
 
+// FFT scratch index -> shared-memory index.  The butterflies touch z at strides 32, 8, 2 and 1;
+// XOR-ing two higher index bits into bits 1..3 spreads every one of those access patterns over the
+// banks (64-bit accesses are served half a warp at a time).
+__device__ __forceinline__ int zsw(int i)
+{
+    return i ^ (((i >> 4) & 3) << 1) ^ (((i >> 5) & 1) << 3);
+}
+
 __device__ void imdct512_warp(const Tables& T, float* plane, int lane)
 {
     float2* z = reinterpret_cast<float2*>(plane);
@@ -1046,42 +1054,45 @@ __device__ void imdct512_warp(const Tables& T, float* plane, int lane)
     __syncwarp();
     // stage 1: radix 4, stride 32, twiddle W128^(lane p)
     bfly4(x[0], x[1], x[2], x[3]);
-    z[lane] = x[0];
-    z[lane + 32] = cmul(x[1], T.wfft[lane]);
-    z[lane + 64] = cmul(x[2], T.wfft[2 * lane]);
-    z[lane + 96] = cmul(x[3], T.wfft[(3 * lane) & 127]);
+    z[zsw(lane)] = x[0];
+    z[zsw(lane + 32)] = cmul(x[1], T.wfft[lane]);
+    z[zsw(lane + 64)] = cmul(x[2], T.wfft[2 * lane]);
+    z[zsw(lane + 96)] = cmul(x[3], T.wfft[(3 * lane) & 127]);
     __syncwarp();
     // stage 2: 4 blocks of 32, stride 8, twiddle W32^(j p) = W128^(4 j p)
     {
         int b = lane >> 3, j = lane & 7, base = b * 32 + j;
-        float2 y0 = z[base], y1 = z[base + 8], y2 = z[base + 16], y3 = z[base + 24];
+        const int i0 = zsw(base), i1 = zsw(base + 8), i2 = zsw(base + 16), i3 = zsw(base + 24);
+        float2 y0 = z[i0], y1 = z[i1], y2 = z[i2], y3 = z[i3];
         bfly4(y0, y1, y2, y3);
         __syncwarp();
-        z[base] = y0;
-        z[base + 8] = cmul(y1, T.wfft[4 * j]);
-        z[base + 16] = cmul(y2, T.wfft[8 * j]);
-        z[base + 24] = cmul(y3, T.wfft[12 * j]);
+        z[i0] = y0;
+        z[i1] = cmul(y1, T.wfft[4 * j]);
+        z[i2] = cmul(y2, T.wfft[8 * j]);
+        z[i3] = cmul(y3, T.wfft[12 * j]);
     }
     __syncwarp();
     // stage 3: 16 blocks of 8, stride 2, twiddle W8^(j p) = W128^(16 j p)
     {
         int b = lane >> 1, j = lane & 1, base = b * 8 + j;
-        float2 y0 = z[base], y1 = z[base + 2], y2 = z[base + 4], y3 = z[base + 6];
+        const int i0 = zsw(base), i1 = zsw(base + 2), i2 = zsw(base + 4), i3 = zsw(base + 6);
+        float2 y0 = z[i0], y1 = z[i1], y2 = z[i2], y3 = z[i3];
         bfly4(y0, y1, y2, y3);
         __syncwarp();
-        z[base] = y0;
-        z[base + 2] = cmul(y1, T.wfft[16 * j]);
-        z[base + 4] = cmul(y2, T.wfft[32 * j]);
-        z[base + 6] = cmul(y3, T.wfft[48 * j]);
+        z[i0] = y0;
+        z[i1] = cmul(y1, T.wfft[16 * j]);
+        z[i2] = cmul(y2, T.wfft[32 * j]);
+        z[i3] = cmul(y3, T.wfft[48 * j]);
     }
     __syncwarp();
     // stage 4: radix 2 on adjacent pairs
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         int u = lane + 32 * r;
-        float2 a = z[2 * u], b = z[2 * u + 1];
-        z[2 * u] = cadd(a, b);
-        z[2 * u + 1] = csub(a, b);
+        const int ia = zsw(2 * u), ib = zsw(2 * u + 1);
+        float2 a = z[ia], b = z[ib];
+        z[ia] = cadd(a, b);
+        z[ib] = csub(a, b);
     }
     __syncwarp();
     // post-twiddle: B[k] sits at pos(k) = 32 (k&3) + 8 ((k>>2)&3) + 2 ((k>>4)&3) + (k>>6)
@@ -1091,8 +1102,8 @@ __device__ void imdct512_warp(const Tables& T, float* plane, int lane)
         int i = lane + 32 * r;
         int k2 = 127 - i;
         float2 p = T.post1[i];
-        float2 B1 = z[32 * (i & 3) + 8 * ((i >> 2) & 3) + 2 * ((i >> 4) & 3) + (i >> 6)];
-        float2 B2 = z[32 * (k2 & 3) + 8 * ((k2 >> 2) & 3) + 2 * ((k2 >> 4) & 3) + (k2 >> 6)];
+        float2 B1 = z[zsw(32 * (i & 3) + 8 * ((i >> 2) & 3) + 2 * ((i >> 4) & 3) + (i >> 6))];
+        float2 B2 = z[zsw(32 * (k2 & 3) + 8 * ((k2 >> 2) & 3) + 2 * ((k2 >> 4) & 3) + (k2 >> 6))];
         u_[2 * r] = p.x * B1.x + p.y * B1.y;         // a_r -> U[2i]
         v_[2 * r] = p.y * B1.x - p.x * B1.y;         // a_i -> V[2i]
         u_[2 * r + 1] = -(p.y * B2.x + p.x * B2.y);  // -b_r -> U[2i+1] (sign folded so that the
@@ -1103,10 +1114,8 @@ __device__ void imdct512_warp(const Tables& T, float* plane, int lane)
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         int i = lane + 32 * r;
-        plane[2 * i] = u_[2 * r];
-        plane[2 * i + 1] = u_[2 * r + 1];
-        plane[128 + 2 * i] = v_[2 * r];
-        plane[128 + 2 * i + 1] = v_[2 * r + 1];
+        reinterpret_cast<float2*>(plane)[i] = make_float2(u_[2 * r], u_[2 * r + 1]);
+        reinterpret_cast<float2*>(plane)[64 + i] = make_float2(v_[2 * r], v_[2 * r + 1]);
     }
     __syncwarp();
 }
