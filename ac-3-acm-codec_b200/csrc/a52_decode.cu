@@ -1462,53 +1462,56 @@ a52_decode_pair_kernel(const DecodeParams P)
                     const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
                     const uint32_t zrow = (zmode == 1) ? 16u : 0u;
                     const uint32_t emit_bit = mute ? 0u : 0x1000000u;
-                    // bap / exponent bytes four at a time (funnelled words, as in pass 1), one mantissa ahead
+                    // four mantissas per trip: one funnelled bap word and one exponent word, their four LUT
+                    // rows fetched together, then the four updates in coded order
                     uint32_t bw_lo = bapw[wi0], ew_lo = expw[wi0];
-                    uint32_t bw_hi = bapw[wi0 + 1], ew_hi = expw[wi0 + 1];
-                    uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
-                    uint32_t b = bv & 0xff, e = ev & 0xff;
-                    uint4 L = lds_v4(lut_addr + (run_n ? (b + zrow) : 0u) * 16);
-                    for (uint32_t k = 0; k < K; k++) {
-                        const bool valid = k < run_n;
-                        const uint32_t slot = run_slot + k;
-                        // next mantissa's bytes: byte (k + 1) & 3 of the current funnelled words
-                        if (((k + 1) & 3) == 0) {
-                            const uint32_t j = ((k + 1) >> 2) + 1;
-                            bw_lo = bw_hi; ew_lo = ew_hi;
-                            bw_hi = bapw[wi0 + j]; ew_hi = expw[wi0 + j];
-                            bv = __funnelshift_r(bw_lo, bw_hi, bsh);
-                            ev = __funnelshift_r(ew_lo, ew_hi, bsh);
+                    for (uint32_t k0 = 0, j = 1; k0 < K; k0 += 4, j++) {
+                        const uint32_t bw_hi = bapw[wi0 + j], ew_hi = expw[wi0 + j];
+                        const uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
+                        bw_lo = bw_hi;
+                        ew_lo = ew_hi;
+                        uint4 Lr[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const uint32_t b = (bv >> (8 * t)) & 0xff;
+                            // mantissas past my run take the row of an undithered zero: nothing moves
+                            Lr[t] = lds_v4(lut_addr + ((k0 + t < run_n) ? (b + zrow) : 0u) * 16);
                         }
-                        const uint32_t sh8 = 8 * ((k + 1) & 3);
-                        const uint32_t bn = (bv >> sh8) & 0xff, en = (ev >> sh8) & 0xff;
-                        const uint4 Ln = lds_v4(lut_addr + ((k + 1 < run_n) ? (bn + zrow) : 0u) * 16);
-                        if (zmode == 2 && b == 0 && valid) {
-                            uint32_t m = cpl_dith;
-                            while (m) {
-                                const uint32_t ch = __ffs(m) - 1;
-                                m &= m - 1;
-                                const uint32_t s2 = ch * 256 + (slot & 255);
-                                G.list[base_z + run_z] = (uint16_t)s2;
-                                run_z++;
-                                planeU[s2] = e;
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const uint32_t b = (bv >> (8 * t)) & 0xff, e = (ev >> (8 * t)) & 0xff;
+                            const uint32_t slot = run_slot + k0 + t;
+                            const uint4 L = Lr[t];
+                            if (zmode == 2 && b == 0 && k0 + t < run_n) {
+                                // one dither value per coupled channel, channel order (parse.c:466-481)
+                                uint32_t m = cpl_dith;
+                                while (m) {
+                                    const uint32_t ch = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const uint32_t s2 = ch * 256 + (slot & 255);
+                                    G.list[base_z + run_z] = (uint16_t)s2;
+                                    run_z++;
+                                    planeU[s2] = e;
+                                }
+                            } else {
+                                // x: cursor increment (classes 1, 2, 4, plain); y: base selector A | width << 16 |
+                                // emit << 24; z: base selector B | 256/period << 16; w: count selector |
+                                // period << 16 | zero-list increment << 24
+                                const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
+                                const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
+                                // starts a field / group code when (phase0 + occurrences so far) % period == 0
+                                const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
+                                const uint32_t per = prmt(L.w, 0, 0x4442);
+                                const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
+                                run_a += L.x;
+                                run_z += L.w >> 24;
+                                if (L.y & emit_bit) {
+                                    G.list[li] = (uint16_t)slot;
+                                    planeU[slot] = make_desc(e, b, pos);
+                                }
+                                pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
                             }
-                        } else {
-                            const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
-                            const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
-                            const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
-                            const uint32_t per = prmt(L.w, 0, 0x4442);
-                            const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
-                            run_a += L.x;
-                            run_z += L.w >> 24;
-                            if (L.y & emit_bit) {
-                                G.list[li] = (uint16_t)slot;
-                                planeU[slot] = make_desc(e, b, pos);
-                            }
-                            pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
                         }
-                        b = bn;
-                        e = en;
-                        L = Ln;
                     }
                 }
                 sync();
