@@ -1236,7 +1236,7 @@ __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes
 constexpr int kMaxPairsPerCta = 12;
 
 __global__ void __launch_bounds__(kMaxPairsPerCta * 64, 1)
-a52_decode_pair_kernel(const DecodeParams P)
+a52_decode_kernel(const DecodeParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     Tables& T = *reinterpret_cast<Tables*>(smem);

@@ -385,7 +385,7 @@ a52_batch_t* a52_batch_create(int device)
     ok = ok && cudaMalloc(&ctx->d_dither, seq.size() * 2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(a52::a52_decode_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024) == cudaSuccess;
     if (!ok) {
         a52_batch_destroy(ctx);
@@ -468,7 +468,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
                          float level, cudaStream_t st, int counter_slot = 0, int max_stream_frames = 0)
 {
     using namespace a52;
-    // work units of the pair kernel: slices of streams (see a52_decode_pair_kernel)
+    // work units of the pair kernel: slices of streams (see a52_decode_kernel)
     P.slice_frames = ctx->slice_frames;
     P.nslices = 1;
     P.carry_init = P.carry != nullptr;
@@ -536,7 +536,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used], e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
     A52_CUDA(cudaEventRecord(e0, st));
-    a52_decode_pair_kernel<<<grid, threads, smem, st>>>(P);
+    a52_decode_kernel<<<grid, threads, smem, st>>>(P);
     A52_CUDA(cudaEventRecord(e1, st));
     A52_CUDA(cudaGetLastError());
     ctx->launches++;
