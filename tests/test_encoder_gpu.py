@@ -133,3 +133,57 @@ def test_large_batch_properties_and_round_trip(encoder, engine, decoder, oracle)
     n = len(x) - 256
     err = y[256:256 + n] - x[:n]
     assert 10 * np.log10((x[:n] ** 2).sum() / (err ** 2).sum()) > 20
+
+
+def test_mixed_corpus_round_trip_sharded(encoder, engine, decoder, oracle):
+    """Config 5 in small: a grid of (sample rate, channels, bitrate) cells inside the reference encoder's
+    feasible region is encoded on the GPU (frames = the oracle's), then all streams - different frame
+    sizes, channel modes and rates, 44.1 kHz frames unaligned - are decoded in ONE batch and again split
+    into 2 and 4 logical shards (LPT partition + 16-byte repack): PCM matches the oracle decoder and is
+    bit-identical whatever the sharding."""
+    import importlib
+    from refbind import A52_STEREO, A52_ADJUST_LEVEL
+    from util import relrms, frame_offsets
+    shard = importlib.import_module("ac3_acm_codec_b200.shard")
+    ora = OracleEnc()
+    cells = [(48000, 1, 64000), (48000, 2, 128000), (44100, 2, 96000), (32000, 3, 160000), (44100, 4, 224000),
+             (48000, 5, 384000), (44100, 6, 448000), (32000, 6, 256000), (48000, 6, 640000), (24000, 2, 64000)]
+    nfr = 5
+    streams = []
+    for k, (rate, nch, br) in enumerate(cells):
+        pcm = synth_pcm(9, k, nch, 1536 * nfr, rate)
+        out = encoder.encode_host(pcm[None], rate, br)
+        fb, want = ora.encode_stream(pcm, rate, br)
+        assert (out["status"] == 0).all() and (out["frames"][0].reshape(-1) == want).all(), (rate, nch, br)
+        streams.append(out["frames"][0].reshape(-1))
+    es = np.concatenate(streams)
+    off, first, flen = [], [0], []
+    pos = 0
+    for sbytes in streams:
+        o = frame_offsets(sbytes, oracle)
+        n = oracle.syncinfo(sbytes[:7])[0]
+        off += [pos + int(x) for x in o]
+        flen += [n] * len(o)
+        first.append(first[-1] + len(o))
+        pos += len(sbytes)
+    off, first, flen = np.array(off, np.uint64), np.array(first, np.uint32), np.array(flen)
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    whole = decoder.decode_host(es, off, first, flags)
+    assert (whole["status"] == 0).all()
+    for k, sbytes in enumerate(streams):
+        nf, want = oracle.decode_stream(sbytes, flags, 1.0, 0.0)
+        got = whole["pcm"][first[k]:first[k + 1]].reshape(-1, 2, 256)
+        assert nf == nfr and relrms(got, want) < 1e-5, cells[k]
+    costs = [len(sb) for sb in streams]
+    for world in (2, 4):
+        parts = shard.partition_streams(costs, world)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(cells)))
+        for r in range(world):
+            if len(parts[r]) == 0:
+                continue
+            sub, soff, sfirst = shard.shard_batch(es, off, flen, first, parts[r])
+            res = decoder.decode_host(sub, soff, sfirst, flags)
+            for j, sidx in enumerate(parts[r]):
+                a = res["pcm"][sfirst[j]:sfirst[j + 1]]
+                b = whole["pcm"][first[sidx]:first[sidx + 1]]
+                assert (a.view(np.uint32) == b.view(np.uint32)).all(), (world, r, sidx)
