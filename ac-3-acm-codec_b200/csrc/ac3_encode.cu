@@ -109,6 +109,9 @@ struct EncShared {
 
 __device__ __forceinline__ int ilog2(uint32_t v) { return v ? 31 - __clz(v) : 0; }
 
+// two 16-bit halves -> one word (low halves of re and im), one PRMT
+__device__ __forceinline__ uint32_t pack16(int re, int im) { return __byte_perm((uint32_t)re, (uint32_t)im, 0x5410); }
+
 __device__ __forceinline__ void put_bits_atomic(uint32_t* frame, uint32_t pos, uint32_t n, uint32_t v)
 {
     // n in 1..16, v < 2^n; big-endian bit order: bit 0 of the frame = msb of word 0
@@ -221,7 +224,7 @@ __device__ void e1_transform(EncShared& S, const EncTables& T, const EncParams& 
         const int im = -(rot(256 + 2 * i) - rot(255 - 2 * i)) >> 1;
         const int bre = -T.xcos1[i], bim = T.xsin1[i];
         const int xr = (re * bre - im * bim) >> 15, xi = (re * bim + bre * im) >> 15;
-        z[T.rev[i]] = ((uint32_t)(uint16_t)(int16_t)xr) | ((uint32_t)(uint16_t)(int16_t)xi << 16);
+        z[T.rev[i]] = pack16(xr, xi);
     }
     __syncwarp();
     // 128-point FFT (:485-568), 7 halving radix-2 passes, two butterflies per lane and pass
@@ -245,8 +248,8 @@ __device__ void e1_transform(EncShared& S, const EncTables& T, const EncParams& 
                 ax = (c * qre - sn * qim) >> 15;
                 ay = (c * qim + qre * sn) >> 15;
             }
-            z[i0] = ((uint32_t)(uint16_t)(int16_t)((bx + ax) >> 1)) | ((uint32_t)(uint16_t)(int16_t)((by + ay) >> 1) << 16);
-            z[i1] = ((uint32_t)(uint16_t)(int16_t)((bx - ax) >> 1)) | ((uint32_t)(uint16_t)(int16_t)((by - ay) >> 1) << 16);
+            z[i0] = pack16((bx + ax) >> 1, (by + ay) >> 1);
+            z[i1] = pack16((bx - ax) >> 1, (by - ay) >> 1);
         }
         __syncwarp();
     }
@@ -501,19 +504,22 @@ __device__ void e3_probe(EncShared& S, const EncTables& T, const EncParams& P, i
     }
 }
 
-// bits left in the frame for the counts of the last probe (bit_alloc, :813-845)
-__device__ int bits_left(const EncShared& S, const EncParams& P)
+// bits left in the frame for the counts of the last probe (bit_alloc, :813-845); warp 0, lane = block
+__device__ int bits_left(const EncShared& S, const EncParams& P, int lane)
 {
-    int used = S.frame_bits;
-    for (int blk = 0; blk < 6; blk++) {
+    int used = 0;
+    if (lane < 6) {
         int n1 = 0, n2 = 0, n4 = 0;
         for (int ch = 0; ch < P.nch_all; ch++) {
-            const int* q = S.cnt[S.head[blk][ch]][ch];
+            const int* q = S.cnt[S.head[lane][ch]][ch];
             n1 += q[0]; n2 += q[1]; n4 += q[2]; used += q[3];
         }
         used += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
     }
-    return 16 * P.frame_words - used;
+    used += __shfl_xor_sync(0xffffffffu, used, 1);
+    used += __shfl_xor_sync(0xffffffffu, used, 2);
+    used += __shfl_xor_sync(0xffffffffu, used, 4);
+    return 16 * P.frame_words - S.frame_bits - used;
 }
 
 // The search of compute_bit_allocation (:921-967) as a state machine fed with one probe result
@@ -638,7 +644,10 @@ ac3_encode_kernel(const EncParams P)
                     for (int blk = 0; blk < 6; blk++)
                         if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, snro, false);
                 __syncthreads();
-                if (tid == 0) search_step(S, bits_left(S, P));
+                if (warp == 0) {
+                    const int left = bits_left(S, P, lane);
+                    if (lane == 0) search_step(S, left);
+                }
                 __syncthreads();
                 if (S.done) break;
             }
@@ -766,11 +775,14 @@ ac3_encode_kernel(const EncParams P)
                         const uint32_t m2 = __ballot_sync(0xffffffffu, b == 2);
                         const uint32_t m4 = __ballot_sync(0xffffffffu, b == 4);
                         const uint32_t lt = (1u << lane) - 1;
-                        int x = 0, per = 1, cls = -1;
-                        if (b == 1) { x = N1 + __popc(m1 & lt); per = 3; cls = 0; }
-                        else if (b == 2) { x = N2 + __popc(m2 & lt); per = 3; cls = 1; }
-                        else if (b == 4) { x = N4 + __popc(m4 & lt); per = 2; cls = 2; }
-                        const int g = x / per, digit = x - g * per;
+                        // occurrence number x of my mantissa in its class -> group g, digit (x < 1500: the
+                        // division by 3 is a multiply-shift)
+                        int x = 0, cls = -1, g = 0, digit = 0;
+                        if (b == 1) { x = N1 + __popc(m1 & lt); cls = 0; }
+                        else if (b == 2) { x = N2 + __popc(m2 & lt); cls = 1; }
+                        else if (b == 4) { x = N4 + __popc(m4 & lt); cls = 2; }
+                        if (cls == 2) { g = x >> 1; digit = x & 1; }
+                        else if (cls >= 0) { g = (x * 43691) >> 17; digit = x - 3 * g; }
                         int width = (cls >= 0 && digit) ? 0 : T.width[b];
                         // inclusive scan of the widths
                         int incl = width;
