@@ -946,6 +946,18 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a)
     return v;
 }
 
+// predicated shared-memory stores through 32-bit shared addresses (no branch, no address rebuild)
+__device__ __forceinline__ void sts_u16_if(uint32_t addr, uint32_t v, uint32_t pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u16 [%0], %1;\n}\n"
+                 :: "r"(addr), "h"((unsigned short)v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, uint32_t pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}\n"
+                 :: "r"(addr), "r"(v), "r"(pred) : "memory");
+}
+
 // peek without a limit check: descriptor positions are clamped to the frame end at emit time
 // and the words past the frame end are zero
 __device__ __forceinline__ uint32_t peek_nz(const uint32_t* w, uint32_t pos, uint32_t n)
@@ -1260,8 +1272,10 @@ a52_decode_kernel(const DecodeParams P)
     for (int i = gt; i < (int)(sizeof(GroupCtl) / 4); i += NT) reinterpret_cast<uint32_t*>(c)[i] = 0;
     for (int i = gt; i < 7 * 256 * 2 / 4; i += NT) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
     __syncthreads();
-    uint32_t tab_base;
+    uint32_t tab_base, list_sa, plane_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(tab_base) : "r"(smem_u32(&T)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(list_sa) : "r"(smem_u32(G.list)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(plane_sa) : "r"(smem_u32(G.plane)));
     uint32_t phase = 0;
     const int ndelay = P.nplanes;            // tails: planes 0..4 main, 5 LFE
 
@@ -1464,26 +1478,45 @@ a52_decode_kernel(const DecodeParams P)
                     const uint32_t emit_bit = mute ? 0u : 0x1000000u;
                     // four mantissas per trip: one funnelled bap word and one exponent word, their four LUT
                     // rows fetched together, then the four updates in coded order
+                    // emit_lut row: x: cursor increment (classes 1, 2, 4, plain); y: base selector A |
+                    // width << 16 | emit << 24; z: base selector B | 256/period << 16; w: count selector |
+                    // period << 16 | zero-list increment << 24
+                    auto emit_one = [&](uint32_t b, uint32_t e, uint32_t slot, const uint4& L) {
+                        const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
+                        const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
+                        // starts a field / group code when (phase0 + occurrences so far) % period == 0
+                        const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
+                        const uint32_t per = prmt(L.w, 0, 0x4442);
+                        const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
+                        run_a += L.x;
+                        run_z += L.w >> 24;
+                        const uint32_t emit = L.y & emit_bit;
+                        sts_u16_if(list_sa + 2 * li, slot, emit);
+                        sts_u32_if(plane_sa + 4 * slot, make_desc(e, b, pos), emit);
+                        pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
+                    };
                     uint32_t bw_lo = bapw[wi0], ew_lo = expw[wi0];
-                    for (uint32_t k0 = 0, j = 1; k0 < K; k0 += 4, j++) {
-                        const uint32_t bw_hi = bapw[wi0 + j], ew_hi = expw[wi0 + j];
-                        const uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
-                        bw_lo = bw_hi;
-                        ew_lo = ew_hi;
-                        uint4 Lr[4];
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const uint32_t b = (bv >> (8 * t)) & 0xff;
+                    if (zmode != 2) {
+                        for (uint32_t k0 = 0, j = 1; k0 < K; k0 += 4, j++) {
+                            const uint32_t bw_hi = bapw[wi0 + j], ew_hi = expw[wi0 + j];
+                            const uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
+                            bw_lo = bw_hi;
+                            ew_lo = ew_hi;
+                            uint4 Lr[4];
                             // mantissas past my run take the row of an undithered zero: nothing moves
-                            Lr[t] = lds_v4(lut_addr + ((k0 + t < run_n) ? (b + zrow) : 0u) * 16);
-                        }
 #pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const uint32_t b = (bv >> (8 * t)) & 0xff, e = (ev >> (8 * t)) & 0xff;
-                            const uint32_t slot = run_slot + k0 + t;
-                            const uint4 L = Lr[t];
-                            if (zmode == 2 && b == 0 && k0 + t < run_n) {
-                                // one dither value per coupled channel, channel order (parse.c:466-481)
+                            for (int t = 0; t < 4; t++)
+                                Lr[t] = lds_v4(lut_addr + ((k0 + t < run_n) ? (((bv >> (8 * t)) & 0xff) + zrow) : 0u) * 16);
+#pragma unroll
+                            for (int t = 0; t < 4; t++)
+                                emit_one((bv >> (8 * t)) & 0xff, (ev >> (8 * t)) & 0xff, run_slot + k0 + t, Lr[t]);
+                        }
+                    } else {
+                        // coupling channel with dither: a bap-0 bin takes one dither value per coupled
+                        // channel, in channel order (parse.c:466-481)
+                        for (uint32_t k = 0; k < run_n; k++) {
+                            const uint32_t b = G.bap[run_idx + k], e = G.exp[run_idx + k], slot = run_slot + k;
+                            if (b == 0) {
                                 uint32_t m = cpl_dith;
                                 while (m) {
                                     const uint32_t ch = __ffs(m) - 1;
@@ -1494,22 +1527,7 @@ a52_decode_kernel(const DecodeParams P)
                                     planeU[s2] = e;
                                 }
                             } else {
-                                // x: cursor increment (classes 1, 2, 4, plain); y: base selector A | width << 16 |
-                                // emit << 24; z: base selector B | 256/period << 16; w: count selector |
-                                // period << 16 | zero-list increment << 24
-                                const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
-                                const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
-                                // starts a field / group code when (phase0 + occurrences so far) % period == 0
-                                const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
-                                const uint32_t per = prmt(L.w, 0, 0x4442);
-                                const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
-                                run_a += L.x;
-                                run_z += L.w >> 24;
-                                if (L.y & emit_bit) {
-                                    G.list[li] = (uint16_t)slot;
-                                    planeU[slot] = make_desc(e, b, pos);
-                                }
-                                pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
+                                emit_one(b, e, slot, lds_v4(lut_addr + b * 16));
                             }
                         }
                     }
