@@ -25,7 +25,7 @@ _NFCH = [2, 1, 2, 3, 3, 4, 4, 5, 1, 1, 2]
 
 EXPORTS = [
     "a52_init", "a52_samples", "a52_syncinfo", "a52_frame", "a52_dynrng", "a52_block", "a52_free",
-    "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index",
+    "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index", "a52_batch_index_device",
     "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes", "a52_batch_set_max_stream_frames",
     "a52_batch_launch_count", "a52_batch_kernel_ms",
     "AC3_encode_init", "AC3_encode_frame",
@@ -65,6 +65,8 @@ def load_library():
     L.a52_batch_last_error.restype = C.c_char_p
     L.a52_batch_last_error.argtypes = [C.c_void_p]
     L.a52_batch_index.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    L.a52_batch_index_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p]
     L.a52_batch_frame_stride.restype = C.c_size_t
     L.a52_batch_frame_stride.argtypes = [C.c_int, C.c_int]
     L.a52_batch_set_max_frame_bytes.argtypes = [C.c_void_p, C.c_int]
@@ -201,6 +203,15 @@ class BatchDecoder:
             out_fmt, pcm_ptr, status_ptr or None, flags_ptr or None, carry_ptr or None, None, DEVICE_PTRS,
             stream or None)
         self._check(rc)
+
+    def index_device(self, es_ptr, stream_off, frame_off_ptr, max_frames, stream_first_ptr, stream=0):
+        """GPU frame indexer over device-resident elementary streams; returns the number of frames."""
+        stream_off = np.ascontiguousarray(stream_off, dtype=np.uint64)
+        n = self.L.a52_batch_index_device(self.ctx, es_ptr, stream_off.ctypes.data, len(stream_off) - 1, frame_off_ptr,
+                                          max_frames, stream_first_ptr, stream or None)
+        if n < 0:
+            raise RuntimeError("a52_batch_index_device failed (%d): %s" % (n, self.L.a52_batch_last_error(self.ctx).decode()))
+        return n
 
     def set_max_frame_bytes(self, n):
         self.L.a52_batch_set_max_frame_bytes(self.ctx, n)

@@ -288,6 +288,39 @@ __global__ void a52_maxlen_kernel(const uint8_t* es, const uint64_t* off, int nf
     if ((threadIdx.x & 31) == 0 && len) atomicMax(out, len);
 }
 
+// Frame indexer on the device: one thread walks one elementary stream with the resync discipline of
+// a52dec.c:240-309 (slide one byte until a52_syncinfo accepts a header, then hop by the frame length).
+// Pass 0 counts the frames of every stream, pass 1 writes their offsets behind stream_first[s].
+__device__ __forceinline__ int dev_syncinfo_len(const uint8_t* b)
+{
+    if (b[0] != 0x0b || b[1] != 0x77) return 0;          // parse.c:98-127
+    if ((b[5] >> 3) >= 12) return 0;
+    const int cod = b[4] & 63, fscod = b[4] >> 6;
+    if (cod >= 38 || fscod == 3) return 0;
+    const int kbps = c_bitrate[cod >> 1];
+    return fscod == 0 ? 4 * kbps : fscod == 2 ? 6 * kbps : 2 * (320 * kbps / 147 + (cod & 1));
+}
+
+__global__ void a52_index_kernel(const uint8_t* es, const uint64_t* stream_off, int nstreams, int* count,
+                                 const uint32_t* stream_first, uint64_t* frame_off, int max_frames)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    uint64_t pos = stream_off[s];
+    const uint64_t end = stream_off[s + 1];
+    int n = 0;
+    uint32_t slot = stream_first ? stream_first[s] : 0;
+    while (pos + 7 <= end) {
+        const int len = dev_syncinfo_len(es + pos);
+        if (!len) { pos++; continue; }
+        if (pos + len > end) break;
+        if (frame_off && (int)(slot + n) < max_frames) frame_off[slot + n] = pos;
+        n++;
+        pos += len;
+    }
+    if (count) count[s] = n;
+}
+
 // longest stream (frames) of a device-resident batch
 __global__ void a52_maxstream_kernel(const uint32_t* first, int nstreams, int* out)
 {
@@ -433,6 +466,40 @@ int a52_batch_index(const uint8_t* es, size_t es_bytes, uint64_t* frame_off, int
         pos += len;
     }
     return n;
+}
+
+int a52_batch_index_device(a52_batch_t* ctx, const uint8_t* es, const uint64_t* stream_off, int nstreams,
+                           uint64_t* frame_off, int max_frames, uint32_t* stream_first, void* cuda_stream)
+{
+    using namespace a52;
+    if (!ctx || nstreams < 0) return -3;
+    if (nstreams == 0) return 0;
+    A52_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (ensure(ctx, ctx->b_off, (size_t)(nstreams + 1) * 8)) return -1;
+    if (ensure(ctx, ctx->b_done, (size_t)nstreams * sizeof(int))) return -1;
+    A52_CUDA(cudaMemcpyAsync(ctx->b_off.p, stream_off, (size_t)(nstreams + 1) * 8, cudaMemcpyHostToDevice, st));
+    const int tpb = 64, grid = (nstreams + tpb - 1) / tpb;
+    a52_index_kernel<<<grid, tpb, 0, st>>>(es, (const uint64_t*)ctx->b_off.p, nstreams, (int*)ctx->b_done.p, nullptr,
+                                          nullptr, 0);
+    std::vector<int> cnt(nstreams);
+    A52_CUDA(cudaMemcpyAsync(cnt.data(), ctx->b_done.p, (size_t)nstreams * sizeof(int), cudaMemcpyDeviceToHost, st));
+    A52_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> first(nstreams + 1);
+    uint64_t total = 0;
+    for (int s = 0; s < nstreams; s++) { first[s] = (uint32_t)total; total += (uint64_t)cnt[s]; }
+    first[nstreams] = (uint32_t)total;
+    if (total > (uint64_t)max_frames) {
+        snprintf(ctx->err, sizeof(ctx->err), "frame table too small: %llu frames found", (unsigned long long)total);
+        return -4;
+    }
+    A52_CUDA(cudaMemcpyAsync(stream_first, first.data(), (size_t)(nstreams + 1) * 4, cudaMemcpyHostToDevice, st));
+    a52_index_kernel<<<grid, tpb, 0, st>>>(es, (const uint64_t*)ctx->b_off.p, nstreams, nullptr, stream_first, frame_off,
+                                          max_frames);
+    A52_CUDA(cudaGetLastError());
+    A52_CUDA(cudaStreamSynchronize(st));       // `first` lives on this stack frame
+    ctx->launches += 2;
+    return (int)total;
 }
 
 size_t a52_batch_frame_stride(int req_flags, int out_fmt)

@@ -78,6 +78,14 @@ const char * a52_batch_last_error (a52_batch_t * ctx);
  * frame.  Returns the number of frames found (<= max_frames). */
 int a52_batch_index (const uint8_t * es, size_t es_bytes, uint64_t * frame_off, int max_frames);
 
+/* The same scan on the GPU for elementary streams that already live in device memory (one thread walks
+ * one stream): stream s = bytes [stream_off[s], stream_off[s+1]) of es.  es, frame_off (exactly the
+ * frames found are written, at most max_frames) and stream_first (nstreams + 1 entries) are DEVICE
+ * pointers, stream_off is a host pointer.  Returns the total number of frames, or a negative value
+ * (frame table too small, CUDA error). */
+int a52_batch_index_device (a52_batch_t * ctx, const uint8_t * es, const uint64_t * stream_off, int nstreams,
+			    uint64_t * frame_off, int max_frames, uint32_t * stream_first, void * cuda_stream);
+
 /* bytes one decoded frame occupies in pcm_out for a request (req_flags as for
  * a52_frame): 1536 * nout_requested * sample size */
 size_t a52_batch_frame_stride (int req_flags, int out_fmt);

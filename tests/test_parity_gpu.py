@@ -249,6 +249,51 @@ def test_carry_split_equals_one_call(decoder, engine, oracle, c2):
     assert (got.view(np.uint32) == whole["pcm"].view(np.uint32)).all()
 
 
+def test_device_frame_indexer(decoder, engine, oracle, c2, golden):
+    """GPU sync scan over device-resident elementary streams (garbage between frames, truncated tails,
+    mixed frame sizes) == the a52dec.c:240-309 resync discipline; the result feeds the device-pointer
+    decode directly."""
+    import torch
+    rng = np.random.RandomState(4)
+    junk = rng.randint(0, 256, 4000).astype(np.uint8)
+    junk[junk == 0x0B] = 0
+    streams = []
+    for s in range(9):
+        fr = c2["frames"][s % 4, :5 + s].reshape(-1) if s % 3 else golden["enc50_dolby_441.es"]
+        cut = 1792 * int(rng.randint(1, 4)) if s % 3 else 1392            # whole frames (44.1 kHz 320 kb/s: 1392 bytes)
+        parts = [junk[: int(rng.randint(0, 200))], fr[:cut], junk[200:200 + int(rng.randint(1, 50))] if s % 2 else fr[:0], fr[cut:]]
+        if s == 4:
+            parts.append(fr[:1000])                       # truncated last frame
+        if s == 7:
+            parts = [junk[:500]]                          # no frame at all
+        streams.append(np.concatenate(parts))
+    es = np.concatenate(streams)
+    soff = np.concatenate([[0], np.cumsum([len(x) for x in streams])]).astype(np.uint64)
+    want_off, want_first = [], [0]
+    for s, x in enumerate(streams):
+        o = frame_offsets(x, oracle)
+        want_off += [int(soff[s]) + int(v) for v in o]
+        want_first.append(len(want_off))
+    es_d = torch.from_numpy(np.concatenate([es, np.zeros(64, np.uint8)])).cuda()
+    off_d = torch.zeros(len(want_off) + 8, dtype=torch.int64, device="cuda")
+    first_d = torch.zeros(len(streams) + 1, dtype=torch.int32, device="cuda")
+    n = decoder.index_device(es_d.data_ptr(), soff, off_d.data_ptr(), len(want_off) + 8, first_d.data_ptr())
+    assert n == len(want_off)
+    assert off_d[:n].cpu().numpy().tolist() == want_off
+    assert first_d.cpu().numpy().tolist() == want_first
+    # decode straight from the device tables (frame_off needs one entry past the end)
+    off_d[n] = len(es)
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    pcm = torch.zeros(n * 1536 * 2, dtype=torch.float32, device="cuda")
+    status = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    decoder.decode_device(es_d.data_ptr(), len(es), off_d.data_ptr(), n, first_d.data_ptr(), len(streams), flags,
+                          pcm.data_ptr(), status_ptr=status.data_ptr(), out_fmt=engine.PCM_F32_PLANAR)
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0
+    host = decoder.decode_host(es, np.array(want_off, np.uint64), np.array(want_first, np.uint32), flags)
+    assert (pcm.cpu().numpy().view(np.uint32) == host["pcm"].reshape(-1).view(np.uint32)).all()
+
+
 def test_time_slicing_is_bit_identical(engine, c2):
     """The kernel hands out slices of streams as work units (carry through global memory between
     slices): any slice length must give the same bits as whole-stream units."""
