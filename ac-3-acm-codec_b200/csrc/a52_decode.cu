@@ -1132,7 +1132,7 @@ __device__ void imdct512_warp(const Tables& T, float* plane, int lane)
     __syncwarp();
 }
 
-__device__ void imdct256_warp(const Tables& T, float* plane, int lane)
+__device__ __noinline__ void imdct256_warp(const Tables& T, float* plane, int lane)
 {
     float2* z = reinterpret_cast<float2*>(plane);
     // two interleaved 64-point transforms: f = lane >> 4 selects the transform
@@ -1243,6 +1243,126 @@ __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes
     g.delay = reinterpret_cast<float*>(p);   p += nplanes * 128 * 4;
     g.xch = reinterpret_cast<uint32_t*>(p);
     return g;
+}
+
+// Window + overlap-add (+ time-domain mix) + store of one block, every output format and both tail
+// representations; thread q owns positions p = 2q, 2q+1 (and their mirrors) of every plane.  Kept out of
+// line: the stereo float fast path in the kernel covers the common request, this covers the rest.
+__device__ __noinline__ void ola_store_generic(const Tables& T, const DecodeParams& P, const PairPtrs& G, const GroupCtl* c,
+                                               uint8_t* out_frame, int blk, int gt, int nfchans, int nmain,
+                                               bool uniform, int lfe_on)
+{
+        const int nout = nmain + lfe_on;
+        const float bias = P.bias;
+        const bool identity = c->identity_mix;
+        const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
+        const float2* win2 = reinterpret_cast<const float2*>(T.window);
+        float2* delay2 = reinterpret_cast<float2*>(G.delay);
+        const int q = gt;
+        if (uniform && c->per_channel) {
+            // a52_downmix on the per-channel tails; zero-gain channels are left out
+            float2 d[5], m[5];
+#pragma unroll
+            for (int ch = 0; ch < 5; ch++)
+                d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? delay2[ch * 64 + q] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < 5; o++) {
+                float ax = 0.f, ay = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 5; ch++) { ax = fmaf(c->wt[o][ch], d[ch].x, ax); ay = fmaf(c->wt[o][ch], d[ch].y, ay); }
+                m[o] = make_float2(ax, ay);
+            }
+#pragma unroll
+            for (int o = 0; o < 5; o++)
+                if (o < nmain) delay2[o * 64 + q] = m[o];
+        } else if (!uniform && !c->per_channel) {
+            // a52_upmix: downmixed tails go back to the coded channels they belong to
+            const MixEntry mx = c_mix[c->acmod * 11 + (c->output & M_MASK)];
+            float2 m[5];
+#pragma unroll
+            for (int o = 0; o < 5; o++) m[o] = delay2[o * 64 + q];
+#pragma unroll
+            for (int ch = 0; ch < 5; ch++) {
+                if (ch < nfchans) {
+                    float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int o = 0; o < 5; o++)
+                        if (mx.up[ch] == o) v = m[o];
+                    delay2[ch * 64 + q] = v;
+                }
+            }
+        }
+        const float2 wl = win2[q], wh = win2[127 - q];      // (w[p], w[p+1]), (w[254-p], w[255-p])
+        float y[6][4];                                       // [output][p, p+1, 254-p, 255-p]
+#pragma unroll
+        for (int o = 0; o < 6; o++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) y[o][r] = 0.f;
+#pragma unroll
+        for (int pl = 0; pl < 6; pl++) {
+            const bool is_lfe = (pl == 5);
+            bool live;
+            if (is_lfe) live = lfe_on;
+            else if (uniform) live = pl < nmain;
+            else live = pl < nfchans && c->gain[pl] != 0.f;
+            if (!live) continue;
+            const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
+            const float2 D = delay2[pl * 64 + q];
+            const float a0 = D.x * wh.y - U.x * wl.x;        // sample p
+            const float a1 = D.y * wh.x - U.y * wl.y;        // sample p + 1
+            const float b0 = D.x * wl.x + U.x * wh.y;        // sample 255 - p
+            const float b1 = D.y * wl.y + U.y * wh.x;        // sample 254 - p
+            delay2[pl * 64 + q] = V;
+            if (is_lfe) {
+                y[0][0] = a0; y[0][1] = a1; y[0][2] = b1; y[0][3] = b0;
+            } else if (uniform || identity) {
+#pragma unroll
+                for (int oo = 0; oo < 6; oo++)
+                    if (oo == pl + lfe_on) { y[oo][0] = a0; y[oo][1] = a1; y[oo][2] = b1; y[oo][3] = b0; }
+            } else {
+#pragma unroll
+                for (int o = 0; o < 5; o++) {
+                    const float wgt = c->wt[o][pl];
+#pragma unroll
+                    for (int oo = 0; oo < 6; oo++)
+                        if (o < nmain && oo == o + lfe_on) {
+                            y[oo][0] = fmaf(wgt, a0, y[oo][0]);
+                            y[oo][1] = fmaf(wgt, a1, y[oo][1]);
+                            y[oo][2] = fmaf(wgt, b1, y[oo][2]);
+                            y[oo][3] = fmaf(wgt, b0, y[oo][3]);
+                        }
+                }
+            }
+        }
+        const int p = 2 * q;
+        if (P.out_fmt == 1 && nout == 2) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
+            dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
+            dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+        } else {
+#pragma unroll
+            for (int oc = 0; oc < 6; oc++) {
+                if (oc >= nout) continue;
+                const float v0 = y[oc][0], v1 = y[oc][1], v2 = y[oc][2], v3 = y[oc][3];
+                if (P.out_fmt == 0) {
+                    float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
+                    *reinterpret_cast<float2*>(dst + p) = make_float2(v0 + bias, v1 + bias);
+                    *reinterpret_cast<float2*>(dst + 254 - p) = make_float2(v2 + bias, v3 + bias);
+                } else if (P.out_fmt == 1) {
+                    float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
+                    dst[p * nout + oc] = v0 + bias;
+                    dst[(p + 1) * nout + oc] = v1 + bias;
+                    dst[(254 - p) * nout + oc] = v2 + bias;
+                    dst[(255 - p) * nout + oc] = v3 + bias;
+                } else {
+                    int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
+                    dst[p * nout + oc] = (int16_t)min(max(__float2int_rn(v0 * 32768.f), -32768), 32767);
+                    dst[(p + 1) * nout + oc] = (int16_t)min(max(__float2int_rn(v1 * 32768.f), -32768), 32767);
+                    dst[(254 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v2 * 32768.f), -32768), 32767);
+                    dst[(255 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v3 * 32768.f), -32768), 32767);
+                }
+            }
+        }
 }
 
 constexpr int kMaxPairsPerCta = 12;
@@ -1666,118 +1786,30 @@ a52_decode_kernel(const DecodeParams P)
 
                 // ================= O =================
                 // thread q = gt owns positions p = 2q, 2q+1 (and their mirrors 254-p, 255-p) of every plane
-                {
-                    const int nout = nmain + lfe_on;
+                if (uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt == 1) {
+                    // the common request: two mixed planes, tails already downmixed, interleaved float out
                     const float bias = P.bias;
-                    const bool identity = c->identity_mix;
                     const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
                     const float2* win2 = reinterpret_cast<const float2*>(T.window);
                     float2* delay2 = reinterpret_cast<float2*>(G.delay);
                     const int q = gt;
-                    if (uniform && c->per_channel) {
-                        // a52_downmix on the per-channel tails; zero-gain channels are left out
-                        float2 d[5], m[5];
+                    const float2 wl = win2[q], wh = win2[127 - q];
+                    float y[2][4];
 #pragma unroll
-                        for (int ch = 0; ch < 5; ch++)
-                            d[ch] = (ch < nfchans && c->gain[ch] != 0.f) ? delay2[ch * 64 + q] : make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int o = 0; o < 5; o++) {
-                            float ax = 0.f, ay = 0.f;
-#pragma unroll
-                            for (int ch = 0; ch < 5; ch++) { ax = fmaf(c->wt[o][ch], d[ch].x, ax); ay = fmaf(c->wt[o][ch], d[ch].y, ay); }
-                            m[o] = make_float2(ax, ay);
-                        }
-#pragma unroll
-                        for (int o = 0; o < 5; o++)
-                            if (o < nmain) delay2[o * 64 + q] = m[o];
-                    } else if (!uniform && !c->per_channel) {
-                        // a52_upmix: downmixed tails go back to the coded channels they belong to
-                        const MixEntry mx = c_mix[c->acmod * 11 + (c->output & M_MASK)];
-                        float2 m[5];
-#pragma unroll
-                        for (int o = 0; o < 5; o++) m[o] = delay2[o * 64 + q];
-#pragma unroll
-                        for (int ch = 0; ch < 5; ch++) {
-                            if (ch < nfchans) {
-                                float2 v = make_float2(0.f, 0.f);
-#pragma unroll
-                                for (int o = 0; o < 5; o++)
-                                    if (mx.up[ch] == o) v = m[o];
-                                delay2[ch * 64 + q] = v;
-                            }
-                        }
-                    }
-                    const float2 wl = win2[q], wh = win2[127 - q];      // (w[p], w[p+1]), (w[254-p], w[255-p])
-                    float y[6][4];                                       // [output][p, p+1, 254-p, 255-p]
-#pragma unroll
-                    for (int o = 0; o < 6; o++)
-#pragma unroll
-                        for (int r = 0; r < 4; r++) y[o][r] = 0.f;
-#pragma unroll
-                    for (int pl = 0; pl < 6; pl++) {
-                        const bool is_lfe = (pl == 5);
-                        bool live;
-                        if (is_lfe) live = lfe_on;
-                        else if (uniform) live = pl < nmain;
-                        else live = pl < nfchans && c->gain[pl] != 0.f;
-                        if (!live) continue;
+                    for (int pl = 0; pl < 2; pl++) {
                         const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
                         const float2 D = delay2[pl * 64 + q];
-                        const float a0 = D.x * wh.y - U.x * wl.x;        // sample p
-                        const float a1 = D.y * wh.x - U.y * wl.y;        // sample p + 1
-                        const float b0 = D.x * wl.x + U.x * wh.y;        // sample 255 - p
-                        const float b1 = D.y * wl.y + U.y * wh.x;        // sample 254 - p
+                        y[pl][0] = D.x * wh.y - U.x * wl.x;        // sample p
+                        y[pl][1] = D.y * wh.x - U.y * wl.y;        // sample p + 1
+                        y[pl][3] = D.x * wl.x + U.x * wh.y;        // sample 255 - p
+                        y[pl][2] = D.y * wl.y + U.y * wh.x;        // sample 254 - p
                         delay2[pl * 64 + q] = V;
-                        if (is_lfe) {
-                            y[0][0] = a0; y[0][1] = a1; y[0][2] = b1; y[0][3] = b0;
-                        } else if (uniform || identity) {
-#pragma unroll
-                            for (int oo = 0; oo < 6; oo++)
-                                if (oo == pl + lfe_on) { y[oo][0] = a0; y[oo][1] = a1; y[oo][2] = b1; y[oo][3] = b0; }
-                        } else {
-#pragma unroll
-                            for (int o = 0; o < 5; o++) {
-                                const float wgt = c->wt[o][pl];
-#pragma unroll
-                                for (int oo = 0; oo < 6; oo++)
-                                    if (o < nmain && oo == o + lfe_on) {
-                                        y[oo][0] = fmaf(wgt, a0, y[oo][0]);
-                                        y[oo][1] = fmaf(wgt, a1, y[oo][1]);
-                                        y[oo][2] = fmaf(wgt, b1, y[oo][2]);
-                                        y[oo][3] = fmaf(wgt, b0, y[oo][3]);
-                                    }
-                            }
-                        }
                     }
-                    const int p = 2 * q;
-                    if (P.out_fmt == 1 && nout == 2) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
-                        dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
-                        dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
-                    } else {
-#pragma unroll
-                        for (int oc = 0; oc < 6; oc++) {
-                            if (oc >= nout) continue;
-                            const float v0 = y[oc][0], v1 = y[oc][1], v2 = y[oc][2], v3 = y[oc][3];
-                            if (P.out_fmt == 0) {
-                                float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
-                                *reinterpret_cast<float2*>(dst + p) = make_float2(v0 + bias, v1 + bias);
-                                *reinterpret_cast<float2*>(dst + 254 - p) = make_float2(v2 + bias, v3 + bias);
-                            } else if (P.out_fmt == 1) {
-                                float* dst = reinterpret_cast<float*>(out_frame) + (size_t)blk * 256 * nout;
-                                dst[p * nout + oc] = v0 + bias;
-                                dst[(p + 1) * nout + oc] = v1 + bias;
-                                dst[(254 - p) * nout + oc] = v2 + bias;
-                                dst[(255 - p) * nout + oc] = v3 + bias;
-                            } else {
-                                int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
-                                dst[p * nout + oc] = (int16_t)min(max(__float2int_rn(v0 * 32768.f), -32768), 32767);
-                                dst[(p + 1) * nout + oc] = (int16_t)min(max(__float2int_rn(v1 * 32768.f), -32768), 32767);
-                                dst[(254 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v2 * 32768.f), -32768), 32767);
-                                dst[(255 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v3 * 32768.f), -32768), 32767);
-                            }
-                        }
-                    }
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
+                    dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
+                    dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+                } else {
+                    ola_store_generic(T, P, G, c, out_frame, blk, gt, nfchans, nmain, uniform, lfe_on);
                 }
                 sync();
                 if (gt == 0) c->per_channel = uniform ? 0 : 1;
