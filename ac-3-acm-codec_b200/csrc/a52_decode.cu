@@ -919,6 +919,13 @@ __device__ __forceinline__ uint32_t lfsr_jump32(uint32_t tab_base, uint32_t s)
 // Planes receive q * 2^-(15+exp) (exact); the channel gain is applied later
 // (mix weights, or a gain pass when every channel is transformed on its own).
 // ---------------------------------------------------------------------------
+// byte mask of the bins k0 .. k0+3 that still belong to a run of n bins
+__device__ __forceinline__ uint32_t run_mask(uint32_t n, uint32_t k0)
+{
+    const int rem = max(0, min((int)n - (int)k0, 4));
+    return __funnelshift_rc(0xffffffffu, 0u, 32 - 8 * rem);
+}
+
 __device__ __forceinline__ uint32_t make_desc(uint32_t exp, uint32_t bap, uint32_t pos)
 {
     return exp | (bap << 5) | (pos << 10);
@@ -1550,13 +1557,14 @@ a52_decode_kernel(const DecodeParams P)
                     uint32_t wlo = bapw[wi0];
                     for (uint32_t k = 0, j = 1; k < K; k += 4, j++) {
                         const uint32_t whi = bapw[wi0 + j];
-                        const uint32_t v = __funnelshift_r(wlo, whi, bsh);
+                        // bytes past my run select the all-zero row 16
+                        const uint32_t vm = run_mask(run_n, k);
+                        const uint32_t v = (__funnelshift_r(wlo, whi, bsh) & vm) | (0x10101010u & ~vm);
                         wlo = whi;
 #pragma unroll
                         for (int t = 0; t < 4; t++) {
-                            const uint32_t b = (k + t < run_n) ? ((v >> (8 * t)) & 0xff) : 16u;
                             uint32_t l;
-                            asm("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(lut32 + b * 4));
+                            asm("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(lut32 + prmt(v, 0, 0x4440 + t) * 4));
                             cnt += l;
                         }
                     }
@@ -1594,7 +1602,7 @@ a52_decode_kernel(const DecodeParams P)
                     const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);
                     uint32_t run_a = 0, run_z = 0;
                     const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
-                    const uint32_t zrow = (zmode == 1) ? 16u : 0u;
+                    const uint32_t zrow4 = (zmode == 1) ? 0x10101010u : 0u;
                     const uint32_t emit_bit = mute ? 0u : 0x1000000u;
                     // four mantissas per trip: one funnelled bap word and one exponent word, their four LUT
                     // rows fetched together, then the four updates in coded order
@@ -1624,9 +1632,9 @@ a52_decode_kernel(const DecodeParams P)
                             ew_lo = ew_hi;
                             uint4 Lr[4];
                             // mantissas past my run take the row of an undithered zero: nothing moves
+                            const uint32_t rows = (bv + zrow4) & run_mask(run_n, k0);
 #pragma unroll
-                            for (int t = 0; t < 4; t++)
-                                Lr[t] = lds_v4(lut_addr + ((k0 + t < run_n) ? (((bv >> (8 * t)) & 0xff) + zrow) : 0u) * 16);
+                            for (int t = 0; t < 4; t++) Lr[t] = lds_v4(lut_addr + prmt(rows, 0, 0x4440 + t) * 16);
 #pragma unroll
                             for (int t = 0; t < 4; t++)
                                 emit_one((bv >> (8 * t)) & 0xff, (ev >> (8 * t)) & 0xff, run_slot + k0 + t, Lr[t]);
