@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "liba52_b200.so")
 A52_CHANNEL, A52_MONO, A52_STEREO, A52_3F, A52_2F1R, A52_3F1R, A52_2F2R, A52_3F2R = range(8)
 A52_CHANNEL1, A52_CHANNEL2, A52_DOLBY = 8, 9, 10
 A52_CHANNEL_MASK, A52_LFE, A52_ADJUST_LEVEL = 15, 16, 32
-PCM_F32_PLANAR, PCM_F32_INTERLEAVED, PCM_S16_INTERLEAVED = 0, 1, 2
+PCM_F32_PLANAR, PCM_F32_INTERLEAVED, PCM_S16_INTERLEAVED, PCM_S16_WAV = 0, 1, 2, 3
+REQ_AS_CODED = 0x100          # include/a52_batch.h: every frame in its own coded mode (libao wav6)
 DEVICE_PTRS = 1
 DRC_STREAM, DRC_OFF = 0, 1
 ST_OK, ST_BAD_SYNC, ST_BAD_FRAME, ST_BAD_BLOCK = 0, 1, 2, 16
@@ -152,7 +153,7 @@ class BatchDecoder:
         stream_first = np.ascontiguousarray(stream_first, dtype=np.uint32)
         nframes, nstreams = len(frame_off), len(stream_first) - 1
         stride = self.L.a52_batch_frame_stride(req_flags, out_fmt)
-        dt = np.int16 if out_fmt == PCM_S16_INTERLEAVED else np.float32
+        dt = np.int16 if out_fmt >= PCM_S16_INTERLEAVED else np.float32
         pcm = np.zeros((nframes, stride // np.dtype(dt).itemsize), dt)
         status = np.zeros(nframes, np.int32)
         flags = np.zeros(nframes, np.int32)

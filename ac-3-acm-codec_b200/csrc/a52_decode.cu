@@ -110,6 +110,10 @@ struct __align__(16) GroupCtl {
     uint16_t plan_K;           // run length per lane
     float    wt[5][5];         // mix matrix [output][coded channel] in {-1, 0, +1} (downmix.c:480-619)
     int      identity_mix;     // output channel o is exactly coded channel o
+    int      nobias_mask;      // main outputs that get NO bias when the channels are transformed one by one:
+                               // with slev == 0 a52_downmix leaves 2/1, 2/2 -> stereo and 3/1, 3/2 -> 3F
+                               // without calling a mixer, and only the mixers add it (downmix.c:526-530,
+                               // 546-552, 563-573; parse.c:893-918)
     uint8_t  gains_dirty;      // dynrng / frame parameters changed since compute_gains()
     uint8_t  segs_dirty;       // coded ranges changed since the segment table was built
 };
@@ -311,6 +315,10 @@ __device__ int parse_frame_header(GroupCtl* c, const uint32_t* w, uint32_t base_
         for (int o = 0; o < mx.nout && ident; o++)
             if (mx.pos[o] != (1u << o) || mx.neg[o]) ident = 0;
         c->identity_mix = ident;
+        const int om = me.output & M_MASK;
+        c->nobias_mask = (slev != 0.f) ? 0
+                       : ((acmod == 4 || acmod == 6) && om == M_STEREO) ? 3
+                       : ((acmod == 5 || acmod == 7) && om == M_3F) ? 5 : 0;
     }
     // delta bit allocation is reset per frame for cpl + fbw (parse.c:173-175)
     c->deltbae[6] = 2;
@@ -619,6 +627,9 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         if (!same) {
             // K odd: consecutive lanes then write their descriptors to different shared-memory banks
             uint32_t K = ((flat + P.group_threads - 1) / P.group_threads) | 1;
+            // the 7 LFE bins stay in one lane: when the LFE channel is not requested its lane takes part in
+            // the bit count but not in the list cursors, which only works for the last lane of the block
+            if (c->lfeon && K < 7) K = 7;
             for (;; K += 2) {
                 uint32_t lanes = 0;
                 for (int k = 0; k < ns; k++) lanes += (c->seg[k].count + K - 1) / K;
@@ -1255,12 +1266,31 @@ __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes
 // Window + overlap-add (+ time-domain mix) + store of one block, every output format and both tail
 // representations; thread q owns positions p = 2q, 2q+1 (and their mirrors) of every plane.  Kept out of
 // line: the stereo float fast path in the kernel covers the common request, this covers the rest.
+// float -> int16 as libao does it (convert2s16.c:33-41): the sample carries the bias 384, so its bit pattern
+// minus that of 384.0f is round-to-nearest-even of x * 32768; the subtraction wraps like the reference's int32
+// does, and an output channel the reference left unbiased goes through the same arithmetic
+__device__ __forceinline__ int16_t s16_of(float v, bool biased)
+{
+    const float x = biased ? v + 384.f : v;
+    const int i = (int)((uint32_t)__float_as_int(x) - 0x43c00000u);
+    return (int16_t)min(max(i, -32768), 32767);
+}
+
+// libao's WAV sample order (convert2s16.c:199-306) per granted mode [+11 with LFE]: nibble ch = position
+// of liba52 plane ch inside a sample group, bits 24-27 = group stride, bits 28-31 = position filled with
+// convert (0) or 15.  Row 2F1R+LFE is the reference's fall-through (:270-285): groups of five.
+__constant__ uint32_t c_wavmap[22] = {
+    0xf2000010, 0xf1000000, 0xf2000010, 0xf3000120, 0xf3000210, 0xf4003120, 0xf4003210, 0xf5043120,
+    0xf1000000, 0xf1000000, 0xf2000010,
+    0xf3000102, 0xf2000001, 0xf3000102, 0xf4001203, 0x45001203, 0xf5041203, 0xf5043102, 0xf6541203,
+    0xf2000001, 0xf2000001, 0xf3000102};
+
 __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodeParams& P, const PairPtrs& G, const GroupCtl* c,
                                                uint8_t* out_frame, int blk, int gt, int nfchans, int nmain,
                                                bool uniform, int lfe_on)
 {
         const int nout = nmain + lfe_on;
-        const float bias = P.bias;
+        const int nobias = uniform ? 0 : c->nobias_mask;
         const bool identity = c->identity_mix;
         const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
         const float2* win2 = reinterpret_cast<const float2*>(T.window);
@@ -1342,7 +1372,10 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
             }
         }
         const int p = 2 * q;
-        if (P.out_fmt == 1 && nout == 2) {
+        const uint32_t wav_map = c_wavmap[(c->output & M_MASK) + (lfe_on ? 11 : 0)];
+        const int wav_stride = (wav_map >> 24) & 15, wav_fill = wav_map >> 28;
+        if (P.out_fmt == 1 && nout == 2 && !nobias) {
+            const float bias = P.bias;
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
             dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
             dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
@@ -1351,6 +1384,8 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
             for (int oc = 0; oc < 6; oc++) {
                 if (oc >= nout) continue;
                 const float v0 = y[oc][0], v1 = y[oc][1], v2 = y[oc][2], v3 = y[oc][3];
+                const bool biased = !(oc >= lfe_on && ((nobias >> (oc - lfe_on)) & 1));
+                const float bias = biased ? P.bias : 0.f;
                 if (P.out_fmt == 0) {
                     float* dst = reinterpret_cast<float*>(out_frame) + ((size_t)blk * nout + oc) * 256;
                     *reinterpret_cast<float2*>(dst + p) = make_float2(v0 + bias, v1 + bias);
@@ -1361,12 +1396,27 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
                     dst[(p + 1) * nout + oc] = v1 + bias;
                     dst[(254 - p) * nout + oc] = v2 + bias;
                     dst[(255 - p) * nout + oc] = v3 + bias;
+                } else if (P.out_fmt == 3) {
+                    // WAV channel order (convert2s16.c:199-306); a value lands where the reference puts it
+                    // and is dropped when that lies past the 256 * nout values wav_play writes
+                    int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
+                    const int pos = (wav_map >> (4 * oc)) & 15, lim = 256 * nout;
+                    const float vv[4] = {v0, v1, v2, v3};
+                    const int ss[4] = {p, p + 1, 254 - p, 255 - p};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const int idx = ss[r] * wav_stride + pos;
+                        if (idx < lim) dst[idx] = s16_of(vv[r], biased);
+                        // the slot the fall-through case reads from a plane nobody wrote: convert (+0.0f)
+                        const int fidx = ss[r] * wav_stride + wav_fill;
+                        if (oc == 0 && wav_fill != 15 && fidx < lim) dst[fidx] = (int16_t)-32768;
+                    }
                 } else {
                     int16_t* dst = reinterpret_cast<int16_t*>(out_frame) + (size_t)blk * 256 * nout;
-                    dst[p * nout + oc] = (int16_t)min(max(__float2int_rn(v0 * 32768.f), -32768), 32767);
-                    dst[(p + 1) * nout + oc] = (int16_t)min(max(__float2int_rn(v1 * 32768.f), -32768), 32767);
-                    dst[(254 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v2 * 32768.f), -32768), 32767);
-                    dst[(255 - p) * nout + oc] = (int16_t)min(max(__float2int_rn(v3 * 32768.f), -32768), 32767);
+                    dst[p * nout + oc] = s16_of(v0, biased);
+                    dst[(p + 1) * nout + oc] = s16_of(v1, biased);
+                    dst[(254 - p) * nout + oc] = s16_of(v2, biased);
+                    dst[(255 - p) * nout + oc] = s16_of(v3, biased);
                 }
             }
         }
@@ -1827,7 +1877,7 @@ a52_decode_kernel(const DecodeParams P)
             if (frame_ok && blk < 6) frame_status = 16 + blk;
             if (frame_status) {
                 int nout = frame_ok ? (c->nout + c->out_lfe) : P.nout_req;
-                int ssz = (P.out_fmt == 2) ? 2 : 4;
+                int ssz = (P.out_fmt >= 2) ? 2 : 4;
                 size_t from = (size_t)blk * 256 * nout * ssz;
                 size_t to = (size_t)6 * 256 * nout * ssz;
                 for (size_t i = from + gt * 4; i < to; i += NT * 4)

@@ -102,7 +102,10 @@ static void build_mode_table(ModeEntry* tab, int req_flags, float level)
                 int acmod = ae == 8 ? 2 : ae;
                 float clev, slev, lv = level;
                 host_mix_levels(acmod, cm, sm, &clev, &slev);
-                int out = host_downmix_init(ae == 8 ? M_DOLBY : acmod, req_flags, &lv, clev, slev);
+                // as-coded request: the frame's own mode is the request (what a52_syncinfo reports)
+                const int in_mode = ae == 8 ? M_DOLBY : acmod;
+                const int req = (req_flags & A52_REQ_AS_CODED) ? (in_mode | (req_flags & (M_LFE | M_ADJUST))) : req_flags;
+                int out = host_downmix_init(in_mode, req, &lv, clev, slev);
                 tab[ae * 16 + cm * 4 + sm].output = out;
                 tab[ae * 16 + cm * 4 + sm].level = lv;
             }
@@ -265,6 +268,7 @@ static void build_tables(Tables* T)
 
 static int nout_of_flags(int flags)
 {
+    if (flags & A52_REQ_AS_CODED) return 6;
     int m = flags & M_MASK;
     if (m > M_DOLBY) m = M_STEREO;
     return h_nfchans[m] + ((flags & M_LFE) ? 1 : 0);
@@ -504,7 +508,7 @@ int a52_batch_index_device(a52_batch_t* ctx, const uint8_t* es, const uint64_t* 
 
 size_t a52_batch_frame_stride(int req_flags, int out_fmt)
 {
-    return (size_t)1536 * a52::nout_of_flags(req_flags) * (out_fmt == A52_PCM_S16_INTERLEAVED ? 2 : 4);
+    return (size_t)1536 * a52::nout_of_flags(req_flags) * (out_fmt >= A52_PCM_S16_INTERLEAVED ? 2 : 4);
 }
 
 void a52_batch_set_max_frame_bytes(a52_batch_t* ctx, int nbytes) { ctx->max_frame_hint = nbytes; }
@@ -620,7 +624,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
     using namespace a52;
     if (!ctx) return -1;
     ctx->err[0] = 0;
-    if (nframes < 0 || nstreams < 0 || (req_flags & M_MASK) > M_DOLBY || out_fmt < 0 || out_fmt > 2) {
+    if (nframes < 0 || nstreams < 0 || (req_flags & M_MASK) > M_DOLBY || out_fmt < 0 || out_fmt > A52_PCM_S16_WAV) {
         snprintf(ctx->err, sizeof(ctx->err), "bad argument");
         return -3;
     }

@@ -1,7 +1,7 @@
 /* include/a52_batch.h - batched entry points of the B200 AC-3 engine (C ABI).
  *
  * One call decodes thousands of independent AC-3 streams: every stream is a
- * run of sync frames walked by one group of 128 GPU threads, frames of one
+ * run of sync frames walked by one pair of GPU warps, frames of one
  * stream in order (overlap-add tail and dither generator carried on chip),
  * streams in parallel.  This is the batched form of the per-frame loop every
  * liba52 caller writes (reference: a52dec.c:240-309 - a52_syncinfo, a52_frame,
@@ -32,6 +32,15 @@ typedef struct a52_batch_s a52_batch_t;
 #define A52_PCM_F32_INTERLEAVED 1   /* float [1536][nout] */
 #define A52_PCM_S16_INTERLEAVED 2   /* int16 [1536][nout], round-to-nearest of x*32768, saturated
 				       (== libao convert2s16.c:33-41 applied to bias-384 floats) */
+#define A52_PCM_S16_WAV         3   /* int16 [6][256][nout]: block by block in WAV channel order exactly as libao's
+				       convert2s16_wav lays it out (convert2s16.c:199-306: L R C LFE SL SR), the
+				       2F1R+LFE case with its fall-through into the 3F1R+LFE layout included
+				       (:270-285: five-sample groups L S R LFE -32768, cut after 1024 values) */
+
+/* OR-ed into req_flags (with A52_LFE / A52_ADJUST_LEVEL as wanted): every frame is decoded in its own coded
+ * mode, i.e. the request is the flags a52_syncinfo reports for that frame - what libao's wav6 driver does by
+ * leaving *flags alone (audio_out_wav.c:69-70, 211-214).  Frames keep the stride of six channels. */
+#define A52_REQ_AS_CODED        0x100
 
 #define A52_BATCH_DEVICE_PTRS   1
 

@@ -102,3 +102,23 @@ def test_no_cpu_fallback_without_gpu(engine):
         engine.BatchEncoder(0)
     with pytest.raises(RuntimeError):
         engine.BatchDecoder(0)
+
+
+def test_a52dec_cli_usage_and_no_cpu_fallback(engine, tmp_path, golden):
+    """The command line tool lists libao's driver names in libao's order
+    (audio_out.c:55-92, without the sound-card ones), rejects what a52dec.c:155-238 rejects, and - like
+    the library - has no CPU path to fall back to."""
+    exe = os.path.join(ROOT, "ac-3-acm-codec_b200", "a52dec_b200")
+    assert os.path.exists(exe), "run sh ac-3-acm-codec_b200/build.sh"
+    r = subprocess.run([exe, "-h"], capture_output=True, timeout=60)
+    assert r.returncode == 1
+    names = [ln.strip() for ln in r.stderr.decode().splitlines() if ln.startswith("\t\t\t")]
+    assert names == ["wav", "wavdolby", "wav6", "aif", "aifdolby", "peak", "peakdolby", "null", "null4", "null6", "float"]
+    for bad in (["-g", "97"], ["-o", "nosuch"], ["-t", "5"], ["-s", "9"], ["-C", "0"]):
+        assert subprocess.run([exe] + bad, capture_output=True, timeout=60, stdin=subprocess.DEVNULL).returncode == 1
+    import torch
+    if not torch.cuda.is_available():
+        p = tmp_path / "s.ac3"
+        golden["enc20_stereo_bias.es"].tofile(p)
+        r = subprocess.run([exe, "-o", "float", str(p)], capture_output=True, timeout=120)
+        assert r.returncode == 1 and r.stdout == b"" and b"init failed" in r.stderr

@@ -114,6 +114,7 @@ def test_c2_fixture_all_stages(decoder, engine, oracle, c2):
     (5, 1, A52_2F2R | A52_LFE, 1, 33), (5, 0, A52_STEREO, 0, 33), (5, 0, A52_2F1R | A52_ADJUST_LEVEL, 0, 33),
     (6, 0, A52_DOLBY | A52_ADJUST_LEVEL, 2, 30), (6, 0, A52_3F, 0, 30), (6, 0, A52_2F1R, 0, 30),
     (6, 1, A52_MONO | A52_ADJUST_LEVEL | A52_LFE, 0, 30),
+    (3, 1, A52_STEREO | A52_ADJUST_LEVEL, 0, 20), (1, 1, A52_MONO, 0, 14), (2, 1, A52_STEREO, 2, 16),
 ])
 def test_feature_streams(decoder, engine, oracle, acmod, lfe, flags, fscod, cod):
     es, fb = make_stream(2000 + acmod * 16 + (flags & 15), acmod, lfe, 4, oracle.bit_allocate, fscod=fscod,
@@ -143,6 +144,34 @@ def test_feature_streams(decoder, engine, oracle, acmod, lfe, flags, fscod, cod)
     nf, want = oracle.decode_stream(es, flags, 1.0, 0.0, dynrng_off=True)
     off, out = gpu_decode(decoder, engine, es, oracle, flags, drc=engine.DRC_OFF)
     assert relrms(planar(out, 4, nout), want) < TOL_PCM
+
+
+@pytest.mark.parametrize("acmod,flags", [(4, A52_STEREO), (6, A52_STEREO), (5, A52_3F), (7, A52_3F | A52_ADJUST_LEVEL),
+                                         (7, A52_STEREO), (6, A52_2F1R), (3, A52_DOLBY), (0, A52_MONO)])
+def test_bias_follows_the_reference_path_by_path(decoder, engine, oracle, acmod, flags):
+    """The bias is added by the IMDCT of pass-through channels and by the time-domain mixers; with slev == 0
+    liba52 calls no mixer for 2/1, 2/2 -> stereo and 3/1, 3/2 -> 3F, so blocks whose channels are transformed
+    one by one come out unbiased there (downmix.c:526-530, 546-552, 563-573; parse.c:893-918).  Floats and
+    libao's int16 (bit trick on the biased float, convert2s16.c:33-41) must follow."""
+    es, fb = make_stream(900 + acmod, acmod, 0, 6, oracle.bit_allocate, frmsizecod=30, features=dict(blksw=0.5))
+    for bias in (384.0, 1.0):
+        nf, want = oracle.decode_stream(es, flags, 1.0, bias)
+        off, out = gpu_decode(decoder, engine, es, oracle, flags, bias=bias)
+        got = planar(out, nf, want.shape[1])
+        d = (got.astype(np.float64) - want).reshape(-1)
+        # one ulp of a biased float is 2^-15 at 384: allow that on top of the relative bound
+        assert np.sqrt((d * d).mean()) < TOL_PCM * np.sqrt(((want - bias) ** 2).mean()) + (2.0 ** -15 if bias > 1 else 1e-7)
+        unbiased = np.abs(want.reshape(nf * 6, -1).mean(1) - bias) > 0.5 * bias
+        if acmod in (4, 6) and flags == A52_STEREO:
+            assert unbiased.any()                                      # the stream does exercise the quirk
+    nf, want = oracle.decode_stream(es, flags, 1.0, 384.0)
+    off, out = gpu_decode(decoder, engine, es, oracle, flags, bias=384.0, fmt=engine.PCM_S16_INTERLEAVED)
+    nout = want.shape[1]
+    got = out["pcm"].view(np.int16)[:, : 1536 * nout].reshape(nf * 6, 256, nout).transpose(0, 2, 1).astype(int)
+    ref16 = s16_of(want).astype(int)
+    # an unbiased sample converts to +-full scale by its sign alone: compare those away from zero only
+    keep = (np.abs(want - 384.0) < 192.0) | (np.abs(want) > 1e-3)
+    assert np.abs(got - ref16)[keep].max() <= 1 and keep.mean() > 0.9
 
 
 def test_transient_640k_stream(decoder, engine, oracle):

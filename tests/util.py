@@ -14,8 +14,10 @@ def relrms(a, b):
 
 
 def s16_of(pcm_bias384):
-    """libao's float(bias 384) -> int16 (convert2s16.c:33-41): bit pattern minus 0x43c00000, clamped."""
+    """libao's float(bias 384) -> int16 (convert2s16.c:33-41): bit pattern minus 0x43c00000 in wrapping int32
+    arithmetic (what the compiled reference does), clamped."""
     i = np.asarray(pcm_bias384, np.float32).view(np.int32).astype(np.int64) - 0x43C00000
+    i = (i + 2 ** 31) % 2 ** 32 - 2 ** 31
     return np.clip(i, -32768, 32767).astype(np.int16)
 
 
