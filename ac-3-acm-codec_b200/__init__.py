@@ -32,6 +32,8 @@ EXPORTS = [
     "AC3_encode_init", "AC3_encode_frame",
     "ac3_batch_create", "ac3_batch_destroy", "ac3_batch_last_error", "ac3_batch_frame_bytes",
     "ac3_batch_encode", "ac3_batch_launch_count", "ac3_batch_kernel_ms",
+    "ac3_wav_channel_map", "ac3_acm_bitrate", "ac3_acm_block_align",
+    "ac3_stream_open", "ac3_stream_convert", "ac3_stream_frame_bytes", "ac3_stream_close",
 ]
 
 
@@ -104,6 +106,16 @@ def load_library():
     L.ac3_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.ac3_batch_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    # encoder front end (include/ac3enc_batch.h)
+    L.ac3_wav_channel_map.argtypes = [C.c_int, C.c_void_p]
+    L.ac3_acm_bitrate.argtypes = [C.c_int, C.c_uint32]
+    L.ac3_acm_block_align.argtypes = [C.c_int, C.c_int]
+    L.ac3_stream_open.restype = C.c_void_p
+    L.ac3_stream_open.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int]
+    L.ac3_stream_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32,
+                                     C.POINTER(C.c_uint32), C.c_int]
+    L.ac3_stream_frame_bytes.argtypes = [C.c_void_p]
+    L.ac3_stream_close.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -320,3 +332,42 @@ class BatchEncoder:
         n = C.c_int(0)
         ms = self.L.ac3_batch_kernel_ms(self.ctx, C.byref(n))
         return ms, n.value
+
+
+def wav_channel_map(channels):
+    """chmap[coded channel] = WAVE-order source channel (create_channel_map, AC3ACM.cpp:1631-1662)."""
+    m = np.zeros(6, np.uint8)
+    if load_library().ac3_wav_channel_map(channels, m.ctypes.data):
+        raise ValueError("unsupported channel count %d" % channels)
+    return m[:channels]
+
+
+class PcmToAc3Stream:
+    """The ACM wrapper's PCM -> AC-3 stream conversion (stream_convert_pcm, AC3ACM.cpp:1665-1798) on the
+    batched encoder: convert(src bytes, dst capacity, start) -> (bytes of src consumed, bytes produced)."""
+
+    def __init__(self, encoder, freq, avg_bytes_per_sec, channels):
+        self.L = load_library()
+        self.enc = encoder
+        self.h = self.L.ac3_stream_open(encoder.ctx, freq, avg_bytes_per_sec, channels)
+        if not self.h:
+            raise ValueError("format refused (as the ACM stream open would)")
+        self.frame_bytes = self.L.ac3_stream_frame_bytes(self.h)
+
+    def convert(self, src, dst_len, start=False):
+        src = np.ascontiguousarray(np.frombuffer(bytes(src), np.uint8))
+        dst = np.zeros(max(dst_len, 1), np.uint8)
+        su, du = C.c_uint32(0), C.c_uint32(0)
+        rc = self.L.ac3_stream_convert(self.h, src.ctypes.data if len(src) else None, len(src), C.byref(su),
+                                       dst.ctypes.data, dst_len, C.byref(du), 1 if start else 0)
+        if rc:
+            raise RuntimeError("ac3_stream_convert failed (%d): %s" % (rc, self.L.ac3_batch_last_error(self.enc.ctx).decode()))
+        return su.value, bytes(dst[:du.value])
+
+    def close(self):
+        if self.h:
+            self.L.ac3_stream_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -11,3 +11,5 @@ $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
 CC=${CC:-gcc}
 $CC -O2 -std=gnu99 -Wall -Wextra -o "$here/a52dec_b200" "$here/cli/a52dec_b200.c" \
     -I"$here/../include" -L"$here" -l:liba52_b200.so -Wl,-rpath,'$ORIGIN' -lm
+$CC -O2 -std=gnu99 -Wall -Wextra -o "$here/ac3enc_b200" "$here/cli/ac3enc_b200.c" \
+    -I"$here/../include" -L"$here" -l:liba52_b200.so -Wl,-rpath,'$ORIGIN' -lm

@@ -310,6 +310,180 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
 }
 
 // ===========================================================================
+// encoder front end: the part of the ACM wrapper that sits around AC3_encode_frame
+// ===========================================================================
+int ac3_wav_channel_map(int channels, uint8_t chmap[6])      // AC3ACM.cpp:1631-1662
+{
+    // WAVE order FL FR FC LFE BL BR; coded order L C R SL SR LFE
+    static const uint8_t with_centre[6] = {0, 2, 1, 3, 4, 0}, six[6] = {0, 2, 1, 4, 5, 3};
+    switch (channels) {
+    case 1: case 2: case 4:
+        for (int i = 0; i < 4; i++) chmap[i] = (uint8_t)i;
+        return 0;
+    case 3: case 5:
+        for (int i = 0; i < 5; i++) chmap[i] = with_centre[i];
+        return 0;
+    case 6:
+        for (int i = 0; i < 6; i++) chmap[i] = six[i];
+        return 0;
+    }
+    return -1;
+}
+
+// 16-bit words per frame at 32 / 44.1 / 48 kHz for the 19 bitrates (AC3ACM.cpp:128-149); 44.1 kHz: the
+// unpadded size, which is what the encoder emits (ac3enc.cpp:1076-1077)
+static const uint16_t acm_kbps[19] = {32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512, 576, 640};
+
+static int acm_frame_words(int rate_index, int i)            // rate_index: 0 = 32 k, 1 = 44.1 k, 2 = 48 k
+{
+    const int kbps = acm_kbps[i];
+    return rate_index == 0 ? 3 * kbps : rate_index == 2 ? 2 * kbps : 320 * kbps / 147;
+}
+
+int ac3_acm_bitrate(int freq, uint32_t avg_bytes_per_sec)    // AC3ACM.cpp:1913-1936
+{
+    const uint32_t fl = avg_bytes_per_sec / 125;
+    for (int i = 0; i < 19; i++)
+        if (fl == acm_kbps[i]) return acm_kbps[i];
+    if (freq == 44100)
+        for (int i = 0; i < 19; i++)
+            if ((uint32_t)((acm_frame_words(1, i) * 2 * 44100 + 768) / 1536) == avg_bytes_per_sec) return acm_kbps[i];
+    return 0;
+}
+
+int ac3_acm_block_align(int freq, int kbps)                  // AC3ACM.cpp:951-953
+{
+    const int ri = freq == 32000 ? 0 : freq == 44100 ? 1 : freq == 48000 ? 2 : -1;
+    if (ri < 0) return 0;
+    for (int i = 0; i < 19; i++)
+        if (acm_kbps[i] == kbps) return acm_frame_words(ri, i) * 2;
+    return 0;
+}
+
+struct ac3_stream_s {
+    ac3_batch_t* ctx;
+    int freq, bitrate, channels, frame_bytes, needed;
+    uint8_t chmap[8];
+    ac3_stream_carry_t carry;
+    std::vector<uint8_t> buf;        // msd->buf: input gathered so far (< needed bytes between calls)
+    std::vector<uint8_t> frame;      // msd->frame: the last frame encoded
+    int fill;                        // msd->bufptr - msd->buf
+    int pending, pending_at;         // msd->blocks bytes of `frame` still owed, from msd->bufend
+    std::vector<int16_t> stage;
+    std::vector<uint8_t> out;
+};
+
+ac3_stream_t* ac3_stream_open(ac3_batch_t* ctx, int freq, uint32_t avg_bytes_per_sec, int channels)
+{
+    if (!ctx || freq < 32000) return nullptr;                // AC3ACM.cpp:1890-1891
+    const int kbps = ac3_acm_bitrate(freq, avg_bytes_per_sec);
+    if (!kbps) return nullptr;
+    const int fb = ac3_batch_frame_bytes(freq, kbps * 1000, channels);
+    if (!fb) return nullptr;
+    ac3_stream_t* s = new ac3_stream_s();
+    s->ctx = ctx;
+    s->freq = freq;
+    s->bitrate = kbps * 1000;
+    s->channels = channels;
+    s->frame_bytes = fb;
+    s->needed = 1536 * channels * (int)sizeof(int16_t);
+    memset(s->chmap, 0, sizeof(s->chmap));
+    ac3_wav_channel_map(channels, s->chmap);
+    memset(&s->carry, 0, sizeof(s->carry));
+    s->buf.resize(s->needed);
+    s->frame.resize(fb + 8);
+    s->fill = s->pending = s->pending_at = 0;
+    return s;
+}
+
+int ac3_stream_frame_bytes(ac3_stream_t* s) { return s ? s->frame_bytes : 0; }
+
+void ac3_stream_close(ac3_stream_t* s) { delete s; }
+
+int ac3_stream_convert(ac3_stream_t* s, const void* src_, uint32_t src_len, uint32_t* src_used, void* dst_,
+                       uint32_t dst_len, uint32_t* dst_used, int start)
+{
+    if (!s) return -1;
+    const uint8_t* src = (const uint8_t*)src_;
+    uint8_t* dst = (uint8_t*)dst_;
+    uint32_t sused = 0, dused = 0;
+    long srcLen = src_len, dstLen = dst_len;
+    if (start) {                                             // ACM_STREAMCONVERTF_START (:1705-1710)
+        s->fill = 0;
+        s->pending = s->pending_at = 0;
+    } else if (s->pending > 0) {                             // the rest of the last frame first (:1711-1734)
+        long tc = s->pending < dstLen ? s->pending : dstLen;
+        if (tc > 0) {
+            memcpy(dst, s->frame.data() + s->pending_at, tc);
+            dused += tc;
+            s->pending -= tc;
+            s->pending_at += tc;
+            dstLen -= tc;
+            dst += tc;
+        }
+        if (dstLen <= 0) {
+            if (src_used) *src_used = 0;
+            if (dst_used) *dst_used = dused;
+            return 0;
+        }
+    }
+    // Walk the reference's loop (:1743-1785) without encoding: it takes input until the gather buffer is full,
+    // encodes, hands out what fits, and stops after the frame that exhausts the destination.
+    int nframes = 0, fill = s->fill;
+    long consumed = 0;
+    {
+        long remaining = srcLen, room = dstLen;
+        while (remaining > 0) {
+            long tc = s->needed - fill;
+            if (tc > remaining) tc = remaining;
+            remaining -= tc;
+            consumed += tc;
+            fill += (int)tc;
+            if (fill >= s->needed) {
+                nframes++;
+                fill = 0;
+                room -= (s->frame_bytes < room ? s->frame_bytes : room);
+                if (room <= 0) break;
+            }
+        }
+    }
+    long tail_from = 0;                                      // input offset of the bytes that stay buffered
+    if (nframes > 0) {
+        // all frames of this call in one launch: the buffered head + input bytes
+        s->stage.resize((size_t)nframes * 1536 * s->channels);
+        uint8_t* st = (uint8_t*)s->stage.data();
+        memcpy(st, s->buf.data(), s->fill);
+        const long take = (long)nframes * s->needed - s->fill;
+        memcpy(st + s->fill, src, take);
+        tail_from = take;
+        s->fill = 0;
+        s->out.resize((size_t)nframes * s->frame_bytes);
+        int rc = ac3_batch_encode(s->ctx, s->stage.data(), 1, nframes, s->freq, s->bitrate, s->channels, s->chmap,
+                                  s->out.data(), nullptr, &s->carry, nullptr, 0, nullptr);
+        if (rc) return rc;
+        for (int f = 0; f < nframes; f++) {
+            const uint8_t* fr = s->out.data() + (size_t)f * s->frame_bytes;
+            long tc = s->frame_bytes < dstLen ? s->frame_bytes : dstLen;
+            if (tc > 0) memcpy(dst, fr, tc);
+            dused += tc;
+            dst += tc;
+            dstLen -= tc;
+            if (f == nframes - 1) {                          // msd->frame / msd->blocks / msd->bufend
+                memcpy(s->frame.data(), fr, s->frame_bytes);
+                s->pending = s->frame_bytes - (int)tc;
+                s->pending_at = (int)tc;
+            }
+        }
+    }
+    memcpy(s->buf.data() + s->fill, src + tail_from, consumed - tail_from);
+    s->fill += (int)(consumed - tail_from);
+    sused += consumed;
+    if (src_used) *src_used = sused;
+    if (dst_used) *dst_used = dused;
+    return 0;
+}
+
+// ===========================================================================
 // drop-in encoder API (include/ac3enc.h): a process-wide singleton like the reference's
 // (static AC3EncodeContext ac3enc_state, ac3enc.cpp:78)
 // ===========================================================================

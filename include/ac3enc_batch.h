@@ -64,6 +64,35 @@ int ac3_batch_encode (ac3_batch_t * ctx, const int16_t * pcm, int nstreams, int 
 		      uint8_t * out, int32_t * status, ac3_stream_carry_t * carry,
 		      const ac3_batch_debug_t * debug, int mem_flags, void * cuda_stream);
 
+/* ---- encoder front end: what the ACM wrapper does around AC3_encode_frame ---- */
+
+/* WAVE channel order (FL FR FC LFE BL BR) -> coded channel order: chmap[coded channel] = source channel, for
+ * 1..6 channels (reference: create_channel_map, AC3ACM.cpp:1631-1662).  Entries past `channels` are written as
+ * the reference writes them; returns 0, or -1 for a channel count it does not know. */
+int ac3_wav_channel_map (int channels, uint8_t chmap[6]);
+
+/* The bitrate in kb/s that a destination format names through nAvgBytesPerSec, validated as the ACM stream
+ * open does (AC3ACM.cpp:128-149, 1913-1936): 125 * one of the 19 AC-3 bitrates, or - 44.1 kHz only - the
+ * rounded byte rate of that bitrate's frame; 0 = not a supported format. */
+int ac3_acm_bitrate (int freq, uint32_t avg_bytes_per_sec);
+
+/* nBlockAlign of the format (AC3ACM.cpp:128-149, 951-953): frame bytes from the wrapper's table, 44.1 kHz
+ * frames unpadded; 0 for an unknown rate / bitrate. */
+int ac3_acm_block_align (int freq, int kbps);
+
+/* Streaming PCM -> AC-3 conversion with the buffering of stream_convert_pcm (AC3ACM.cpp:1665-1798): input is
+ * gathered into frames of 1536 samples per channel (WAVE channel order, mapped with ac3_wav_channel_map), a
+ * frame that does not fit the destination is carried over to the next call, input past a full destination
+ * stays unconsumed, a trailing partial frame stays buffered.  All whole frames one call completes are encoded
+ * in ONE launch.  ac3_stream_open returns NULL where the wrapper refuses the format (rate below 32 kHz,
+ * :1890-1891; byte rate not in the table; configuration AC3_encode_init rejects). */
+typedef struct ac3_stream_s ac3_stream_t;
+ac3_stream_t * ac3_stream_open (ac3_batch_t * ctx, int freq, uint32_t avg_bytes_per_sec, int channels);
+int ac3_stream_convert (ac3_stream_t * s, const void * src, uint32_t src_len, uint32_t * src_used,
+			void * dst, uint32_t dst_len, uint32_t * dst_used, int start);
+int ac3_stream_frame_bytes (ac3_stream_t * s);
+void ac3_stream_close (ac3_stream_t * s);
+
 long ac3_batch_launch_count (ac3_batch_t * ctx);
 double ac3_batch_kernel_ms (ac3_batch_t * ctx, int * nlaunches);
 
