@@ -348,6 +348,10 @@ struct a52_batch_s {
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
     uint16_t* d_dither = nullptr;
+    int host_chunk_streams = 128;  // streams per pipelined chunk of a host-pointer call
+    int host_concurrency = 4;      // chunk kernels in flight at once (a chunk alone is latency-bound: its CTAs
+                                   // are small, several launches share the SMs)
+    cudaStream_t s_runs[8] = {};
     int* d_counter = nullptr;      // [0..31] work counters (one per pipelined chunk), [63] max frame length
     cudaStream_t s_in = nullptr, s_out = nullptr, s_run = nullptr;   // host-mode pipeline: H2D, D2H, kernels
     cudaEvent_t ev_in[32] = {nullptr}, ev_run[32] = {nullptr};
@@ -403,6 +407,10 @@ a52_batch_t* a52_batch_create(int device)
     if (g) ctx->warps_per_cta = atoi(g);
     const char* sf = getenv("A52_B200_SLICE_FRAMES");
     if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
+    const char* hc = getenv("A52_B200_HOST_CHUNK_STREAMS");
+    if (hc && atoi(hc) > 0) ctx->host_chunk_streams = atoi(hc);
+    const char* hq = getenv("A52_B200_HOST_CONCURRENCY");
+    if (hq && atoi(hq) > 0 && atoi(hq) <= 8) ctx->host_concurrency = atoi(hq);
 
     // constant tables
     a52::Tables* T = new a52::Tables;
@@ -445,6 +453,8 @@ void a52_batch_destroy(a52_batch_t* ctx)
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->s_run) cudaStreamDestroy(ctx->s_run);
+    for (int i = 0; i < 8; i++)
+        if (ctx->s_runs[i]) cudaStreamDestroy(ctx->s_runs[i]);
     for (int i = 0; i < 32; i++) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_run[i]) cudaEventDestroy(ctx->ev_run[i]);
@@ -535,8 +545,11 @@ double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
     return n ? total / n : 0.0;
 }
 
+// scratch_base / scratch_total: position of this launch's streams inside the per-stream scratch arrays when
+// several launches of one call are in flight at once (host pipeline); 0 / 0 = a launch on its own
 static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int max_frame_bytes,
-                         float level, cudaStream_t st, int counter_slot = 0, int max_stream_frames = 0)
+                         float level, cudaStream_t st, int counter_slot = 0, int max_stream_frames = 0,
+                         int scratch_base = 0, int scratch_total = 0)
 {
     using namespace a52;
     // work units of the pair kernel: slices of streams (see a52_decode_kernel)
@@ -546,12 +559,13 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.slice_done = nullptr;
     if (ctx->pair_kernel && max_stream_frames > ctx->slice_frames) {
         P.nslices = (max_stream_frames + ctx->slice_frames - 1) / ctx->slice_frames;
-        if (ensure(ctx, ctx->b_done, (size_t)P.nstreams * sizeof(int))) return -1;
-        A52_CUDA(cudaMemsetAsync(ctx->b_done.p, 0, (size_t)P.nstreams * sizeof(int), st));
-        P.slice_done = (int*)ctx->b_done.p;
+        const size_t total = scratch_total ? (size_t)scratch_total : (size_t)P.nstreams;
+        if (ensure(ctx, ctx->b_done, total * sizeof(int))) return -1;
+        A52_CUDA(cudaMemsetAsync((int*)ctx->b_done.p + scratch_base, 0, (size_t)P.nstreams * sizeof(int), st));
+        P.slice_done = (int*)ctx->b_done.p + scratch_base;
         if (!P.carry) {
-            if (ensure(ctx, ctx->b_slice, (size_t)P.nstreams * sizeof(StreamCarry))) return -1;
-            P.carry = (StreamCarry*)ctx->b_slice.p;
+            if (ensure(ctx, ctx->b_slice, total * sizeof(StreamCarry))) return -1;
+            P.carry = (StreamCarry*)ctx->b_slice.p + scratch_base;
         }
     }
     // per-request constants
@@ -684,6 +698,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
         A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
         A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) A52_CUDA(cudaStreamCreateWithFlags(&ctx->s_runs[i], cudaStreamNonBlocking));
         for (int i = 0; i < 32; i++) {
             A52_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
             A52_CUDA(cudaEventCreateWithFlags(&ctx->ev_run[i], cudaEventDisableTiming));
@@ -742,7 +757,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
     A52_CUDA(cudaStreamSynchronize(s_run));
 
     // chunk plan: contiguous stream ranges; each chunk's bitstream is the byte span of its frames
-    int nchunks = nstreams / 256;
+    int nchunks = nstreams / ctx->host_chunk_streams;
     if (nchunks > 32) nchunks = 32;
     if (nchunks < 1) nchunks = 1;
     std::vector<size_t> cb0(nchunks), cb1(nchunks);
@@ -772,14 +787,16 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         int s0 = (int)((long long)cidx * nstreams / nchunks), s1 = (int)((long long)(cidx + 1) * nstreams / nchunks);
         uint32_t fa = stream_first[s0], fb = stream_first[s1];
         if (s1 == s0) continue;
+        // chunk kernels go round the run streams: a caller-given stream keeps them in order on itself
+        cudaStream_t s_k = st ? st : ctx->s_runs[cidx % ctx->host_concurrency];
         if (slice_input) {
             if (cb1[cidx] > cb0[cidx])
                 A52_CUDA(cudaMemcpyAsync((uint8_t*)ctx->b_es.p + cb0[cidx], es + cb0[cidx], cb1[cidx] - cb0[cidx],
                                          cudaMemcpyHostToDevice, s_in));
             A52_CUDA(cudaEventRecord(ctx->ev_in[cidx], s_in));
-            A52_CUDA(cudaStreamWaitEvent(s_run, ctx->ev_in[cidx], 0));
-        } else if (cidx == 0) {
-            A52_CUDA(cudaStreamWaitEvent(s_run, ctx->ev_in[0], 0));
+            A52_CUDA(cudaStreamWaitEvent(s_k, ctx->ev_in[cidx], 0));
+        } else {
+            A52_CUDA(cudaStreamWaitEvent(s_k, ctx->ev_in[0], 0));
         }
         DecodeParams Pc = P;
         Pc.stream_first = (const uint32_t*)ctx->b_first.p + s0;
@@ -790,14 +807,16 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             int n = (int)(stream_first[q + 1] - stream_first[q]);
             if (n > chunk_max) chunk_max = n;
         }
-        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_run, cidx, chunk_max);
+        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_k, cidx, chunk_max, s0, nstreams);
         if (rc) return rc;
-        A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_run));
+        A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_k));
         A52_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_run[cidx], 0));
         if (fb > fa)
             A52_CUDA(cudaMemcpyAsync((uint8_t*)pcm_out + (size_t)fa * stride, Pc.pcm + (size_t)fa * stride,
                                      (size_t)(fb - fa) * stride, cudaMemcpyDeviceToHost, s_out));
     }
+    if (!st)
+        for (int i = 0; i < ctx->host_concurrency; i++) A52_CUDA(cudaStreamSynchronize(ctx->s_runs[i]));
     A52_CUDA(cudaStreamSynchronize(s_run));
     if (frame_status) A52_CUDA(cudaMemcpyAsync(frame_status, P.status, (size_t)nframes * 4, cudaMemcpyDeviceToHost, s_run));
     if (frame_flags) A52_CUDA(cudaMemcpyAsync(frame_flags, P.frame_flags, (size_t)nframes * 4, cudaMemcpyDeviceToHost, s_run));
