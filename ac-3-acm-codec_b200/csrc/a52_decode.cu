@@ -72,6 +72,7 @@ struct __align__(16) GroupCtl {
     int      stream;           // current stream index (-1 = done)
     int      frame_ok;         // frame header valid
     int      err;              // error raised inside the current block
+    int      tr_ticket;        // transform jobs of the pending block handed out so far
     uint32_t base_bit;         // bit offset of the frame inside the staged buffer
     uint32_t limit_bit;        // end of frame (bits) inside the staged buffer
     uint32_t bitpos;           // cursor (bits), advanced block by block
@@ -1530,15 +1531,77 @@ a52_decode_kernel(const DecodeParams P)
                 sync();
             }
 
+            // The transforms of a block run while thread 0 reads the side information of the NEXT block: the
+            // other warp starts on them at once, the parsing warp joins when it is through (jobs by ticket).
+            // What they need of the finished block is kept in registers (p_*); a seventh pass flushes block 5.
             int blk = 0;
-            for (; blk < 6 && frame_ok; blk++) {
+            bool pend = false;
+            int p_blk = 0;
+            uint32_t p_live = 0, p_blksw = 0;
+            bool p_uniform = false;
+            if (frame_ok)
+            for (;; blk++) {
+                const bool more = blk < 6;
                 // dither states of this block's first rows (row r of the zero list goes to warp r & 1);
                 // requested early so that the L2 latency hides behind the side information
-                uint32_t ring = P.dither_seq[(dither_index + 1 + 32 * w + lane) % kDitherPeriod];
-                // ================= P =================
-                if (gt == 0) c->err = parse_block(c, W, P);
+                uint32_t ring = 0;
+                if (more) ring = P.dither_seq[(dither_index + 1 + 32 * w + lane) % kDitherPeriod];
+                // ================= P (block blk) | T (block blk - 1) =================
+                if (more && gt == 0) c->err = parse_block(c, W, P);
+                __syncwarp();
+                if (pend) {
+                    const int njobs = __popc(p_live);
+                    for (;;) {
+                        int j = 0;
+                        if (lane == 0) j = atomicAdd(&c->tr_ticket, 1);
+                        j = __shfl_sync(0xffffffffu, j, 0);
+                        if (j >= njobs) break;
+                        uint32_t m = p_live;
+                        for (int k = 0; k < j; k++) m &= m - 1;
+                        const int pl = __ffs(m) - 1;
+                        const bool shortblk = (pl < 5) && ((p_blksw >> (p_uniform ? 0 : pl)) & 1);
+                        if (shortblk) imdct256_warp(T, G.plane + pl * 256, lane);
+                        else imdct512_warp(T, G.plane + pl * 256, lane);
+                    }
+                }
                 sync();
-                if (c->err) break;
+                // ================= O (block blk - 1) =================
+                if (pend) {
+                    const int nmain = c->nout, lfe_on = c->out_lfe, nfch = c->nfchans;
+                    // thread q = gt owns positions p = 2q, 2q+1 (and their mirrors 254-p, 255-p) of every plane
+                    if (p_uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt == 1) {
+                        // the common request: two mixed planes, tails already downmixed, interleaved float out
+                        const float bias = P.bias;
+                        const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
+                        const float2* win2 = reinterpret_cast<const float2*>(T.window);
+                        float2* delay2 = reinterpret_cast<float2*>(G.delay);
+                        const int q = gt;
+                        const float2 wl = win2[q], wh = win2[127 - q];
+                        float y[2][4];
+#pragma unroll
+                        for (int pl = 0; pl < 2; pl++) {
+                            const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
+                            const float2 D = delay2[pl * 64 + q];
+                            y[pl][0] = D.x * wh.y - U.x * wl.x;        // sample p
+                            y[pl][1] = D.y * wh.x - U.y * wl.y;        // sample p + 1
+                            y[pl][3] = D.x * wl.x + U.x * wh.y;        // sample 255 - p
+                            y[pl][2] = D.y * wl.y + U.y * wh.x;        // sample 254 - p
+                            delay2[pl * 64 + q] = V;
+                        }
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)p_blk * 512);
+                        dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
+                        dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+                    } else {
+                        ola_store_generic(T, P, G, c, out_frame, p_blk, gt, nfch, nmain, p_uniform, lfe_on);
+                    }
+                    sync();
+                    if (gt == 0) {
+                        c->per_channel = p_uniform ? 0 : 1;
+                        c->tr_ticket = 0;
+                    }
+                    pend = false;
+                }
+                if (!more || c->err) break;
                 const int nfchans = c->nfchans;
                 const uint32_t chincpl = c->chincpl;
                 const uint32_t limit = c->limit_bit;
@@ -1824,53 +1887,23 @@ a52_decode_kernel(const DecodeParams P)
                     case 3: mix_planes<3, NT>(G.plane, c, gt); break;
                     default: mix_planes<4, NT>(G.plane, c, gt); break;
                     }
-                    sync();
                 }
 
-                // ================= T: planes alternate between the warps =================
+                // the transforms wait for the next pass: what they need of this block
                 {
                     const int ntr = uniform ? nmain : nfchans;
-                    int job = 0;
+                    uint32_t live = 0;
                     for (int pl = 0; pl < 6; pl++) {
                         if (pl < 5 ? (pl >= ntr) : !lfe_on) continue;
                         if (!uniform && pl < 5 && c->gain[pl] == 0.f) continue;
-                        if ((job++ & 1) != w) continue;
-                        bool shortblk = (pl < 5) && ((c->blksw >> (uniform ? 0 : pl)) & 1);
-                        if (shortblk) imdct256_warp(T, G.plane + pl * 256, lane);
-                        else imdct512_warp(T, G.plane + pl * 256, lane);
+                        live |= 1u << pl;
                     }
+                    p_live = live;
+                    p_blksw = c->blksw;
+                    p_uniform = uniform;
+                    p_blk = blk;
+                    pend = true;
                 }
-                sync();
-
-                // ================= O =================
-                // thread q = gt owns positions p = 2q, 2q+1 (and their mirrors 254-p, 255-p) of every plane
-                if (uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt == 1) {
-                    // the common request: two mixed planes, tails already downmixed, interleaved float out
-                    const float bias = P.bias;
-                    const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
-                    const float2* win2 = reinterpret_cast<const float2*>(T.window);
-                    float2* delay2 = reinterpret_cast<float2*>(G.delay);
-                    const int q = gt;
-                    const float2 wl = win2[q], wh = win2[127 - q];
-                    float y[2][4];
-#pragma unroll
-                    for (int pl = 0; pl < 2; pl++) {
-                        const float2 U = plane2[pl * 128 + q], V = plane2[pl * 128 + 64 + q];
-                        const float2 D = delay2[pl * 64 + q];
-                        y[pl][0] = D.x * wh.y - U.x * wl.x;        // sample p
-                        y[pl][1] = D.y * wh.x - U.y * wl.y;        // sample p + 1
-                        y[pl][3] = D.x * wl.x + U.x * wh.y;        // sample 255 - p
-                        y[pl][2] = D.y * wl.y + U.y * wh.x;        // sample 254 - p
-                        delay2[pl * 64 + q] = V;
-                    }
-                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
-                    dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
-                    dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
-                } else {
-                    ola_store_generic(T, P, G, c, out_frame, blk, gt, nfchans, nmain, uniform, lfe_on);
-                }
-                sync();
-                if (gt == 0) c->per_channel = uniform ? 0 : 1;
                 sync();
             }   // blocks
 
