@@ -455,3 +455,64 @@ def test_large_batch_properties(decoder, engine, oracle, c2):
         d = c2["digest"][b]
         p = got.astype(np.float64)
         assert abs((p * p).sum() - d[1]) / d[1] < 1e-5
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_sweep_heterogeneous_batches(decoder, engine, oracle, seed):
+    """Randomised breadth: 14 synthetic streams per seed with random coded mode, LFE, sample rate, frame size,
+    feature mix and length go through ONE launch per request (6 random requests incl. the as-coded one), in a
+    random output format; PCM, granted flags and per-frame status are compared with the oracle stream by
+    stream.  (The narrow-band / unrequested-LFE defect was of the kind only such mixes hit.)"""
+    rng = np.random.RandomState(1000 + seed)
+    streams = []
+    while len(streams) < 14:
+        acmod, lfe, fscod = int(rng.randint(8)), int(rng.randint(2)), int(rng.randint(3))
+        cod = int(rng.choice([14, 20, 24, 28, 30, 33, 36]))
+        feats = dict(blksw=float(rng.choice([0, 0.3, 0.8])), cpl=float(rng.choice([0, 0.7])),
+                     dynrng=float(rng.rand()), deltba=float(rng.choice([0, 0.3])), reuse=float(rng.rand()),
+                     dith=float(rng.choice([0, 0.8, 1.0])))
+        try:
+            es, fb = make_stream(int(rng.randint(1 << 30)), acmod, lfe, int(rng.randint(1, 6)), oracle.bit_allocate,
+                                 fscod=fscod, frmsizecod=cod, features=feats)
+        except (RuntimeError, AssertionError):
+            continue                                   # this mode does not fit that frame size
+        streams.append((es, acmod, lfe))
+    chunks, off, first, pos = [], [], [0], 0
+    for es, _, _ in streams:
+        o = frame_offsets(es, oracle)
+        pad = (-len(es)) % 16
+        off += [pos + int(x) for x in o]
+        first.append(first[-1] + len(o))
+        chunks.append(np.concatenate([es, np.zeros(pad, np.uint8)]))
+        pos += len(es) + pad
+    whole = np.concatenate(chunks)
+    off, first = np.array(off, np.uint64), np.array(first, np.uint32)
+    requests = [A52_STEREO | A52_ADJUST_LEVEL, A52_3F2R | A52_LFE, engine.REQ_AS_CODED | A52_LFE | A52_ADJUST_LEVEL]
+    requests += [int(rng.choice([A52_MONO, A52_DOLBY, A52_3F, A52_2F1R, A52_3F1R, A52_2F2R, A52_CHANNEL1]))
+                 | int(rng.choice([0, A52_LFE])) | int(rng.choice([0, A52_ADJUST_LEVEL])) for _ in range(3)]
+    for req in requests:
+        fmt = int(rng.choice([engine.PCM_F32_PLANAR, engine.PCM_F32_INTERLEAVED, engine.PCM_S16_INTERLEAVED]))
+        bias = 384.0 if fmt == engine.PCM_S16_INTERLEAVED else float(rng.choice([0.0, 1.0]))
+        level = float(rng.choice([1.0, 0.5]))
+        out = decoder.decode_host(whole, off, first, req, level, bias, out_fmt=fmt)
+        for k, (es, acmod, lfe) in enumerate(streams):
+            r = req
+            if req & engine.REQ_AS_CODED:               # the request a52dec's wav6 makes: what a52_syncinfo reports
+                r = (oracle.syncinfo(es[:7])[1] | (req & A52_ADJUST_LEVEL))
+            nf, want = oracle.decode_stream(es, r, level, bias)
+            sl = slice(first[k], first[k + 1])
+            assert (out["status"][sl] == 0).all(), (req, k, out["status"][sl])
+            dump = oracle.decode_dump(es, req_flags=r)
+            assert out["flags"][first[k]] == dump[0]["out_flags"], (req, k)
+            nout = want.shape[1]
+            raw = out["pcm"][sl]
+            if fmt == engine.PCM_F32_PLANAR:
+                got = raw[:, :6 * nout * 256].reshape(nf * 6, nout, 256)
+            else:
+                got = raw[:, :1536 * nout].reshape(nf * 6, 256, nout).transpose(0, 2, 1)
+            if fmt == engine.PCM_S16_INTERLEAVED:
+                keep = (np.abs(want - 384.0) < 192.0) | (np.abs(want) > 1e-3)
+                assert np.abs(got.astype(int) - s16_of(want).astype(int))[keep].max() <= 1, (req, k)
+            else:
+                d = (got.astype(np.float64) - want).reshape(-1)
+                assert np.sqrt((d * d).mean()) <= TOL_PCM * np.sqrt(((want - bias) ** 2).mean()) + (1e-7 if bias == 0 else 2.0 ** -15 * (bias > 1) + 1e-6), (req, k)
