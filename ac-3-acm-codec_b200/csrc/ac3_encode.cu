@@ -90,8 +90,8 @@ struct EncShared {
     uint8_t  enc[6][6][256];             // exponents as the decoder will see them (run heads)
     int16_t  last[6][256];               // previous 256 samples per coded channel
     union {
-        // E1..E3: one block of interleaved input, FFT scratch, masking curves before the snr offset (run heads)
-        struct { int16_t pcmblk[256 * 6]; uint32_t z[6][128]; int16_t mask[6][6][50]; } e1;
+        // E1..E3: FFT scratch, masking curves before the snr offset (run heads)
+        struct { uint32_t z[6][128]; int16_t mask[6][6][50]; } e1;
         // E4: the frame being packed, group-code accumulators and their bit positions
         struct { uint32_t frame[kFrameWords]; uint32_t codes[kCodes]; uint16_t gpos[kCodes]; } e4;
     } u;
@@ -189,18 +189,19 @@ __device__ uint32_t warp_crc(const EncTables& T, const uint32_t* frame, int b0, 
 // ---------------------------------------------------------------------------
 // E1: one (block, channel): window, normalise, MDCT-512, exponents.  One warp.
 // ---------------------------------------------------------------------------
-__device__ void e1_transform(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane)
+// `smp[r]` = the block's new sample lane + 32 r of this channel (the caller fetches them a block ahead)
+__device__ __forceinline__ void e1_transform(EncShared& S, const EncTables& T, int blk, int ch, int lane,
+                                             const int (&smp_in)[8])
 {
     int16_t* in = reinterpret_cast<int16_t*>(S.coef[blk][ch]);       // 512 samples live in the coefficient slot
     uint32_t* z = S.u.e1.z[ch];
-    const int src = P.chmap[ch];
     // previous 256 samples | new 256 samples, windowed (ac3enc.cpp:1673-1693)
     uint32_t amax = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const int j = lane + 32 * r;
         const int old = S.last[ch][j];
-        const int cur = S.u.e1.pcmblk[j * P.nch_all + src];
+        const int cur = smp_in[r];
         S.last[ch][j] = (int16_t)cur;
         const int a = (int16_t)((old * T.window[j]) >> 15);
         const int b = (int16_t)((cur * T.window[255 - j]) >> 15);
@@ -587,14 +588,27 @@ ac3_encode_kernel(const EncParams P)
             const size_t fidx = (size_t)s * P.nframes + f;
             const int16_t* pcm = P.pcm + fidx * 1536 * P.nch_all;
             // ================= E1 =================
-            for (int blk = 0; blk < 6; blk++) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(pcm + (size_t)blk * 256 * P.nch_all);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(S.u.e1.pcmblk);
-                for (int i = tid; i < 128 * P.nch_all; i += kThreads) dst[i] = src[i];
-                __syncthreads();
-                if (active) e1_transform(S, T, P, blk, warp, lane);
-                __syncthreads();
+            // a warp works through its channel's six blocks on its own: samples straight from global memory
+            // (the six warps of the CTA share the lines), one block ahead of the transform that uses them
+            if (active) {
+                const int16_t* mine = pcm + P.chmap[warp];
+                int nxt[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) nxt[r] = __ldg(mine + (size_t)(lane + 32 * r) * P.nch_all);
+#pragma unroll 1
+                for (int blk = 0; blk < 6; blk++) {
+                    int cur[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) cur[r] = nxt[r];
+                    if (blk < 5) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++)
+                            nxt[r] = __ldg(mine + (size_t)((blk + 1) * 256 + lane + 32 * r) * P.nch_all);
+                    }
+                    e1_transform(S, T, blk, warp, lane, cur);
+                }
             }
+            if (P.dbg_coef) __syncthreads();
             if (P.dbg_coef) {
                 for (int i = tid; i < 6 * 6 * 256; i += kThreads) {
                     const int ch = (i >> 8) % 6;
@@ -604,6 +618,7 @@ ac3_encode_kernel(const EncParams P)
             }
             // ================= E2 =================
             if (active) {
+                __syncwarp();
                 const int bits = e2_exponents(S, P, warp, lane);
                 if (lane == 0) S.exp_bits[warp] = bits;
             }
@@ -682,26 +697,62 @@ ac3_encode_kernel(const EncParams P)
             for (int i = tid; i < kFrameWords; i += kThreads) frame[i] = 0;
             for (int i = tid; i < kCodes; i += kThreads) S.u.e4.codes[i] = 0;
             __syncthreads();
-            if (tid == 0) {
-                // side information, serial (:1113-1147, 1210-1259, 1316-1337); sections written by the
-                // warps are skipped over and their positions recorded
+            if (warp == 0) {
+                // side information (:1113-1147, 1210-1259, 1316-1337): lane 0 writes the BSI, lanes 0..5 then
+                // size one block each, a prefix sum places the blocks, and every lane writes its block's
+                // fields; sections written later by the channel warps are skipped over, positions recorded
                 SerialBits w{frame, 0};
-                w.put(16, 0x0b77);
-                w.put(16, 0);
-                w.put(2, P.fscod);
-                w.put(6, P.frmsizecod);
-                w.put(5, P.bsid);
-                w.put(3, 0);
-                w.put(3, P.acmod);
-                if ((P.acmod & 1) && P.acmod != 1) w.put(2, 1);
-                if (P.acmod & 4) w.put(2, 1);
-                if (P.acmod == 2) w.put(2, 0);
-                w.put(1, P.lfe);
-                w.put(5, 31);
-                w.put(4, 0);
-                w.put(1, 1);
-                w.put(3, 0);
-                for (int blk = 0; blk < 6; blk++) {
+                if (lane == 0) {
+                    w.put(16, 0x0b77);
+                    w.put(16, 0);
+                    w.put(2, P.fscod);
+                    w.put(6, P.frmsizecod);
+                    w.put(5, P.bsid);
+                    w.put(3, 0);
+                    w.put(3, P.acmod);
+                    if ((P.acmod & 1) && P.acmod != 1) w.put(2, 1);
+                    if (P.acmod & 4) w.put(2, 1);
+                    if (P.acmod == 2) w.put(2, 0);
+                    w.put(1, P.lfe);
+                    w.put(5, 31);
+                    w.put(4, 0);
+                    w.put(1, 1);
+                    w.put(3, 0);
+                }
+                const uint32_t bsi_bits = __shfl_sync(0xffffffffu, w.pos, 0);
+                const int blk = lane < 6 ? lane : 5;
+                uint32_t exp_len[6], len = 0, mant = 0;
+                {
+                    int nnew = 0, n1 = 0, n2 = 0, n4 = 0;
+                    for (int ch = 0; ch < P.nch; ch++) nnew += S.strategy[blk][ch] != 0;
+#pragma unroll
+                    for (int ch = 0; ch < 6; ch++) {
+                        exp_len[ch] = 0;
+                        if (ch >= P.nch_all) continue;
+                        const int st = S.strategy[blk][ch];
+                        if (st) {
+                            const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
+                            const int ng = (((P.lfe && ch == 5) ? 7 : 223) + gs * 3 - 4) / (3 * gs);
+                            exp_len[ch] = 4 + 7 * ng + ((P.lfe && ch == 5) ? 0 : 2);
+                        }
+                        const int* q = S.cnt[S.head[blk][ch]][ch];
+                        n1 += q[0]; n2 += q[1]; n4 += q[2]; mant += q[3];
+                        len += exp_len[ch];
+                    }
+                    mant += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
+                    len += 2 * P.nch + 1 + (blk == 0 ? 2 : 1) + (P.acmod == 2 ? (blk == 0 ? 5 : 1) : 0)
+                         + 2 * P.nch + (P.lfe ? 1 : 0) + 6 * nnew
+                         + 1 + (blk == 0 ? 11 : 0) + 1 + (blk == 0 ? 6 + 7 * P.nch_all : 0) + 2 + mant;
+                    if (lane >= 6) len = 0;
+                }
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane < 6) {
+                    w.pos = bsi_bits + incl - len;
                     w.put(P.nch, 0);                                     // blksw
                     w.put(P.nch, (1u << P.nch) - 1);                     // dithflag
                     w.put(1, 0);                                         // dynrnge
@@ -711,13 +762,11 @@ ac3_encode_kernel(const EncParams P)
                     if (P.lfe) w.put(1, S.strategy[blk][5]);
                     for (int ch = 0; ch < P.nch; ch++)
                         if (S.strategy[blk][ch]) w.put(6, 50);
-                    for (int ch = 0; ch < P.nch_all; ch++) {
-                        const int st = S.strategy[blk][ch];
-                        if (!st) continue;
-                        const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
-                        const int ng = (((P.lfe && ch == 5) ? 7 : 223) + gs * 3 - 4) / (3 * gs);
+#pragma unroll
+                    for (int ch = 0; ch < 6; ch++) {
+                        if (ch >= P.nch_all || !exp_len[ch]) continue;
                         S.exp_pos[blk][ch] = w.pos;
-                        w.pos += 4 + 7 * ng + ((P.lfe && ch == 5) ? 0 : 2);
+                        w.pos += exp_len[ch];
                     }
                     w.put(1, blk == 0);
                     if (blk == 0) w.put(11, (2u << 9) | (1u << 7) | (1u << 5) | (2u << 3) | 4u);
@@ -728,12 +777,6 @@ ac3_encode_kernel(const EncParams P)
                     }
                     w.put(2, 0);
                     S.mant_pos[blk] = w.pos;
-                    int n1 = 0, n2 = 0, n4 = 0;
-                    for (int ch = 0; ch < P.nch_all; ch++) {
-                        const int* q = S.cnt[S.head[blk][ch]][ch];
-                        n1 += q[0]; n2 += q[1]; n4 += q[2]; w.pos += q[3];
-                    }
-                    w.pos += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
                 }
             }
             __syncthreads();
