@@ -114,6 +114,9 @@ struct ac3_batch_s {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     struct Buf { void* p = nullptr; size_t cap = 0; } b_pcm, b_out, b_status, b_carry, b_coef, b_shift, b_strat, b_enc, b_bap, b_snr;
+    // host-pointer calls: PCM H2D | kernel | frames D2H on three streams, chunks of streams
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[16] = {}, ev_run[16] = {};
 };
 
 #define AC3_CUDA(call)                                                                       \
@@ -155,7 +158,7 @@ ac3_batch_t* ac3_batch_create(int device)
     ac3e::build_enc_tables(T);
     bool ok = cudaMemcpyToSymbol(ac3e::g_enc_tables, T, sizeof(*T)) == cudaSuccess;
     delete T;
-    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, 16 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(ac3e::ac3_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(ac3e::EncShared) + sizeof(ac3e::EncTables) + 32)) == cudaSuccess;
     if (!ok) { ac3_batch_destroy(ctx); return nullptr; }
@@ -172,6 +175,12 @@ void ac3_batch_destroy(ac3_batch_t* ctx)
         if (b->p) cudaFree(b->p);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->s_in) {
+        cudaStreamDestroy(ctx->s_in);
+        cudaStreamDestroy(ctx->s_run);
+        cudaStreamDestroy(ctx->s_out);
+        for (int i = 0; i < 16; i++) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_run[i]); }
+    }
     delete ctx;
 }
 
@@ -234,6 +243,7 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
         }
     P.work_counter = ctx->d_counter;
     const bool dev = (mem_flags & AC3_BATCH_DEVICE_PTRS) != 0;
+    bool pipelined = false;
     if (dev) {
         P.pcm = pcm; P.out = out; P.status = status; P.carry = (EncCarry*)carry;
         if (debug) {
@@ -243,13 +253,15 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
     } else {
         if (ac3_ensure(ctx, ctx->b_pcm, pcm_bytes) || ac3_ensure(ctx, ctx->b_out, out_bytes) ||
             ac3_ensure(ctx, ctx->b_status, total * 4)) return -1;
-        AC3_CUDA(cudaMemcpyAsync(ctx->b_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+        pipelined = !st && !debug && nstreams >= 1024;
+        if (!pipelined) AC3_CUDA(cudaMemcpyAsync(ctx->b_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
         P.pcm = (const int16_t*)ctx->b_pcm.p;
         P.out = (uint8_t*)ctx->b_out.p;
         P.status = (int32_t*)ctx->b_status.p;
         if (carry) {
             if (ac3_ensure(ctx, ctx->b_carry, sizeof(EncCarry) * (size_t)nstreams)) return -1;
-            AC3_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, st));
+            if (!pipelined)
+                AC3_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, st));
             P.carry = (EncCarry*)ctx->b_carry.p;
         }
         if (debug && debug->coef) {
@@ -275,6 +287,54 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
     }
     int grid = ctx->num_sms * occ;
     if (grid > nstreams) grid = nstreams;
+    if (pipelined) {
+        // Large host-pointer batches: chunks of streams flow through PCM H2D | kernel | frames D2H on three
+        // CUDA streams (a chunk still fills every SM several times over).
+        if (!ctx->s_in) {
+            AC3_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+            AC3_CUDA(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking));
+            AC3_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+            for (int i = 0; i < 16; i++) {
+                AC3_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+                AC3_CUDA(cudaEventCreateWithFlags(&ctx->ev_run[i], cudaEventDisableTiming));
+            }
+        }
+        int nchunks = nstreams / 512;
+        if (nchunks > 16) nchunks = 16;
+        AC3_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(int), ctx->s_run));
+        if (carry) AC3_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, ctx->s_run));
+        const size_t pcm_per = (size_t)nframes * 1536 * channels * 2, out_per = (size_t)nframes * c.frame_words * 2;
+        for (int k = 0; k < nchunks; k++) {
+            const int s0 = (int)((long long)k * nstreams / nchunks), s1 = (int)((long long)(k + 1) * nstreams / nchunks);
+            AC3_CUDA(cudaMemcpyAsync((uint8_t*)ctx->b_pcm.p + s0 * pcm_per, (const uint8_t*)pcm + s0 * pcm_per,
+                                     (s1 - s0) * pcm_per, cudaMemcpyHostToDevice, ctx->s_in));
+            AC3_CUDA(cudaEventRecord(ctx->ev_in[k], ctx->s_in));
+            AC3_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[k], 0));
+            EncParams Pk = P;
+            Pk.pcm = P.pcm + (size_t)s0 * nframes * 1536 * channels;
+            Pk.out = P.out + s0 * out_per;
+            Pk.status = P.status + (size_t)s0 * nframes;
+            Pk.carry = P.carry ? P.carry + s0 : nullptr;
+            Pk.nstreams = s1 - s0;
+            Pk.work_counter = ctx->d_counter + k;
+            int gk = ctx->num_sms * occ;
+            if (gk > s1 - s0) gk = s1 - s0;
+            ac3_encode_kernel<<<gk, kThreads, smem, ctx->s_run>>>(Pk);
+            AC3_CUDA(cudaGetLastError());
+            ctx->launches++;
+            AC3_CUDA(cudaEventRecord(ctx->ev_run[k], ctx->s_run));
+            AC3_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_run[k], 0));
+            AC3_CUDA(cudaMemcpyAsync(out + s0 * out_per, P.out + s0 * out_per, (s1 - s0) * out_per, cudaMemcpyDeviceToHost, ctx->s_out));
+            if (status)
+                AC3_CUDA(cudaMemcpyAsync(status + (size_t)s0 * nframes, P.status + (size_t)s0 * nframes,
+                                         (size_t)(s1 - s0) * nframes * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        if (carry) AC3_CUDA(cudaMemcpyAsync(carry, P.carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, ctx->s_run));
+        AC3_CUDA(cudaStreamSynchronize(ctx->s_run));
+        AC3_CUDA(cudaStreamSynchronize(ctx->s_out));
+        AC3_CUDA(cudaStreamSynchronize(ctx->s_in));
+        return 0;
+    }
     AC3_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
         if (ctx->ev_pool.size() < 8192) {

@@ -187,3 +187,19 @@ def test_mixed_corpus_round_trip_sharded(encoder, engine, decoder, oracle):
                 a = res["pcm"][sfirst[j]:sfirst[j + 1]]
                 b = whole["pcm"][first[sidx]:first[sidx + 1]]
                 assert (a.view(np.uint32) == b.view(np.uint32)).all(), (world, r, sidx)
+
+
+def test_pipelined_host_batch_equals_single_launch(encoder):
+    """Host-pointer calls of 1024 streams and more are cut into chunks that flow through H2D | kernel | D2H;
+    the frames, statuses and carry records must not depend on that."""
+    rng = np.random.RandomState(4)
+    base = np.stack([synth_pcm(11, s, 2, 1536 * 3, 48000, noise=0.03) for s in range(8)])
+    pick = rng.randint(0, 8, 1300)
+    pcm = np.ascontiguousarray(base[pick])
+    big = encoder.encode_host(pcm, 48000, 192000, carry=[None] * 1300)
+    small = encoder.encode_host(base, 48000, 192000, carry=[None] * 8)
+    assert (big["status"] == 0).all()
+    assert (big["frames"] == small["frames"][pick]).all()
+    for k in (0, 511, 650, 1299):
+        a, b = big["carry"][k], small["carry"][pick[k]]
+        assert bytes(a) == bytes(b)
