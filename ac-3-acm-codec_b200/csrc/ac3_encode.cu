@@ -96,6 +96,7 @@ struct EncShared {
         struct { uint32_t frame[kFrameWords]; uint32_t codes[kCodes]; uint16_t gpos[kCodes]; } e4;
     } u;
     int      cnt[6][6][4];               // per exponent set: 3-, 5-, 11-level mantissas, bits of plain fields
+    int      pcnt[2][6][6][4];           // the same for the search probes, two buffers used in turn
     uint8_t  strategy[6][6];
     uint8_t  head[6][6];                 // block holding the exponent set a (block, channel) uses
     int8_t   exp_shift[6][6];
@@ -103,7 +104,7 @@ struct EncShared {
     uint32_t mant_pos[6];                // bit position of a block's first mantissa
     int      exp_bits[6];                // per channel: bits of its exponent sections (ac3enc.cpp:760)
     int      frame_bits;                 // everything but mantissas
-    int      probe_cs, probe_fs, phase, cs, fs, done, failed;
+    int      cs, fs, failed;             // result of the search (and the warm start of the next frame's)
     uint32_t crc[2];
 };
 
@@ -471,7 +472,7 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
 
 // E3b: baps of one exponent set for an snr offset (:393-420) + class counts.  One warp.
 __device__ void e3_probe(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane,
-                         int snroffset, bool store)
+                         int snroffset, bool store, int (*cnt)[6][4])
 {
     const bool is_lfe = P.lfe && ch == 5;
     const int end = is_lfe ? 7 : 223;
@@ -498,21 +499,21 @@ __device__ void e3_probe(EncShared& S, const EncTables& T, const EncParams& P, i
 #pragma unroll
     for (int o = 16; o; o >>= 1) fixed += __shfl_xor_sync(0xffffffffu, fixed, o);
     if (lane == 0) {
-        S.cnt[blk][ch][0] = n1;
-        S.cnt[blk][ch][1] = n2;
-        S.cnt[blk][ch][2] = n4;
-        S.cnt[blk][ch][3] = fixed;
+        cnt[blk][ch][0] = n1;
+        cnt[blk][ch][1] = n2;
+        cnt[blk][ch][2] = n4;
+        cnt[blk][ch][3] = fixed;
     }
 }
 
-// bits left in the frame for the counts of the last probe (bit_alloc, :813-845); warp 0, lane = block
-__device__ int bits_left(const EncShared& S, const EncParams& P, int lane)
+// bits left in the frame for the counts of the last probe (bit_alloc, :813-845); one warp, lane = block
+__device__ int bits_left(const EncShared& S, const EncParams& P, int lane, const int (*cnt)[6][4])
 {
     int used = 0;
     if (lane < 6) {
         int n1 = 0, n2 = 0, n4 = 0;
         for (int ch = 0; ch < P.nch_all; ch++) {
-            const int* q = S.cnt[S.head[lane][ch]][ch];
+            const int* q = cnt[S.head[lane][ch]][ch];
             n1 += q[0]; n2 += q[1]; n4 += q[2]; used += q[3];
         }
         used += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
@@ -520,37 +521,43 @@ __device__ int bits_left(const EncShared& S, const EncParams& P, int lane)
     used += __shfl_xor_sync(0xffffffffu, used, 1);
     used += __shfl_xor_sync(0xffffffffu, used, 2);
     used += __shfl_xor_sync(0xffffffffu, used, 4);
-    return 16 * P.frame_words - S.frame_bits - used;
+    // lanes 0..7 hold the sum: every lane returns lane 0's value (all of them step the search)
+    return __shfl_sync(0xffffffffu, 16 * P.frame_words - S.frame_bits - used, 0);
 }
 
 // The search of compute_bit_allocation (:921-967) as a state machine fed with one probe result
 // at a time.  phase 0: csnr down by 4 until it fits; 1: csnr up by 4; 2: csnr up by 1;
-// 3: fsnr up by 4; 4: fsnr up by 1; 5: done.
-__device__ void search_step(EncShared& S, int left)
+// 3: fsnr up by 4; 4: fsnr up by 1; 5: done.  Every warp runs its own copy on the same inputs, so a
+// probe costs one CTA barrier, not two.
+struct Search {
+    int phase, cs, fs, probe_cs, probe_fs, done, failed;
+};
+
+__device__ __forceinline__ void search_step(Search& q, int left)
 {
-    int ph = S.phase;
+    int ph = q.phase;
     if (ph == 0) {
-        if (left >= 0) { S.cs = S.probe_cs; ph = 1; }
+        if (left >= 0) { q.cs = q.probe_cs; ph = 1; }
         else {
-            S.probe_cs -= 4;
-            if (S.probe_cs < 0) { S.failed = 1; S.cs = 0; S.fs = 0; S.phase = 5; S.done = 1; return; }
+            q.probe_cs -= 4;
+            if (q.probe_cs < 0) { q.failed = 1; q.cs = 0; q.fs = 0; q.phase = 5; q.done = 1; }
             return;
         }
     } else if (left >= 0) {
-        S.cs = S.probe_cs;
-        S.fs = S.probe_fs;
+        q.cs = q.probe_cs;
+        q.fs = q.probe_fs;
     } else {
         ph++;
     }
     // next candidate of the current phase, falling through exhausted phases
     for (;;) {
-        if (ph == 1) { if (S.cs + 4 <= 63) { S.probe_cs = S.cs + 4; S.probe_fs = 0; break; } ph = 2; }
-        else if (ph == 2) { if (S.cs + 1 <= 63) { S.probe_cs = S.cs + 1; S.probe_fs = 0; break; } ph = 3; }
-        else if (ph == 3) { if (S.fs + 4 <= 15) { S.probe_cs = S.cs; S.probe_fs = S.fs + 4; break; } ph = 4; }
-        else if (ph == 4) { if (S.fs + 1 <= 15) { S.probe_cs = S.cs; S.probe_fs = S.fs + 1; break; } ph = 5; }
-        else { S.done = 1; break; }
+        if (ph == 1) { if (q.cs + 4 <= 63) { q.probe_cs = q.cs + 4; q.probe_fs = 0; break; } ph = 2; }
+        else if (ph == 2) { if (q.cs + 1 <= 63) { q.probe_cs = q.cs + 1; q.probe_fs = 0; break; } ph = 3; }
+        else if (ph == 3) { if (q.fs + 4 <= 15) { q.probe_cs = q.cs; q.probe_fs = q.fs + 4; break; } ph = 4; }
+        else if (ph == 4) { if (q.fs + 1 <= 15) { q.probe_cs = q.cs; q.probe_fs = q.fs + 1; break; } ph = 5; }
+        else { q.done = 1; break; }
     }
-    S.phase = ph;
+    q.phase = ph;
 }
 
 // ---------------------------------------------------------------------------
@@ -639,12 +646,6 @@ ac3_encode_kernel(const EncParams P)
                 }
                 fb += 1 + 2 * 4 + 3 + 6 + P.nch_all * (4 + 3) + 2 + 16;
                 S.frame_bits = fb;
-                S.probe_cs = S.cs;                                       // warm start (:921)
-                S.probe_fs = 0;
-                S.fs = 0;
-                S.phase = 0;
-                S.done = 0;
-                S.failed = 0;
             }
             // ================= E3 =================
             if (active) {
@@ -653,30 +654,31 @@ ac3_encode_kernel(const EncParams P)
                     if (S.head[blk][warp] == blk) e3_mask(S, T, P, blk, warp, lane, psd);
             }
             __syncthreads();
-            for (;;) {
-                const int snro = (((S.probe_cs - 15) << 4) + S.probe_fs) << 2;
+            Search q;
+            q.cs = S.cs;
+            q.probe_cs = q.cs;                                           // warm start (:921)
+            q.probe_fs = q.fs = q.phase = q.done = q.failed = 0;
+            for (int par = 0;; par ^= 1) {
+                const int snro = (((q.probe_cs - 15) << 4) + q.probe_fs) << 2;
                 if (active)
                     for (int blk = 0; blk < 6; blk++)
-                        if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, snro, false);
+                        if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, snro, false, S.pcnt[par]);
                 __syncthreads();
-                if (warp == 0) {
-                    const int left = bits_left(S, P, lane);
-                    if (lane == 0) search_step(S, left);
-                }
-                __syncthreads();
-                if (S.done) break;
+                search_step(q, bits_left(S, P, lane, S.pcnt[par]));
+                if (q.done) break;
             }
             {
                 // the accepted allocation (or, after a failed search, all-zero baps)
-                const int snro = (((S.cs - 15) << 4) + S.fs) << 2;
+                const int snro = (((q.cs - 15) << 4) + q.fs) << 2;
+                if (tid == 0) { S.cs = q.cs; S.fs = q.fs; S.failed = q.failed; }
                 if (active)
                     for (int blk = 0; blk < 6; blk++)
                         if (S.head[blk][warp] == blk) {
-                            if (S.failed) {
+                            if (q.failed) {
                                 for (int i = lane; i < 256; i += 32) S.expo[blk][warp][i] = 0;
                                 if (lane < 4) S.cnt[blk][warp][lane] = 0;
                             } else {
-                                e3_probe(S, T, P, blk, warp, lane, snro, true);
+                                e3_probe(S, T, P, blk, warp, lane, snro, true, S.cnt);
                             }
                         }
             }
