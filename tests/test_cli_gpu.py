@@ -55,31 +55,62 @@ def same_f32(a, b, what):
     assert np.sqrt((d * d).mean()) <= 1e-5 * np.sqrt((fa * fa).mean()), what
 
 
+def ref_file(tmp_path, args, path):
+    """The reference CLI with its stdout in a FILE: libao then rewinds and writes the final sizes."""
+    out = tmp_path / ("ref_%d.out" % abs(hash((tuple(args), path))))
+    with open(out, "wb") as f:
+        r = subprocess.run([REF] + args + [path], stdout=f, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr[-300:]
+    return open(out, "rb").read()
+
+
+def cli_batch(tmp_path, drv, paths, extra=()):
+    """ONE run of a52dec_b200 for all paths (-O: every input is a stream of the same batch)."""
+    out = tmp_path / ("cli_%s_%d" % (drv, abs(hash(tuple(paths) + tuple(extra)))))
+    out.mkdir()
+    run(CLI, ["-o", drv, "-O", str(out)] + list(extra) + list(paths))
+    ext = {"wav": "wav", "wavdolby": "wav", "wav6": "wav", "aif": "aif", "aifdolby": "aif", "peak": "txt",
+           "peakdolby": "txt"}.get(drv, "raw")
+    return [open(out / (os.path.basename(p) + "." + ext), "rb").read() for p in paths]
+
+
+def same_aif(a, b, what):
+    assert a[:54] == b[:54], (what, a[:54], b[:54])
+    sa, sb = np.frombuffer(a[54:], ">i2").astype(int), np.frombuffer(b[54:], ">i2").astype(int)
+    assert len(sa) == len(sb) > 0 and np.abs(sa - sb).max() <= 1, what
+
+
 @need
 def test_every_driver_on_natural_streams(tmp_path, c2, golden):
     cases = [("c2", c2["frames"][1, :24].reshape(-1)), ("stereo", np.tile(golden["enc20_stereo_bias.es"], 3)),
              ("441", golden["enc50_dolby_441.es"])]
-    for name, es in cases:
-        p = write(tmp_path, name + ".ac3", es)
-        full = name == "c2"                      # every driver on the 5.1 stream, the main ones on the others
-        for drv in ("wav", "wavdolby", "wav6") if full else ("wav", "wav6"):
-            same_s16(wav_split(run(REF, ["-o", drv], p)[0]), wav_split(run(CLI, ["-o", drv], p)[0]), (name, drv), True)
-        for drv in ("aif", "aifdolby") if full else ("aif",):
-            a, b = run(REF, ["-o", drv], p)[0], run(CLI, ["-o", drv], p)[0]
-            assert a[:54] == b[:54], (name, drv)
-            sa, sb = np.frombuffer(a[54:], ">i2").astype(int), np.frombuffer(b[54:], ">i2").astype(int)
-            assert len(sa) == len(sb) and np.abs(sa - sb).max() <= 1
-        same_f32(run(REF, ["-o", "float"], p)[0], run(CLI, ["-o", "float"], p)[0], (name, "float"))
-        for drv in ("peak", "peakdolby") if full else ():
-            a, b = run(REF, ["-o", drv], p)[0].decode(), run(CLI, ["-o", drv], p)[0].decode()
+    paths = [write(tmp_path, name + ".ac3", es) for name, es in cases]
+    # every driver, the three files as one batch per driver; complete files (final headers) are compared
+    for drv in ("wav", "wavdolby", "wav6"):
+        for p, got in zip(paths, cli_batch(tmp_path, drv, paths)):
+            same_s16(wav_split(ref_file(tmp_path, ["-o", drv], p)), wav_split(got), (p, drv), True)
+    for drv in ("aif", "aifdolby"):
+        for p, got in zip(paths, cli_batch(tmp_path, drv, paths)):
+            same_aif(ref_file(tmp_path, ["-o", drv], p), got, (p, drv))
+    for p, got in zip(paths, cli_batch(tmp_path, "float", paths)):
+        same_f32(ref_file(tmp_path, ["-o", "float"], p), got, (p, "float"))
+    for drv in ("peak", "peakdolby"):
+        for p, got in zip(paths, cli_batch(tmp_path, drv, paths)):
+            a, b = ref_file(tmp_path, ["-o", drv], p).decode(), got.decode()
             va, vb = float(a.split()[3]), float(b.split()[3])
             assert a.startswith("peak level = ") and abs(va - vb) <= 1e-4 + 1e-5 * va, (a, b)
-        for drv in ("null", "null4", "null6") if full else ():
-            assert run(CLI, ["-o", drv], p)[0] == run(REF, ["-o", drv], p)[0] == b""
+    for drv in ("null", "null4", "null6"):
+        assert cli_batch(tmp_path, drv, paths) == [b"", b"", b""]
+        assert ref_file(tmp_path, ["-o", drv], paths[0]) == b""
+    # one input without -O: stdout; a pipe cannot be rewound, the open-ended sizes stay (audio_out_wav.c:44-58)
+    p = paths[1]
+    ra, rb = run(REF, ["-o", "wav"], p)[0], run(CLI, ["-o", "wav"], p)[0]
+    same_s16(wav_split(ra), wav_split(rb), "pipe", True)
+    assert struct.unpack("<I", rb[4:8])[0] == 0xfffffffc
     # default driver is the first of the list (wav), stdin works as input
     es = open(p, "rb").read()
     r = subprocess.run([CLI], input=es, capture_output=True, timeout=300, check=True).stdout
-    same_s16(wav_split(run(REF, [], p)[0]), wav_split(r), "stdin", True)
+    same_s16(wav_split(ra), wav_split(r), "stdin", True)
 
 
 @need
@@ -93,29 +124,32 @@ def test_options_r_a_g(tmp_path, golden):
         assert run(CLI, bad, p, ok=(1,))[2] == run(REF, bad, p, ok=(1,))[2] == 1
 
 
+MODES = [(0, 0), (1, 0), (1, 1), (2, 1), (3, 0), (3, 1), (4, 0), (4, 1), (5, 0), (5, 1), (6, 0), (6, 1), (7, 0), (7, 1)]
+
+
 @need
-@pytest.mark.parametrize("acmod,lfe", [(0, 0), (1, 0), (1, 1), (2, 1), (3, 0), (3, 1), (4, 0), (4, 1), (5, 0), (5, 1),
-                                       (6, 0), (6, 1), (7, 0), (7, 1)])
-def test_wav6_every_coded_mode(tmp_path, oracle, acmod, lfe):
+def test_wav6_every_coded_mode(tmp_path, oracle):
     """wav6 leaves the request to the stream: every coded mode comes out in WAV channel order, extensible
-    header with the right speaker mask - including libao's 2/1+LFE fall-through (convert2s16.c:270-285)."""
-    es, fb = make_stream(4100 + acmod * 2 + lfe, acmod, lfe, 3, oracle.bit_allocate, frmsizecod=30)
-    p = write(tmp_path, "m.ac3", es)
-    a, b = wav_split(run(REF, ["-o", "wav6"], p)[0]), wav_split(run(CLI, ["-o", "wav6"], p)[0])
-    same_s16(a, b, (acmod, lfe))
-    if (acmod, lfe) == (4, 1):
-        assert (b[1].reshape(-1, 1024)[:, 4::5] == -32768).all()
-    # the other drivers on the same stream, two per mode (mono sources stay mono: one-channel header; aif and
-    # float take two planes whatever the grant)
-    for drv in (("wav", "aif"), ("wavdolby", "float"))[(acmod + lfe) & 1]:
-        ra, rb = run(REF, ["-o", drv], p)[0], run(CLI, ["-o", drv], p)[0]
-        if drv == "float":
-            same_f32(ra, rb, (acmod, lfe, drv))
-        elif drv == "aif":
-            sa, sb = np.frombuffer(ra[54:], ">i2").astype(int), np.frombuffer(rb[54:], ">i2").astype(int)
-            assert ra[:54] == rb[:54] and len(sa) == len(sb) and np.abs(sa - sb).max() <= 1
-        else:
-            same_s16(wav_split(ra), wav_split(rb), (acmod, lfe, drv))
+    header with the right speaker mask - including libao's 2/1+LFE fall-through (convert2s16.c:270-285).
+    All fourteen modes are streams of ONE batch per driver."""
+    paths = []
+    for acmod, lfe in MODES:
+        es, fb = make_stream(4100 + acmod * 2 + lfe, acmod, lfe, 3, oracle.bit_allocate, frmsizecod=30)
+        paths.append(write(tmp_path, "m%d%d.ac3" % (acmod, lfe), es))
+    for (acmod, lfe), p, got in zip(MODES, paths, cli_batch(tmp_path, "wav6", paths)):
+        b = wav_split(got)
+        same_s16(wav_split(ref_file(tmp_path, ["-o", "wav6"], p)), b, (acmod, lfe))
+        if (acmod, lfe) == (4, 1):
+            assert (b[1].reshape(-1, 1024)[:, 4::5] == -32768).all()
+    # the stereo drivers on the same streams (mono sources stay mono: one-channel header; aif and float take
+    # two planes whatever the grant)
+    for drv in ("wav", "wavdolby"):
+        for m, p, got in zip(MODES, paths, cli_batch(tmp_path, drv, paths)):
+            same_s16(wav_split(ref_file(tmp_path, ["-o", drv], p)), wav_split(got), (m, drv))
+    for m, p, got in zip(MODES, paths, cli_batch(tmp_path, "aif", paths)):
+        same_aif(ref_file(tmp_path, ["-o", "aif"], p), got, (m, "aif"))
+    for m, p, got in zip(MODES, paths, cli_batch(tmp_path, "float", paths, extra=["-C", "2"])):
+        same_f32(ref_file(tmp_path, ["-o", "float"], p), got, (m, "float"))
 
 
 @need
