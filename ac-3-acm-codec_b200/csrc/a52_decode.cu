@@ -1569,8 +1569,9 @@ a52_decode_kernel(const DecodeParams P)
                 if (pend) {
                     const int nmain = c->nout, lfe_on = c->out_lfe, nfch = c->nfchans;
                     // thread q = gt owns positions p = 2q, 2q+1 (and their mirrors 254-p, 255-p) of every plane
-                    if (p_uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt == 1) {
-                        // the common request: two mixed planes, tails already downmixed, interleaved float out
+                    if (p_uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt != 0) {
+                        // the common request: two mixed planes, tails already downmixed, interleaved float or
+                        // int16 out (two channels: libao's WAV order is liba52's)
                         const float bias = P.bias;
                         const float2* plane2 = reinterpret_cast<const float2*>(G.plane);
                         const float2* win2 = reinterpret_cast<const float2*>(T.window);
@@ -1588,9 +1589,19 @@ a52_decode_kernel(const DecodeParams P)
                             y[pl][2] = D.y * wl.y + U.y * wh.x;        // sample 254 - p
                             delay2[pl * 64 + q] = V;
                         }
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)p_blk * 512);
-                        dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
-                        dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+                        if (P.out_fmt == 1) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)p_blk * 512);
+                            dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
+                            dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+                        } else {
+                            // int16 (convert2s16.c:33-41): L R L R of samples p, p + 1 in one 8-byte store
+                            auto two = [](float l, float r) {
+                                return (uint32_t)(uint16_t)s16_of(l, true) | ((uint32_t)(uint16_t)s16_of(r, true) << 16);
+                            };
+                            uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<int16_t*>(out_frame) + (size_t)p_blk * 512);
+                            dst[q] = make_uint2(two(y[0][0], y[1][0]), two(y[0][1], y[1][1]));
+                            dst[127 - q] = make_uint2(two(y[0][2], y[1][2]), two(y[0][3], y[1][3]));
+                        }
                     } else {
                         ola_store_generic(T, P, G, c, out_frame, p_blk, gt, nfch, nmain, p_uniform, lfe_on);
                     }

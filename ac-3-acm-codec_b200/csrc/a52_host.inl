@@ -348,8 +348,9 @@ struct a52_batch_s {
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
     uint16_t* d_dither = nullptr;
-    int host_chunk_streams = 128;  // streams per pipelined chunk of a host-pointer call
-    int host_concurrency = 4;      // chunk kernels in flight at once (a chunk alone is latency-bound: its CTAs
+    int host_chunk_streams = 128;  // streams per pipelined chunk of a host-pointer call (A52_B200_HOST_CHUNK_STREAMS)
+    int host_chunk_env = 0;
+    int host_concurrency = 8;      // chunk kernels in flight at once (a chunk alone is latency-bound: its CTAs
                                    // are small, several launches share the SMs)
     cudaStream_t s_runs[8] = {};
     int* d_counter = nullptr;      // [0..31] work counters (one per pipelined chunk), [63] max frame length
@@ -408,7 +409,7 @@ a52_batch_t* a52_batch_create(int device)
     const char* sf = getenv("A52_B200_SLICE_FRAMES");
     if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
     const char* hc = getenv("A52_B200_HOST_CHUNK_STREAMS");
-    if (hc && atoi(hc) > 0) ctx->host_chunk_streams = atoi(hc);
+    if (hc && atoi(hc) > 0) { ctx->host_chunk_streams = atoi(hc); ctx->host_chunk_env = 1; }
     const char* hq = getenv("A52_B200_HOST_CONCURRENCY");
     if (hq && atoi(hq) > 0 && atoi(hq) <= 8) ctx->host_concurrency = atoi(hq);
 
@@ -757,7 +758,10 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
     A52_CUDA(cudaStreamSynchronize(s_run));
 
     // chunk plan: contiguous stream ranges; each chunk's bitstream is the byte span of its frames
-    int nchunks = nstreams / ctx->host_chunk_streams;
+    // chunk size: small chunks start the PCM copy early (what counts when the copy is the bottleneck: float
+    // output), larger ones keep more streams in flight (what counts when the kernels are: int16 output)
+    const int chunk_streams = ctx->host_chunk_env ? ctx->host_chunk_streams : (stride >= 8192 ? 128 : 256);
+    int nchunks = nstreams / chunk_streams;
     if (nchunks > 32) nchunks = 32;
     if (nchunks < 1) nchunks = 1;
     std::vector<size_t> cb0(nchunks), cb1(nchunks);

@@ -208,6 +208,9 @@ def test_s16_and_interleaved_output(decoder, engine, oracle, c2):
     got = out["pcm"].reshape(8, 1536, 2)
     assert np.abs(got.astype(int) - want_s16.astype(int)).max() <= 1
     assert (got == want_s16).mean() > 0.999
+    # two channels: libao's WAV order is liba52's order (convert2s16.c:213-217)
+    off, out = gpu_decode(decoder, engine, es, oracle, flags, fmt=engine.PCM_S16_WAV)
+    assert (out["pcm"].reshape(8, 1536, 2) == got).all()
     nf, want = oracle.decode_stream(es, flags, 1.0, 0.0)
     off, out = gpu_decode(decoder, engine, es, oracle, flags, fmt=engine.PCM_F32_INTERLEAVED)
     got = out["pcm"].reshape(8, 6, 256, 2).transpose(0, 1, 3, 2).reshape(48, 2, 256)
