@@ -519,3 +519,30 @@ def test_random_sweep_heterogeneous_batches(decoder, engine, oracle, seed):
             else:
                 d = (got.astype(np.float64) - want).reshape(-1)
                 assert np.sqrt((d * d).mean()) <= TOL_PCM * np.sqrt(((want - bias) ** 2).mean()) + (1e-7 if bias == 0 else 2.0 ** -15 * (bias > 1) + 1e-6), (req, k)
+
+
+def test_host_pipeline_chunks(decoder, engine, oracle, c2):
+    """A host-pointer call of several hundred streams is cut into chunks of streams whose copies and kernels
+    overlap on several CUDA streams.  None of that may show: every copy of a base stream must come out
+    bit-identical to the base stream decoded on its own, for equal and for ragged stream lengths, with and
+    without caller carry records."""
+    base = c2["frames"]                                              # [4, 64, 1792]
+    flags = A52_STEREO | A52_ADJUST_LEVEL
+    solo = [decoder.decode_host(base[k].reshape(-1), np.arange(64, dtype=np.uint64) * 1792,
+                                np.array([0, 64], np.uint32), flags, out_fmt=engine.PCM_F32_INTERLEAVED)["pcm"]
+            for k in range(4)]
+    rng = np.random.RandomState(8)
+    for ragged in (False, True):
+        ns = 600
+        pick = rng.randint(0, 4, ns)
+        lens = rng.randint(33, 65, ns) if ragged else np.full(ns, 64)
+        es = np.concatenate([base[pick[s], :lens[s]].reshape(-1) for s in range(ns)])
+        first = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+        off = np.arange(int(first[-1]), dtype=np.uint64) * 1792
+        for with_carry in (False, True):
+            carry = [engine.CarryStruct() for _ in range(ns)] if with_carry else None
+            out = decoder.decode_host(es, off, first, flags, out_fmt=engine.PCM_F32_INTERLEAVED, carry=carry)
+            assert (out["status"] == 0).all()
+            for s in range(0, ns, 7):
+                got = out["pcm"][first[s]:first[s + 1]]
+                assert (got.view(np.uint32) == solo[pick[s]][:lens[s]].view(np.uint32)).all(), (ragged, with_carry, s)
