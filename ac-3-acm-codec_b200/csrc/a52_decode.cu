@@ -73,6 +73,9 @@ struct __align__(16) GroupCtl {
     int      frame_ok;         // frame header valid
     int      err;              // error raised inside the current block
     int      tr_ticket;        // transform jobs of the pending block handed out so far
+    // what the last full locate pass left for blocks that repeat its baps, ranges and flags
+    uint32_t loc_ta, loc_tb, loc_tz, loc_mant;
+    uint8_t  loc_valid, loc_dithflag, loc_chincpl, repeat;
     uint32_t base_bit;         // bit offset of the frame inside the staged buffer
     uint32_t limit_bit;        // end of frame (bits) inside the staged buffer
     uint32_t bitpos;           // cursor (bits), advanced block by block
@@ -306,6 +309,7 @@ __device__ int parse_frame_header(GroupCtl* c, const uint32_t* w, uint32_t base_
     c->dynrng = c->level;
     c->gains_dirty = 1;
     c->segs_dirty = 1;
+    c->loc_valid = 0;
     // mix matrix as float weights (so that the mixers are plain multiply-adds); fixed for the frame
     {
         const MixEntry mx = c_mix[acmod * 11 + me.output];
@@ -590,6 +594,12 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         compute_gains(c);
         c->gains_dirty = 0;
     }
+    // may the locate stage reuse what its last full pass left?  (same baps and exponents: nothing
+    // reallocated; same coded ranges; same dither and coupling flags)
+    c->repeat = c->loc_valid && !c->segs_dirty && do_alloc == 0 && c->dithflag == c->loc_dithflag
+                && c->chincpl == c->loc_chincpl;
+    c->loc_dithflag = c->dithflag;
+    c->loc_chincpl = c->chincpl;
     if (c->segs_dirty) {
     c->segs_dirty = 0;
 
@@ -1247,11 +1257,12 @@ static_assert(sizeof(GroupCtl) <= 1200, "GroupCtl grew: check the shared-memory 
 struct PairPtrs : WarpPtrs {
     float*    delay;   // [nplanes][128] overlap-add tails
     uint32_t* xch;     // [2][8] scan totals of the two warps
+    uint4*    loc;     // [64] per-thread record of the last full locate pass (see stage L)
 };
 
 __host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
 {
-    return warp_smem_bytes(fbuf_bytes, nplanes) + nplanes * 128 * 4 + 64;
+    return warp_smem_bytes(fbuf_bytes, nplanes) + nplanes * 128 * 4 + 64 + 64 * 16;
 }
 
 __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes)
@@ -1260,7 +1271,8 @@ __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes
     static_cast<WarpPtrs&>(g) = carve(base, fbuf_bytes, nplanes);
     uint8_t* p = reinterpret_cast<uint8_t*>(g.mbar) + 16;
     g.delay = reinterpret_cast<float*>(p);   p += nplanes * 128 * 4;
-    g.xch = reinterpret_cast<uint32_t*>(p);
+    g.xch = reinterpret_cast<uint32_t*>(p);  p += 64;
+    g.loc = reinterpret_cast<uint4*>(p);
     return g;
 }
 
@@ -1655,6 +1667,23 @@ a52_decode_kernel(const DecodeParams P)
                 const int nseg = c->nseg;
                 uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
                 bool mute = false;
+                // What the lane plan, pass 1 and the scans produce is a function of the baps, the coded ranges
+                // and the dither / coupling flags alone.  A block that changes none of them (every exponent
+                // set and allocation reused: the rule, not the exception) takes it from the per-thread record
+                // the last full pass left (G.loc) and goes straight to pass 2.
+                const bool rep = c->repeat != 0;
+                uint32_t v_ta, v_tb, v_tz, v_mant, v_base_lo, v_base_hi, v_base_z, v_phase0, v_posrel;
+                if (rep) {
+                    const uint4 q = G.loc[gt];
+                    run_idx = q.x & 0x7ff; run_n = (q.x >> 11) & 31; zmode = (q.x >> 16) & 3;
+                    mute = (q.x >> 18) & 1; v_base_z = q.x >> 19;
+                    run_slot = q.y & 0x7ff;
+                    v_phase0 = ((q.y >> 11) & 3) | (((q.y >> 13) & 3) << 8) | (((q.y >> 15) & 1) << 16);
+                    v_posrel = q.y >> 16;
+                    v_base_lo = q.z; v_base_hi = q.w;
+                    v_ta = c->loc_ta; v_tb = c->loc_tb; v_tz = c->loc_tz; v_mant = c->loc_mant;
+                    sync();                                   // the planes are zero before descriptors land
+                } else {
                 {
                     int sgi = -1;
                     for (int k = 0; k < nseg; k++)
@@ -1672,11 +1701,10 @@ a52_decode_kernel(const DecodeParams P)
                 // pass 1: class counts of my run.  The bap bytes are fetched a 32-bit word at a time (runs
                 // start at any byte: each word is funnelled together with its predecessor); one 32-bit LUT
                 // word per bap carries 5-bit counters (3-, 5-, 11-level, zero) and the plain field bits.
-                const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
-                const uint32_t* expw = reinterpret_cast<const uint32_t*>(G.exp);
-                const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
                 uint32_t cnt = 0;
                 {
+                    const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
+                    const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
                     const uint32_t lut32 = tab_base + (uint32_t)offsetof(Tables, cnt_lut32);
                     uint32_t wlo = bapw[wi0];
                     for (uint32_t k = 0, j = 1; k < K; k += 4, j++) {
@@ -1715,15 +1743,34 @@ a52_decode_kernel(const DecodeParams P)
                 uint32_t ibits = warp_incl_scan(mybits, lane);
                 if (lane == 31) G.xch[w * 8 + 3] = ibits;
                 sync();
-                const uint32_t mant_bits = G.xch[3] + G.xch[11];
                 if (w) ibits += G.xch[3];
+                {
+                    const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
+                    v_ta = ta; v_tb = tb; v_tz = tz;
+                    v_mant = G.xch[3] + G.xch[11];
+                    v_base_lo = e1 | ((L2 + e2) << 16);
+                    v_base_hi = (L4 + e4) | ((LP + ep) << 16);
+                    v_base_z = LZ + ez;
+                    v_phase0 = p1 | (p2 << 8) | (p4 << 16);
+                    v_posrel = ibits - mybits;
+                    G.loc[gt] = make_uint4(run_idx | (run_n << 11) | (zmode << 16) | ((uint32_t)mute << 18) | (v_base_z << 19),
+                                           run_slot | (p1 << 11) | (p2 << 13) | (p4 << 15) | (v_posrel << 16),
+                                           v_base_lo, v_base_hi);
+                    if (gt == 0) { c->loc_ta = ta; c->loc_tb = tb; c->loc_tz = tz; c->loc_mant = v_mant; c->loc_valid = 1; }
+                }
+                }   // full pass
+                const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
+                const uint32_t* expw = reinterpret_cast<const uint32_t*>(G.exp);
+                const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
+                const uint32_t ta = v_ta, tb = v_tb, tz = v_tz, mant_bits = v_mant;
+                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
                 const uint32_t bitpos = c->bitpos;
                 const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
                 {
-                    uint32_t pos = min(bitpos + ibits - mybits, limit);
-                    const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
-                    const uint32_t base_z = LZ + ez;
-                    const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);
+                    uint32_t pos = min(bitpos + v_posrel, limit);
+                    const uint32_t base_lo = v_base_lo, base_hi = v_base_hi;
+                    const uint32_t base_z = v_base_z;
+                    const uint32_t phase0 = v_phase0;
                     uint32_t run_a = 0, run_z = 0;
                     const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
                     const uint32_t zrow4 = (zmode == 1) ? 0x10101010u : 0u;
