@@ -14,7 +14,8 @@
 //   alloc   parametric bit allocation          (bit_allocate.c:124-265) lanes = bands / bins
 //   locate  lanes own contiguous runs of the block's mantissas in coded order: count pass,
 //           warp prefix sums of group counters and bit widths, then an emit pass that writes
-//           a descriptor per mantissa and per-class work lists (parse.c:336-433)
+//           a descriptor per mantissa and per-class work lists (parse.c:336-433); a block
+//           that reallocates nothing reuses the count pass and the scans of the last one
 //   unpack  per class, convergent: dither (32 LFSR states kept in the warp, advanced 32 steps
 //           at a time), 3/5/11-level groups one lane per group code, plain fields
 //   couple  coupling fan-out, rematrix         (parse.c:435-556, 837-865)
@@ -23,6 +24,7 @@
 //           post-twiddle                        (imdct.c:258-345)
 //   ola     KBD window + overlap-add + PCM store (imdct.c:276-292); the overlap tails
 //           stay in shared memory from block to block and frame to frame
+// imdct + ola of block b run in the pass of block b + 1, beside its side-info parse.
 //
 // The dither generator position and the overlap tails enter and leave the call
 // (and pass from one slice of a stream to the next) through a52_stream_carry_t.
