@@ -211,3 +211,17 @@ def test_corrupted_frames_same_errors(oracle, ref):
             for ba, bb in zip(fa["blocks"], fb_["blocks"]):
                 assert np.array_equal(ba["pcm"].view(np.uint32), bb["pcm"].view(np.uint32)), it
     assert nerr > 10        # the fuzz does reach the error returns
+
+
+@pytest.mark.parametrize("acmod,flags", [(4, 2), (6, 2), (5, 3), (7, 3 | 32), (7, 2), (6, 4), (3, 10), (0, 1)])
+def test_bias_placement_oracle_vs_reference(oracle, ref, acmod, flags):
+    """Where liba52 adds the bias depends on the transform path: the IMDCT of pass-through channels and the
+    time-domain mixers add it, and with slev == 0 no mixer runs for 2/1, 2/2 -> stereo and 3/1, 3/2 -> 3F
+    (downmix.c:526-573, parse.c:893-918).  The CUDA path is checked against the oracle for this
+    (test_bias_follows_the_reference_path_by_path); here the oracle is pinned to the reference, bit for bit."""
+    from bitstream_writer import make_stream
+    es, fb = make_stream(900 + acmod, acmod, 0, 6, oracle.bit_allocate, frmsizecod=30, features=dict(blksw=0.5))
+    for bias in (384.0, 1.0, 0.0):
+        n1, a = oracle.decode_stream(es, flags, 1.0, bias)
+        n2, b = ref.decode_stream(es, flags, 1.0, bias)
+        assert n1 == n2 == 6 and (a.view(np.uint32) == b.view(np.uint32)).all(), (acmod, flags, bias)
