@@ -90,6 +90,7 @@ struct DecodeParams {
     int             slice_frames;    // pair kernel: frames per work unit
     int             nslices;         // pair kernel: work units per stream (1 = whole streams)
     int             carry_init;      // carry[] holds the caller's initial state (else streams start fresh)
+    uint4*          snap;            // [resident pairs][nplanes * 64]: plane image after a full locate pass
     int*            slice_done;      // [nstreams] slices completed per stream
     // optional dumps
     uint8_t*        dbg_exp;

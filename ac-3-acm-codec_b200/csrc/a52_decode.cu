@@ -76,7 +76,7 @@ struct __align__(16) GroupCtl {
     int      err;              // error raised inside the current block
     int      tr_ticket;        // transform jobs of the pending block handed out so far
     // what the last full locate pass left for blocks that repeat its baps, ranges and flags
-    uint32_t loc_ta, loc_tb, loc_tz, loc_mant;
+    uint32_t loc_ta, loc_tb, loc_tz, loc_mant, loc_bitpos;
     uint8_t  loc_valid, loc_dithflag, loc_chincpl, repeat;
     uint32_t base_bit;         // bit offset of the frame inside the staged buffer
     uint32_t limit_bit;        // end of frame (bits) inside the staged buffer
@@ -1000,7 +1000,7 @@ __device__ __forceinline__ uint32_t peek_nz(const uint32_t* w, uint32_t pos, uin
 // 3-, 5- and 11-level groups: one lane per group code (parse.c:368-421)
 template <int PER, int WBITS, int QSTRIDE, int NT = 32>
 __device__ __forceinline__ void unpack_groups(const WarpPtrs& G, const uint32_t* W, uint32_t base, uint32_t n,
-                                              const int16_t* qtab, int lane)
+                                              const int16_t* qtab, int lane, uint32_t pos_delta, uint32_t limit)
 {
     uint32_t* planeU = reinterpret_cast<uint32_t*>(G.plane);
     const uint32_t ng = (n + PER - 1) / PER;
@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void unpack_groups(const WarpPtrs& G, const uint32_t*
             slot[dg] = G.list[base + k];
             d[dg] = planeU[slot[dg]];
         }
-        const uint32_t code = peek_nz(W, (d[0] >> 10) & 0x7fff, WBITS);
+        const uint32_t code = peek_nz(W, min(((d[0] >> 10) & 0x7fff) + pos_delta, limit), WBITS);
 #pragma unroll
         for (int dg = PER - 1; dg >= 0; dg--) {                // descending: a clamped duplicate is overwritten
             const int q = qtab[dg * QSTRIDE + code];
@@ -1259,12 +1259,11 @@ static_assert(sizeof(GroupCtl) <= 1200, "GroupCtl grew: check the shared-memory 
 struct PairPtrs : WarpPtrs {
     float*    delay;   // [nplanes][128] overlap-add tails
     uint32_t* xch;     // [2][8] scan totals of the two warps
-    uint4*    loc;     // [64] per-thread record of the last full locate pass (see stage L)
 };
 
 __host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
 {
-    return warp_smem_bytes(fbuf_bytes, nplanes) + nplanes * 128 * 4 + 64 + 64 * 16;
+    return warp_smem_bytes(fbuf_bytes, nplanes) + nplanes * 128 * 4 + 64;
 }
 
 __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes)
@@ -1273,8 +1272,7 @@ __device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes
     static_cast<WarpPtrs&>(g) = carve(base, fbuf_bytes, nplanes);
     uint8_t* p = reinterpret_cast<uint8_t*>(g.mbar) + 16;
     g.delay = reinterpret_cast<float*>(p);   p += nplanes * 128 * 4;
-    g.xch = reinterpret_cast<uint32_t*>(p);  p += 64;
-    g.loc = reinterpret_cast<uint4*>(p);
+    g.xch = reinterpret_cast<uint32_t*>(p);
     return g;
 }
 
@@ -1470,6 +1468,8 @@ a52_decode_kernel(const DecodeParams P)
     asm volatile("mov.u32 %0, %1;" : "=r"(plane_sa) : "r"(smem_u32(G.plane)));
     uint32_t phase = 0;
     const int ndelay = P.nplanes;            // tails: planes 0..4 main, 5 LFE
+    // this pair's scratch in global memory: the image of the planes after a full locate pass
+    uint4* const snap = P.snap + (size_t)(blockIdx.x * (blockDim.x >> 6) + pair) * (P.nplanes * 64);
 
     // Work units are SLICES of streams (P.slice_frames frames), handed out slice-major from one ticket
     // counter: all first slices, then all second slices, ...  A slice starts from the carry record its
@@ -1661,180 +1661,169 @@ a52_decode_kernel(const DecodeParams P)
                 }
 
                 // ================= L =================
-                for (int i = gt; i < P.nplanes * 256 / 4; i += NT)
-                    reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
-                const uint32_t K = c->plan_K;
-                const uint32_t cpl_dith = chincpl & c->dithflag;
-                const uint32_t ncpl_dith = __popc(cpl_dith);
-                const int nseg = c->nseg;
-                uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
-                bool mute = false;
-                // What the lane plan, pass 1 and the scans produce is a function of the baps, the coded ranges
-                // and the dither / coupling flags alone.  A block that changes none of them (every exponent
-                // set and allocation reused: the rule, not the exception) takes it from the per-thread record
-                // the last full pass left (G.loc) and goes straight to pass 2.
+                // What the locate passes produce - descriptors in the coefficient slots, the work lists, the
+                // class totals - is a function of the baps, the coded ranges and the dither / coupling flags,
+                // up to one common shift of the bit positions.  A block that changes none of them (every
+                // exponent set and allocation reused: the rule, not the exception) restores the image of the
+                // planes the last full pass left in the pair's scratch (global memory, L2-resident), keeps the
+                // lists as they are and lets the unpack stage add the shift.
                 const bool rep = c->repeat != 0;
-                uint32_t v_ta, v_tb, v_tz, v_mant, v_base_lo, v_base_hi, v_base_z, v_phase0, v_posrel;
-                if (rep) {
-                    const uint4 q = G.loc[gt];
-                    run_idx = q.x & 0x7ff; run_n = (q.x >> 11) & 31; zmode = (q.x >> 16) & 3;
-                    mute = (q.x >> 18) & 1; v_base_z = q.x >> 19;
-                    run_slot = q.y & 0x7ff;
-                    v_phase0 = ((q.y >> 11) & 3) | (((q.y >> 13) & 3) << 8) | (((q.y >> 15) & 1) << 16);
-                    v_posrel = q.y >> 16;
-                    v_base_lo = q.z; v_base_hi = q.w;
-                    v_ta = c->loc_ta; v_tb = c->loc_tb; v_tz = c->loc_tz; v_mant = c->loc_mant;
-                    sync();                                   // the planes are zero before descriptors land
-                } else {
-                {
-                    int sgi = -1;
-                    for (int k = 0; k < nseg; k++)
-                        if (gt >= c->plan_lane0[k] && gt < c->plan_lane0[k + 1]) sgi = k;
-                    if (sgi >= 0) {
-                        const Segment sg = c->seg[sgi];
-                        const uint32_t o = (gt - c->plan_lane0[sgi]) * K;
-                        run_idx = sg.arr * 256 + sg.start + o;
-                        run_slot = sg.plane * 256 + sg.start + o;
-                        run_n = min(K, (uint32_t)sg.count - o);
-                        zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : ((c->dithflag >> sg.arr) & 1u);
-                        mute = (sg.arr == 5) && !c->out_lfe;
-                    }
-                }
-                // pass 1: class counts of my run.  The bap bytes are fetched a 32-bit word at a time (runs
-                // start at any byte: each word is funnelled together with its predecessor); one 32-bit LUT
-                // word per bap carries 5-bit counters (3-, 5-, 11-level, zero) and the plain field bits.
-                uint32_t cnt = 0;
-                {
-                    const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
-                    const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
-                    const uint32_t lut32 = tab_base + (uint32_t)offsetof(Tables, cnt_lut32);
-                    uint32_t wlo = bapw[wi0];
-                    for (uint32_t k = 0, j = 1; k < K; k += 4, j++) {
-                        const uint32_t whi = bapw[wi0 + j];
-                        // bytes past my run select the all-zero row 16
-                        const uint32_t vm = run_mask(run_n, k);
-                        const uint32_t v = (__funnelshift_r(wlo, whi, bsh) & vm) | (0x10101010u & ~vm);
-                        wlo = whi;
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            uint32_t l;
-                            asm("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(lut32 + prmt(v, 0, 0x4440 + t) * 4));
-                            cnt += l;
-                        }
-                    }
-                }
-                const uint32_t n1 = cnt & 31, n2 = (cnt >> 5) & 31, n4 = (cnt >> 10) & 31, n0 = (cnt >> 15) & 31;
-                const uint32_t fixed = cnt >> 20;
-                const uint32_t np = run_n - n1 - n2 - n4 - n0;
-                const uint32_t nz = n0 * (zmode == 2 ? ncpl_dith : zmode);
-                const uint32_t pa = mute ? 0u : (n1 | (n2 << 16)), pb = mute ? 0u : (n4 | (np << 16));
-                uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
-                uint32_t iz = warp_incl_scan(nz, lane);
-                if (lane == 31) { G.xch[w * 8 + 0] = ia; G.xch[w * 8 + 1] = ib; G.xch[w * 8 + 2] = iz; }
-                sync();
-                const uint32_t ta = G.xch[0] + G.xch[8], tb = G.xch[1] + G.xch[9], tz = G.xch[2] + G.xch[10];
-                if (w) { ia += G.xch[0]; ib += G.xch[1]; iz += G.xch[2]; }
-                const uint32_t e1 = (ia - pa) & 0xffff, e2 = (ia - pa) >> 16;
-                const uint32_t e4 = (ib - pb) & 0xffff, ep = (ib - pb) >> 16, ez = iz - nz;
-                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
-                const uint32_t p1 = e1 % 3, p2 = e2 % 3, p4 = e4 & 1;
-                const uint32_t s1 = (p1 + n1 + 2) / 3 - (p1 != 0);
-                const uint32_t s2 = (p2 + n2 + 2) / 3 - (p2 != 0);
-                const uint32_t s4 = (p4 + n4 + 1) / 2 - (p4 != 0);
-                const uint32_t mybits = fixed + 5 * s1 + 7 * (s2 + s4);
-                uint32_t ibits = warp_incl_scan(mybits, lane);
-                if (lane == 31) G.xch[w * 8 + 3] = ibits;
-                sync();
-                if (w) ibits += G.xch[3];
-                {
-                    const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
-                    v_ta = ta; v_tb = tb; v_tz = tz;
-                    v_mant = G.xch[3] + G.xch[11];
-                    v_base_lo = e1 | ((L2 + e2) << 16);
-                    v_base_hi = (L4 + e4) | ((LP + ep) << 16);
-                    v_base_z = LZ + ez;
-                    v_phase0 = p1 | (p2 << 8) | (p4 << 16);
-                    v_posrel = ibits - mybits;
-                    G.loc[gt] = make_uint4(run_idx | (run_n << 11) | (zmode << 16) | ((uint32_t)mute << 18) | (v_base_z << 19),
-                                           run_slot | (p1 << 11) | (p2 << 13) | (p4 << 15) | (v_posrel << 16),
-                                           v_base_lo, v_base_hi);
-                    if (gt == 0) { c->loc_ta = ta; c->loc_tb = tb; c->loc_tz = tz; c->loc_mant = v_mant; c->loc_valid = 1; }
-                }
-                }   // full pass
-                const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
-                const uint32_t* expw = reinterpret_cast<const uint32_t*>(G.exp);
-                const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
-                const uint32_t ta = v_ta, tb = v_tb, tz = v_tz, mant_bits = v_mant;
-                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
                 const uint32_t bitpos = c->bitpos;
-                const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
-                {
-                    uint32_t pos = min(bitpos + v_posrel, limit);
-                    const uint32_t base_lo = v_base_lo, base_hi = v_base_hi;
-                    const uint32_t base_z = v_base_z;
-                    const uint32_t phase0 = v_phase0;
-                    uint32_t run_a = 0, run_z = 0;
-                    const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
-                    const uint32_t zrow4 = (zmode == 1) ? 0x10101010u : 0u;
-                    const uint32_t emit_bit = mute ? 0u : 0x1000000u;
-                    // four mantissas per trip: one funnelled bap word and one exponent word, their four LUT
-                    // rows fetched together, then the four updates in coded order
-                    // emit_lut row: x: cursor increment (classes 1, 2, 4, plain); y: base selector A |
-                    // width << 16 | emit << 24; z: base selector B | 256/period << 16; w: count selector |
-                    // period << 16 | zero-list increment << 24
-                    auto emit_one = [&](uint32_t b, uint32_t e, uint32_t slot, const uint4& L) {
-                        const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
-                        const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
-                        // starts a field / group code when (phase0 + occurrences so far) % period == 0
-                        const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
-                        const uint32_t per = prmt(L.w, 0, 0x4442);
-                        const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
-                        run_a += L.x;
-                        run_z += L.w >> 24;
-                        const uint32_t emit = L.y & emit_bit;
-                        sts_u16_if(list_sa + 2 * li, slot, emit);
-                        sts_u32_if(plane_sa + 4 * slot, make_desc(e, b, pos), emit);
-                        pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
-                    };
-                    uint32_t bw_lo = bapw[wi0], ew_lo = expw[wi0];
-                    if (zmode != 2) {
-                        for (uint32_t k0 = 0, j = 1; k0 < K; k0 += 4, j++) {
-                            const uint32_t bw_hi = bapw[wi0 + j], ew_hi = expw[wi0 + j];
-                            const uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
-                            bw_lo = bw_hi;
-                            ew_lo = ew_hi;
-                            uint4 Lr[4];
-                            // mantissas past my run take the row of an undithered zero: nothing moves
-                            const uint32_t rows = (bv + zrow4) & run_mask(run_n, k0);
-#pragma unroll
-                            for (int t = 0; t < 4; t++) Lr[t] = lds_v4(lut_addr + prmt(rows, 0, 0x4440 + t) * 16);
-#pragma unroll
-                            for (int t = 0; t < 4; t++)
-                                emit_one((bv >> (8 * t)) & 0xff, (ev >> (8 * t)) & 0xff, run_slot + k0 + t, Lr[t]);
+                uint32_t ta, tb, tz, mant_bits, pos_delta = 0;
+                uint4* const plane4 = reinterpret_cast<uint4*>(G.plane);
+                if (rep) {
+                    for (int i = gt; i < P.nplanes * 64; i += NT) plane4[i] = __ldcg(snap + i);
+                    ta = c->loc_ta; tb = c->loc_tb; tz = c->loc_tz; mant_bits = c->loc_mant;
+                    pos_delta = bitpos - c->loc_bitpos;
+                } else {
+                    for (int i = gt; i < P.nplanes * 256 / 4; i += NT)
+                        reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
+                    const uint32_t K = c->plan_K;
+                    const uint32_t cpl_dith = chincpl & c->dithflag;
+                    const uint32_t ncpl_dith = __popc(cpl_dith);
+                    const int nseg = c->nseg;
+                    uint32_t run_idx = 0, run_slot = 0, run_n = 0, zmode = 0;
+                    bool mute = false;
+                    {
+                        int sgi = -1;
+                        for (int k = 0; k < nseg; k++)
+                            if (gt >= c->plan_lane0[k] && gt < c->plan_lane0[k + 1]) sgi = k;
+                        if (sgi >= 0) {
+                            const Segment sg = c->seg[sgi];
+                            const uint32_t o = (gt - c->plan_lane0[sgi]) * K;
+                            run_idx = sg.arr * 256 + sg.start + o;
+                            run_slot = sg.plane * 256 + sg.start + o;
+                            run_n = min(K, (uint32_t)sg.count - o);
+                            zmode = (sg.arr == 6) ? (ncpl_dith ? 2u : 0u) : ((c->dithflag >> sg.arr) & 1u);
+                            mute = (sg.arr == 5) && !c->out_lfe;
                         }
-                    } else {
-                        // coupling channel with dither: a bap-0 bin takes one dither value per coupled
-                        // channel, in channel order (parse.c:466-481)
-                        for (uint32_t k = 0; k < run_n; k++) {
-                            const uint32_t b = G.bap[run_idx + k], e = G.exp[run_idx + k], slot = run_slot + k;
-                            if (b == 0) {
-                                uint32_t m = cpl_dith;
-                                while (m) {
-                                    const uint32_t ch = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const uint32_t s2 = ch * 256 + (slot & 255);
-                                    G.list[base_z + run_z] = (uint16_t)s2;
-                                    run_z++;
-                                    planeU[s2] = e;
-                                }
-                            } else {
-                                emit_one(b, e, slot, lds_v4(lut_addr + b * 16));
+                    }
+                    // pass 1: class counts of my run.  The bap bytes are fetched a 32-bit word at a time (runs
+                    // start at any byte: each word is funnelled together with its predecessor); one 32-bit LUT
+                    // word per bap carries 5-bit counters (3-, 5-, 11-level, zero) and the plain field bits.
+                    const uint32_t* bapw = reinterpret_cast<const uint32_t*>(G.bap);
+                    const uint32_t* expw = reinterpret_cast<const uint32_t*>(G.exp);
+                    const uint32_t wi0 = run_idx >> 2, bsh = (run_idx & 3) * 8;
+                    uint32_t cnt = 0;
+                    {
+                        const uint32_t lut32 = tab_base + (uint32_t)offsetof(Tables, cnt_lut32);
+                        uint32_t wlo = bapw[wi0];
+                        for (uint32_t k = 0, j = 1; k < K; k += 4, j++) {
+                            const uint32_t whi = bapw[wi0 + j];
+                            // bytes past my run select the all-zero row 16
+                            const uint32_t vm = run_mask(run_n, k);
+                            const uint32_t v = (__funnelshift_r(wlo, whi, bsh) & vm) | (0x10101010u & ~vm);
+                            wlo = whi;
+    #pragma unroll
+                            for (int t = 0; t < 4; t++) {
+                                uint32_t l;
+                                asm("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(lut32 + prmt(v, 0, 0x4440 + t) * 4));
+                                cnt += l;
                             }
                         }
+                    }
+                    const uint32_t n1 = cnt & 31, n2 = (cnt >> 5) & 31, n4 = (cnt >> 10) & 31, n0 = (cnt >> 15) & 31;
+                    const uint32_t fixed = cnt >> 20;
+                    const uint32_t np = run_n - n1 - n2 - n4 - n0;
+                    const uint32_t nz = n0 * (zmode == 2 ? ncpl_dith : zmode);
+                    const uint32_t pa = mute ? 0u : (n1 | (n2 << 16)), pb = mute ? 0u : (n4 | (np << 16));
+                    uint32_t ia = warp_incl_scan(pa, lane), ib = warp_incl_scan(pb, lane);
+                    uint32_t iz = warp_incl_scan(nz, lane);
+                    if (lane == 31) { G.xch[w * 8 + 0] = ia; G.xch[w * 8 + 1] = ib; G.xch[w * 8 + 2] = iz; }
+                    sync();
+                    ta = G.xch[0] + G.xch[8]; tb = G.xch[1] + G.xch[9]; tz = G.xch[2] + G.xch[10];
+                    if (w) { ia += G.xch[0]; ib += G.xch[1]; iz += G.xch[2]; }
+                    const uint32_t e1 = (ia - pa) & 0xffff, e2 = (ia - pa) >> 16;
+                    const uint32_t e4 = (ib - pb) & 0xffff, ep = (ib - pb) >> 16, ez = iz - nz;
+                    const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
+                    const uint32_t p1 = e1 % 3, p2 = e2 % 3, p4 = e4 & 1;
+                    const uint32_t s1 = (p1 + n1 + 2) / 3 - (p1 != 0);
+                    const uint32_t s2 = (p2 + n2 + 2) / 3 - (p2 != 0);
+                    const uint32_t s4 = (p4 + n4 + 1) / 2 - (p4 != 0);
+                    const uint32_t mybits = fixed + 5 * s1 + 7 * (s2 + s4);
+                    uint32_t ibits = warp_incl_scan(mybits, lane);
+                    if (lane == 31) G.xch[w * 8 + 3] = ibits;
+                    sync();
+                    mant_bits = G.xch[3] + G.xch[11];
+                    if (w) ibits += G.xch[3];
+                    const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
+                    {
+                        uint32_t pos = min(bitpos + ibits - mybits, limit);
+                        const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
+                        const uint32_t base_z = LZ + ez;
+                        const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);
+                        uint32_t run_a = 0, run_z = 0;
+                        const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
+                        const uint32_t zrow4 = (zmode == 1) ? 0x10101010u : 0u;
+                        const uint32_t emit_bit = mute ? 0u : 0x1000000u;
+                        // four mantissas per trip: one funnelled bap word and one exponent word, their four LUT
+                        // rows fetched together, then the four updates in coded order
+                        // emit_lut row: x: cursor increment (classes 1, 2, 4, plain); y: base selector A |
+                        // width << 16 | emit << 24; z: base selector B | 256/period << 16; w: count selector |
+                        // period << 16 | zero-list increment << 24
+                        auto emit_one = [&](uint32_t b, uint32_t e, uint32_t slot, const uint4& L) {
+                            const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
+                            const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
+                            // starts a field / group code when (phase0 + occurrences so far) % period == 0
+                            const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
+                            const uint32_t per = prmt(L.w, 0, 0x4442);
+                            const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
+                            run_a += L.x;
+                            run_z += L.w >> 24;
+                            const uint32_t emit = L.y & emit_bit;
+                            sts_u16_if(list_sa + 2 * li, slot, emit);
+                            sts_u32_if(plane_sa + 4 * slot, make_desc(e, b, pos), emit);
+                            pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
+                        };
+                        uint32_t bw_lo = bapw[wi0], ew_lo = expw[wi0];
+                        if (zmode != 2) {
+                            for (uint32_t k0 = 0, j = 1; k0 < K; k0 += 4, j++) {
+                                const uint32_t bw_hi = bapw[wi0 + j], ew_hi = expw[wi0 + j];
+                                const uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
+                                bw_lo = bw_hi;
+                                ew_lo = ew_hi;
+                                uint4 Lr[4];
+                                // mantissas past my run take the row of an undithered zero: nothing moves
+                                const uint32_t rows = (bv + zrow4) & run_mask(run_n, k0);
+    #pragma unroll
+                                for (int t = 0; t < 4; t++) Lr[t] = lds_v4(lut_addr + prmt(rows, 0, 0x4440 + t) * 16);
+    #pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                    emit_one((bv >> (8 * t)) & 0xff, (ev >> (8 * t)) & 0xff, run_slot + k0 + t, Lr[t]);
+                            }
+                        } else {
+                            // coupling channel with dither: a bap-0 bin takes one dither value per coupled
+                            // channel, in channel order (parse.c:466-481)
+                            for (uint32_t k = 0; k < run_n; k++) {
+                                const uint32_t b = G.bap[run_idx + k], e = G.exp[run_idx + k], slot = run_slot + k;
+                                if (b == 0) {
+                                    uint32_t m = cpl_dith;
+                                    while (m) {
+                                        const uint32_t ch = __ffs(m) - 1;
+                                        m &= m - 1;
+                                        const uint32_t s2 = ch * 256 + (slot & 255);
+                                        G.list[base_z + run_z] = (uint16_t)s2;
+                                        run_z++;
+                                        planeU[s2] = e;
+                                    }
+                                } else {
+                                    emit_one(b, e, slot, lds_v4(lut_addr + b * 16));
+                                }
+                            }
+                        }
+                    }
+                    sync();
+                    for (int i = gt; i < P.nplanes * 64; i += NT) __stcg(snap + i, plane4[i]);
+                    if (gt == 0) {
+                        c->loc_ta = ta; c->loc_tb = tb; c->loc_tz = tz; c->loc_mant = mant_bits;
+                        c->loc_bitpos = bitpos;
+                        c->loc_valid = 1;
                     }
                 }
                 sync();
                 if (gt == 0) c->bitpos = bitpos + mant_bits;
+                const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
+                const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
 
                 // ================= U =================
                 if (tz) {
@@ -1851,15 +1840,15 @@ a52_decode_kernel(const DecodeParams P)
                     }
                     dither_index = (dither_index + tz) % kDitherPeriod;
                 }
-                if (t1) unpack_groups<3, 5, 32, NT>(G, W, 0, t1, &T.q1[0][0], gt);
-                if (t2) unpack_groups<3, 7, 128, NT>(G, W, L2, t2, &T.q2[0][0], gt);
-                if (t4) unpack_groups<2, 7, 128, NT>(G, W, L4, t4, &T.q4[0][0], gt);
+                if (t1) unpack_groups<3, 5, 32, NT>(G, W, 0, t1, &T.q1[0][0], gt, pos_delta, limit);
+                if (t2) unpack_groups<3, 7, 128, NT>(G, W, L2, t2, &T.q2[0][0], gt, pos_delta, limit);
+                if (t4) unpack_groups<2, 7, 128, NT>(G, W, L4, t4, &T.q4[0][0], gt, pos_delta, limit);
                 for (uint32_t k = gt; k < tp; k += NT) {
                     const uint32_t slot = G.list[LP + k];
                     const uint32_t d = planeU[slot];
                     const uint32_t b = (d >> 5) & 15;
                     const uint32_t wbits = T.bap_bits[b];
-                    const uint32_t raw = peek_nz(W, (d >> 10) & 0x7fff, wbits);
+                    const uint32_t raw = peek_nz(W, min(((d >> 10) & 0x7fff) + pos_delta, limit), wbits);
                     int q = ((int)(raw << (32 - wbits))) >> 16;
                     if (b <= 5) q = T.q35[(b & 4) * 2 + raw];
                     G.plane[slot] = (float)q * pow2neg(15 + (d & 31));

@@ -366,7 +366,7 @@ struct a52_batch_s {
     float mode_level = 0;
     // host-mode scratch
     struct Buf { void* p = nullptr; size_t cap = 0; } b_es, b_off, b_first, b_pcm, b_status, b_flags,
-        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo, b_slice, b_done;
+        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo, b_slice, b_done, b_snap;
 };
 
 #define A52_CUDA(call)                                                                       \
@@ -446,7 +446,7 @@ void a52_batch_destroy(a52_batch_t* ctx)
     cudaSetDevice(ctx->device);
     a52_batch_s::Buf* bufs[] = {&ctx->b_es, &ctx->b_off, &ctx->b_first, &ctx->b_pcm, &ctx->b_status,
                                 &ctx->b_flags, &ctx->b_carry, &ctx->b_dexp, &ctx->b_dbap, &ctx->b_dcoef,
-                                &ctx->b_dinfo, &ctx->b_slice, &ctx->b_done};
+                                &ctx->b_dinfo, &ctx->b_slice, &ctx->b_done, &ctx->b_snap};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_dither) cudaFree(ctx->d_dither);
@@ -550,7 +550,7 @@ double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
 // several launches of one call are in flight at once (host pipeline); 0 / 0 = a launch on its own
 static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int max_frame_bytes,
                          float level, cudaStream_t st, int counter_slot = 0, int max_stream_frames = 0,
-                         int scratch_base = 0, int scratch_total = 0)
+                         int scratch_base = 0, int scratch_total = 0, int snap_streams = 0)
 {
     using namespace a52;
     // work units of the pair kernel: slices of streams (see a52_decode_kernel)
@@ -607,6 +607,18 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     if (grid > ctx->num_sms) grid = ctx->num_sms;
     if (grid < 1) grid = 1;
     A52_CUDA(cudaMemsetAsync(ctx->d_counter + counter_slot, 0, sizeof(int), st));
+    // scratch of the locate stage: one plane image per resident pair.  Launches of one host-pointer call run
+    // side by side: each takes the region of its counter slot, all regions sized for the largest chunk.
+    {
+        const int nmax = scratch_total ? snap_streams : P.nstreams;
+        size_t pairs = (size_t)nmax + ctx->num_sms;
+        const size_t cap = (size_t)ctx->num_sms * fit;
+        if (pairs > cap) pairs = cap;
+        const size_t region = pairs * P.nplanes * 1024;
+        const int regions = scratch_total ? 32 : 1;
+        if (ensure(ctx, ctx->b_snap, region * regions)) return -1;
+        P.snap = (uint4*)((uint8_t*)ctx->b_snap.p + region * (scratch_total ? counter_slot : 0));
+    }
     // timing events
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
         if (ctx->ev_pool.size() < 8192) {
@@ -811,7 +823,8 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             int n = (int)(stream_first[q + 1] - stream_first[q]);
             if (n > chunk_max) chunk_max = n;
         }
-        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_k, cidx, chunk_max, s0, nstreams);
+        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_k, cidx, chunk_max, s0, nstreams,
+                               (nstreams + nchunks - 1) / nchunks + 1);
         if (rc) return rc;
         A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_k));
         A52_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_run[cidx], 0));
