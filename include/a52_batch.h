@@ -78,6 +78,10 @@ typedef struct {
     int32_t * info;
 } a52_batch_debug_t;
 
+/* A context owns device scratch (work counters, carry and locate-stage scratch, staging buffers): like an
+ * a52_state_t (liba52 is re-entrant per state, one state = one thread at a time, NEWS:3) it serves ONE call at
+ * a time.  Asynchronous device-pointer calls of one context must be issued on one CUDA stream (or be ordered
+ * by the caller); use one context per host thread or stream for concurrency. */
 a52_batch_t * a52_batch_create (int device);
 void a52_batch_destroy (a52_batch_t * ctx);
 const char * a52_batch_last_error (a52_batch_t * ctx);

@@ -46,6 +46,7 @@ typedef struct {
     int32_t * snr;
 } ac3_batch_debug_t;
 
+/* one call at a time per context (it owns device scratch); one context per host thread or stream */
 ac3_batch_t * ac3_batch_create (int device);
 void ac3_batch_destroy (ac3_batch_t * ctx);
 const char * ac3_batch_last_error (ac3_batch_t * ctx);
