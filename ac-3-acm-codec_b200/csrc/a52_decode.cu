@@ -1632,7 +1632,8 @@ a52_decode_kernel(const DecodeParams P)
                 const uint32_t limit = c->limit_bit;
 
                 // ================= E =================
-                {
+                // (a block that repeats the last allocation has no exponents to decode and nothing to allocate)
+                if (!c->repeat) {
                     int bad = 0, k = 0;
                     for (int a = 0; a < 7; a++) {
                         if (!c->expstr[a]) continue;
@@ -1868,7 +1869,7 @@ a52_decode_kernel(const DecodeParams P)
                     }
                 }
                 if (c->out_lfe && gt < 7) G.plane[5 * 256 + gt] *= c->gain[5];
-                sync();
+                if (!unif || c->out_lfe) sync();
                 if (chincpl) {
                     const int first = __ffs(chincpl) - 1;
                     for (int bin = c->cplstrtmant + gt; bin < c->cplendmant; bin += NT) {
