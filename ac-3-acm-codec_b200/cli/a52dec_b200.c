@@ -438,13 +438,14 @@ static int disable_dynrng, disable_adjust;
 static double gain = 1;
 static int demux_track, demux_pid, demux_pes;
 static const char * out_dir;
+static int extract_only;	/* -x: write the demultiplexed elementary stream (what extract_a52 does) */
 
 static void usage (const char * argv0)
 {
     int i;
     fprintf (stderr,
 	     "usage: %s [-h] [-o <mode>] [-s [<track>]] [-t <pid>] [-T] [-c] [-r] [-a] \\\n"
-	     "\t\t[-g <gain>] [-O <dir>] [-C <frames>] <file> [<file> ...]\n"
+	     "\t\t[-g <gain>] [-O <dir>] [-C <frames>] [-x] <file> [<file> ...]\n"
 	     "\t-h\tdisplay help and available audio output modes\n"
 	     "\t-s\tuse program stream demultiplexer, track 0-7 or 0x80-0x87\n"
 	     "\t-t\tuse transport stream demultiplexer, pid 0x10-0x1ffe\n"
@@ -455,6 +456,7 @@ static void usage (const char * argv0)
 	     "\t-g\tadd specified gain in decibels, -96.0 to +96.0\n"
 	     "\t-O\tdecode all files as one batch, one output per file in <dir>\n"
 	     "\t-C\tframes of a stream per engine call (default 4096)\n"
+	     "\t-x\tonly demultiplex: write the AC-3 elementary stream (extract_a52; default -s 0x80)\n"
 	     "\t-o\taudio output mode\n", argv0);
     for (i = 0; drivers[i].name; i++)
 	fprintf (stderr, "\t\t\t%s\n", drivers[i].name);
@@ -562,7 +564,7 @@ int main (int argc, char ** argv)
     int chunk = 4096;		/* frames of one stream per engine call (-C) */
 
     fprintf (stderr, "a52dec_b200 - a52dec's command line on the batched B200 AC-3 engine\n");
-    while ((c = getopt (argc, argv, "hs::t:Tcrag:o:O:C:")) != -1)
+    while ((c = getopt (argc, argv, "hs::t:Tcrag:o:O:C:x")) != -1)
 	switch (c) {
 	case 'o':
 	    for (i = 0; drivers[i].name; i++)
@@ -614,6 +616,9 @@ int main (int argc, char ** argv)
 	case 'O':
 	    out_dir = optarg;
 	    break;
+	case 'x':
+	    extract_only = 1;
+	    break;
 	case 'C':
 	    chunk = strtol (optarg, &s, 0);
 	    if (chunk < 1 || *s) {
@@ -626,6 +631,8 @@ int main (int argc, char ** argv)
 	}
     if (!drv)
 	drv = drivers;
+    if (extract_only && !demux_pid && !demux_pes && !demux_track)
+	demux_track = 0x80;	/* extract_a52.c:40: program stream, first AC-3 track */
     ninputs = argc - optind;
     if (ninputs > 1 && !out_dir) {
 	fprintf (stderr, "several inputs need -O <dir>\n");
@@ -656,6 +663,28 @@ int main (int argc, char ** argv)
 	    in[i].es = raw;
 	if (!in[i].es.p)
 	    bytes_add (&in[i].es, (const uint8_t *) "", 0);
+	if (extract_only) {
+	    /* extract_a52 (src/extract_a52.c): the demultiplexers above with fwrite in the place of the
+	     * decoder; no GPU is touched */
+	    FILE * fp = stdout;
+	    if (out_dir) {
+		char path[4096];
+		const char * base = strrchr (in[i].path, '/');
+		base = base ? base + 1 : in[i].path;
+		snprintf (path, sizeof (path), "%s/%s.ac3", out_dir, base);
+		if (!(fp = fopen (path, "wb"))) {
+		    fprintf (stderr, "%s - could not open file %s\n", strerror (errno), path);
+		    return 1;
+		}
+	    }
+	    fwrite (in[i].es.p, 1, in[i].es.n, fp);
+	    if (fp != stdout)
+		fclose (fp);
+	    else
+		fflush (stdout);
+	    fatal |= in[i].fatal;
+	    continue;
+	}
 	memset (in[i].es.p + in[i].es.n, 0, 16);
 	index_frames (in[i].es.p, in[i].es.n, &in[i].fr);
 	for (long k = 0; k < in[i].fr.skipped; k++)
@@ -675,6 +704,8 @@ int main (int argc, char ** argv)
 	    in[i].sink.fp = stdout;
     }
 
+    if (extract_only)
+	return fatal ? 1 : 0;
     ctx = a52_batch_create (0);
     if (!ctx) {
 	fprintf (stderr, "A52 init failed\n");
