@@ -1392,6 +1392,17 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)blk * 512);
             dst[q] = make_float4(y[0][0] + bias, y[1][0] + bias, y[0][1] + bias, y[1][1] + bias);
             dst[127 - q] = make_float4(y[0][2] + bias, y[1][2] + bias, y[0][3] + bias, y[1][3] + bias);
+        } else if (P.out_fmt == 1 && nout == 6 && !nobias) {
+            // 5.1 interleaved float: samples p, p + 1 of the six channels are 48 contiguous, 16-byte aligned bytes
+            const float bias = P.bias;
+            float4* lo = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + ((size_t)blk * 256 + p) * 6);
+            float4* hi = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + ((size_t)blk * 256 + 254 - p) * 6);
+            lo[0] = make_float4(y[0][0] + bias, y[1][0] + bias, y[2][0] + bias, y[3][0] + bias);
+            lo[1] = make_float4(y[4][0] + bias, y[5][0] + bias, y[0][1] + bias, y[1][1] + bias);
+            lo[2] = make_float4(y[2][1] + bias, y[3][1] + bias, y[4][1] + bias, y[5][1] + bias);
+            hi[0] = make_float4(y[0][2] + bias, y[1][2] + bias, y[2][2] + bias, y[3][2] + bias);
+            hi[1] = make_float4(y[4][2] + bias, y[5][2] + bias, y[0][3] + bias, y[1][3] + bias);
+            hi[2] = make_float4(y[2][3] + bias, y[3][3] + bias, y[4][3] + bias, y[5][3] + bias);
         } else {
 #pragma unroll
             for (int oc = 0; oc < 6; oc++) {

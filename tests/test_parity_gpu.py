@@ -215,6 +215,14 @@ def test_s16_and_interleaved_output(decoder, engine, oracle, c2):
     off, out = gpu_decode(decoder, engine, es, oracle, flags, fmt=engine.PCM_F32_INTERLEAVED)
     got = out["pcm"].reshape(8, 6, 256, 2).transpose(0, 1, 3, 2).reshape(48, 2, 256)
     assert relrms(got, want) < TOL_PCM
+    # six channels interleaved (vector stores of 48 bytes per sample pair), with and without bias
+    for bias in (0.0, 384.0):
+        flags6 = A52_3F2R | A52_LFE
+        nf, want = oracle.decode_stream(es, flags6, 1.0, bias)
+        off, out = gpu_decode(decoder, engine, es, oracle, flags6, bias=bias, fmt=engine.PCM_F32_INTERLEAVED)
+        got = out["pcm"].reshape(8, 6, 256, 6).transpose(0, 1, 3, 2).reshape(48, 6, 256)
+        d = (got.astype(np.float64) - want).reshape(-1)
+        assert np.sqrt((d * d).mean()) < TOL_PCM * np.sqrt(((want - bias) ** 2).mean()) + (2.0 ** -15 if bias else 0)
 
 
 # ---------------------------------------------------------------------------
