@@ -299,13 +299,17 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
                 AC3_CUDA(cudaEventCreateWithFlags(&ctx->ev_run[i], cudaEventDisableTiming));
             }
         }
-        int nchunks = nstreams / 512;
-        if (nchunks > 16) nchunks = 16;
+        // a chunk is a whole number of waves (one CTA per stream, num_sms * occ resident): anything else pays
+        // for a second, nearly empty wave; the last chunk takes the remainder
+        const int wave = ctx->num_sms * occ;
+        int per = wave * ((nstreams + 16 * wave - 1) / (16 * wave));
+        int nchunks = nstreams / per;
+        if (nchunks < 1) nchunks = 1;
         AC3_CUDA(cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(int), ctx->s_run));
         if (carry) AC3_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, ctx->s_run));
         const size_t pcm_per = (size_t)nframes * 1536 * channels * 2, out_per = (size_t)nframes * c.frame_words * 2;
         for (int k = 0; k < nchunks; k++) {
-            const int s0 = (int)((long long)k * nstreams / nchunks), s1 = (int)((long long)(k + 1) * nstreams / nchunks);
+            const int s0 = k * per, s1 = (k + 1 == nchunks) ? nstreams : (k + 1) * per;
             AC3_CUDA(cudaMemcpyAsync((uint8_t*)ctx->b_pcm.p + s0 * pcm_per, (const uint8_t*)pcm + s0 * pcm_per,
                                      (s1 - s0) * pcm_per, cudaMemcpyHostToDevice, ctx->s_in));
             AC3_CUDA(cudaEventRecord(ctx->ev_in[k], ctx->s_in));
