@@ -71,6 +71,8 @@ struct EncParams {
     int32_t*  status;
     EncCarry* carry;
     int*      work_counter;
+    int*      slice_done;                // [nstreams] slices finished per stream (work units are slices of streams)
+    int       slice_frames, nslices;
     int nstreams, nframes;
     int nch_all, nch, lfe, acmod, fscod, halfrate, bsid, frmsizecod, frame_words;
     uint32_t crc_inv;                    // x^-(16 fs58 - 16) mod poly (ac3enc.cpp:1627)
@@ -580,18 +582,35 @@ ac3_encode_kernel(const EncParams P)
     const int nbytes = P.frame_words * 2;
     const bool active = warp < P.nch_all;                              // warp = coded channel
 
+    // Work units are slices of streams (P.slice_frames frames), handed out slice-major from one ticket counter;
+    // a slice starts from the carry record its predecessor left in global memory.  The predecessor holds a
+    // smaller ticket and every CTA of the grid is resident, so the wait below cannot deadlock.  Slices keep
+    // the last wave of a launch short (4096 streams on 444 resident CTAs are 9.2 waves of whole streams).
+    const int nunits = P.nstreams * P.nslices;
     for (;;) {
         if (tid == 0) s_stream = atomicAdd(P.work_counter, 1);
         __syncthreads();
-        const int s = s_stream;
-        if (s >= P.nstreams) break;
+        const int ticket = s_stream;
+        if (ticket >= nunits) break;
+        const int slice = ticket / P.nstreams, s = ticket - slice * P.nstreams;
+        const int f_begin = slice * P.slice_frames;
+        const int f_end = (P.nslices > 1 && f_begin + P.slice_frames < P.nframes) ? f_begin + P.slice_frames : P.nframes;
+        if (slice > 0) {
+            if (tid == 0) {
+                volatile int* done = P.slice_done + s;
+                while (*done < slice) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
         // carry in
+        const bool started = P.carry && __ldcg(&P.carry[s].started);
         for (int i = tid; i < 6 * 256; i += kThreads)
-            S.last[i >> 8][i & 255] = (P.carry && P.carry[s].started) ? P.carry[s].last_samples[i >> 8][i & 255] : 0;
-        if (tid == 0) S.cs = (P.carry && P.carry[s].started) ? P.carry[s].csnroffst : 40;      // :1092
+            S.last[i >> 8][i & 255] = started ? __ldcg(&P.carry[s].last_samples[i >> 8][i & 255]) : (int16_t)0;
+        if (tid == 0) S.cs = started ? __ldcg(&P.carry[s].csnroffst) : 40;      // :1092
         __syncthreads();
 
-        for (int f = 0; f < P.nframes; f++) {
+        for (int f = f_begin; f < f_end; f++) {
             const size_t fidx = (size_t)s * P.nframes + f;
             const int16_t* pcm = P.pcm + fidx * 1536 * P.nch_all;
             // ================= E1 =================
@@ -918,6 +937,11 @@ ac3_encode_kernel(const EncParams P)
         if (P.carry) {
             for (int i = tid; i < 6 * 256; i += kThreads) P.carry[s].last_samples[i >> 8][i & 255] = S.last[i >> 8][i & 255];
             if (tid == 0) { P.carry[s].csnroffst = S.cs; P.carry[s].started = 1; }
+        }
+        if (P.nslices > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(P.slice_done + s, slice + 1);
         }
         __syncthreads();
     }

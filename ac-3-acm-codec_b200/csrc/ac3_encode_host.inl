@@ -113,7 +113,8 @@ struct ac3_batch_s {
     long launches = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    struct Buf { void* p = nullptr; size_t cap = 0; } b_pcm, b_out, b_status, b_carry, b_coef, b_shift, b_strat, b_enc, b_bap, b_snr;
+    struct Buf { void* p = nullptr; size_t cap = 0; } b_pcm, b_out, b_status, b_carry, b_coef, b_shift, b_strat, b_enc, b_bap, b_snr, b_done, b_scarry;
+    int slice_frames = 32;         // frames per work unit (AC3_B200_SLICE_FRAMES)
     // host-pointer calls: PCM H2D | kernel | frames D2H on three streams, chunks of streams
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[16] = {}, ev_run[16] = {};
@@ -154,6 +155,8 @@ ac3_batch_t* ac3_batch_create(int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->num_sms = prop.multiProcessorCount;
+    const char* sf = getenv("AC3_B200_SLICE_FRAMES");
+    if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
     ac3e::EncTables* T = new ac3e::EncTables;
     ac3e::build_enc_tables(T);
     bool ok = cudaMemcpyToSymbol(ac3e::g_enc_tables, T, sizeof(*T)) == cudaSuccess;
@@ -170,7 +173,8 @@ void ac3_batch_destroy(ac3_batch_t* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ac3_batch_s::Buf* bufs[] = {&ctx->b_pcm, &ctx->b_out, &ctx->b_status, &ctx->b_carry, &ctx->b_coef,
-                                &ctx->b_shift, &ctx->b_strat, &ctx->b_enc, &ctx->b_bap, &ctx->b_snr};
+                                &ctx->b_shift, &ctx->b_strat, &ctx->b_enc, &ctx->b_bap, &ctx->b_snr, &ctx->b_done,
+                                &ctx->b_scarry};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -287,6 +291,31 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
     }
     int grid = ctx->num_sms * occ;
     if (grid > nstreams) grid = nstreams;
+    // work units: slices of streams (see the kernel); the carry record links the slices of a stream
+    P.slice_frames = ctx->slice_frames;
+    P.nslices = 1;
+    if (nframes > ctx->slice_frames && !P.dbg_coef) {
+        P.nslices = (nframes + ctx->slice_frames - 1) / ctx->slice_frames;
+        cudaStream_t s0 = pipelined ? ctx->s_run : st;
+        if (pipelined && !ctx->s_in) {
+            AC3_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+            AC3_CUDA(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking));
+            AC3_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+            for (int i = 0; i < 16; i++) {
+                AC3_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+                AC3_CUDA(cudaEventCreateWithFlags(&ctx->ev_run[i], cudaEventDisableTiming));
+            }
+            s0 = ctx->s_run;
+        }
+        if (ac3_ensure(ctx, ctx->b_done, (size_t)nstreams * sizeof(int))) return -1;
+        AC3_CUDA(cudaMemsetAsync(ctx->b_done.p, 0, (size_t)nstreams * sizeof(int), s0));
+        P.slice_done = (int*)ctx->b_done.p;
+        if (!P.carry) {
+            if (ac3_ensure(ctx, ctx->b_scarry, (size_t)nstreams * sizeof(EncCarry))) return -1;
+            AC3_CUDA(cudaMemsetAsync(ctx->b_scarry.p, 0, (size_t)nstreams * sizeof(EncCarry), s0));
+            P.carry = (EncCarry*)ctx->b_scarry.p;
+        }
+    }
     if (pipelined) {
         // Large host-pointer batches: chunks of streams flow through PCM H2D | kernel | frames D2H on three
         // CUDA streams (a chunk still fills every SM several times over).
@@ -319,6 +348,7 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
             Pk.out = P.out + s0 * out_per;
             Pk.status = P.status + (size_t)s0 * nframes;
             Pk.carry = P.carry ? P.carry + s0 : nullptr;
+            Pk.slice_done = P.slice_done ? P.slice_done + s0 : nullptr;
             Pk.nstreams = s1 - s0;
             Pk.work_counter = ctx->d_counter + k;
             int gk = ctx->num_sms * occ;
@@ -333,7 +363,7 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
                 AC3_CUDA(cudaMemcpyAsync(status + (size_t)s0 * nframes, P.status + (size_t)s0 * nframes,
                                          (size_t)(s1 - s0) * nframes * 4, cudaMemcpyDeviceToHost, ctx->s_out));
         }
-        if (carry) AC3_CUDA(cudaMemcpyAsync(carry, P.carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, ctx->s_run));
+        if (carry) AC3_CUDA(cudaMemcpyAsync(carry, ctx->b_carry.p, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, ctx->s_run));
         AC3_CUDA(cudaStreamSynchronize(ctx->s_run));
         AC3_CUDA(cudaStreamSynchronize(ctx->s_out));
         AC3_CUDA(cudaStreamSynchronize(ctx->s_in));
@@ -360,7 +390,7 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
 
     AC3_CUDA(cudaMemcpyAsync(out, P.out, out_bytes, cudaMemcpyDeviceToHost, st));
     if (status) AC3_CUDA(cudaMemcpyAsync(status, P.status, total * 4, cudaMemcpyDeviceToHost, st));
-    if (carry) AC3_CUDA(cudaMemcpyAsync(carry, P.carry, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, st));
+    if (carry) AC3_CUDA(cudaMemcpyAsync(carry, ctx->b_carry.p, sizeof(EncCarry) * (size_t)nstreams, cudaMemcpyDeviceToHost, st));
     if (P.dbg_coef && debug) {
         AC3_CUDA(cudaMemcpyAsync(debug->coef, P.dbg_coef, total * 9216 * 4, cudaMemcpyDeviceToHost, st));
         AC3_CUDA(cudaMemcpyAsync(debug->exp_shift, P.dbg_shift, total * 36, cudaMemcpyDeviceToHost, st));

@@ -203,3 +203,30 @@ def test_pipelined_host_batch_equals_single_launch(encoder):
     for k in (0, 511, 650, 1299):
         a, b = big["carry"][k], small["carry"][pick[k]]
         assert bytes(a) == bytes(b)
+
+
+def test_time_slices_are_invisible(engine, monkeypatch):
+    """Streams longer than a slice (32 frames) are encoded as several work units linked by the carry record
+    (last 256 samples per channel, SNR search warm start): byte-identical to whole-stream units, to the
+    oracle, and to a caller who cuts the stream himself."""
+    nch, rate, br, nfr = 2, 48000, 192000, 75
+    pcm = np.stack([synth_pcm(12, s, nch, 1536 * nfr, rate, noise=0.03, bursts=(s == 1)) for s in range(5)])
+    outs = []
+    for sf in ("32", "7", "1000"):
+        monkeypatch.setenv("AC3_B200_SLICE_FRAMES", sf)
+        enc = engine.BatchEncoder(0)
+        outs.append(enc.encode_host(pcm, rate, br, carry=[None] * 5))
+        enc.close()
+    for o in outs[1:]:
+        assert (o["frames"] == outs[0]["frames"]).all() and (o["status"] == 0).all()
+        assert all(bytes(a) == bytes(b) for a, b in zip(o["carry"], outs[0]["carry"]))
+    ora = OracleEnc()
+    fb, want = ora.encode_stream(pcm[1], rate, br)
+    assert outs[0]["frames"][1].reshape(-1).tobytes() == want.tobytes()
+    # the caller's own cut: 40 + 35 frames with the carry record
+    monkeypatch.setenv("AC3_B200_SLICE_FRAMES", "32")
+    enc = engine.BatchEncoder(0)
+    a = enc.encode_host(pcm[:, :1536 * 40], rate, br, carry=[None] * 5)
+    b = enc.encode_host(pcm[:, 1536 * 40:], rate, br, carry=list(a["carry"]))
+    enc.close()
+    assert (np.concatenate([a["frames"], b["frames"]], axis=1) == outs[0]["frames"]).all()
