@@ -97,6 +97,9 @@ struct DecodeParams {
     uint8_t*        dbg_bap;
     float*          dbg_coef;
     int32_t*        dbg_info;
+    // a52_downmix_init for every BSI combination under this call's request: [acmod_ext 0..8][cmixlev * 4 +
+    // surmixlev].  Travels with the launch (constant bank), so contexts and calls share no mutable state.
+    ModeEntry       mode[9 * 16];
 };
 
 }  // namespace a52

@@ -46,7 +46,6 @@ namespace a52 {
 // ---------------------------------------------------------------------------
 // constant memory (warp-uniform lookups only)
 // ---------------------------------------------------------------------------
-__constant__ ModeEntry c_mode[9 * 16];     // [acmod_ext 0..8][cmixlev*4 + surmixlev]
 __constant__ MixEntry  c_mix[8 * 11];      // [acmod][output mode]
 __constant__ uint8_t   c_nfchans[8] = {2, 1, 2, 3, 3, 4, 4, 5};
 __constant__ uint16_t  c_bitrate[19] = {32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320,
@@ -301,7 +300,7 @@ __device__ int parse_frame_header(GroupCtl* c, const uint32_t* w, uint32_t base_
     c->slev = slev;
     c->lfeon = br.get(1);
 
-    ModeEntry me = c_mode[acmod_ext * 16 + cmix * 4 + smix];
+    ModeEntry me = P.mode[acmod_ext * 16 + cmix * 4 + smix];
     if (me.output < 0) return 2;                               // A52_ST_BAD_FRAME
     c->output = me.output;
     c->out_lfe = (c->lfeon && (P.req_flags & M_LFE)) ? 1 : 0;

@@ -364,6 +364,7 @@ struct a52_batch_s {
     // cached mode table key
     int mode_flags = -1;
     float mode_level = 0;
+    a52::ModeEntry mode_tab[9 * 16];   // the request's grant / level table, copied into every launch's parameters
     // host-mode scratch
     struct Buf { void* p = nullptr; size_t cap = 0; } b_es, b_off, b_first, b_pcm, b_status, b_flags,
         b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo, b_slice, b_done, b_snap;
@@ -571,14 +572,11 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     }
     // per-request constants
     if (ctx->mode_flags != P.req_flags || ctx->mode_level != level) {
-        ModeEntry tab[9 * 16];
-        build_mode_table(tab, P.req_flags, level);
-        A52_CUDA(cudaMemcpyToSymbolAsync(c_mode, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
-        // the host array dies at return: make sure the copy has been consumed
-        A52_CUDA(cudaStreamSynchronize(st));
+        build_mode_table(ctx->mode_tab, P.req_flags, level);
         ctx->mode_flags = P.req_flags;
         ctx->mode_level = level;
     }
+    memcpy(P.mode, ctx->mode_tab, sizeof(P.mode));
     if (max_frame_bytes < 128) max_frame_bytes = 128;
     if (max_frame_bytes > 3840) max_frame_bytes = 3840;
     P.fbuf_bytes = align16(max_frame_bytes + 15) + 16 + 16;
