@@ -27,6 +27,13 @@ struct __align__(16) Tables {
     float2   pre2[64];
     float2   post2[32];
     float2   wfft[128];        // e^{-2 pi j k / 128}
+    // the same twiddles with every factor duplicated, (x, x, y, y): operands of the packed two-channel
+    // transform (fma.rn.f32x2 has no scalar-broadcast form, so the broadcast lives in the table)
+    float4   pre1d[128];
+    float4   wfftd[128];
+    float4   post1d[64];
+    float4   win2d[128];       // (w[2q], w[2q], w[2q+1], w[2q+1])
+    uint4    fftaddr[32];      // per lane: swizzled scratch byte offsets of the paired transform (see imdct512_pair)
     int16_t  q1[3][32];        // grouped 3-level values by (digit, 5-bit code)
     int16_t  q2[3][128];       // grouped 5-level values by (digit, 7-bit code)
     int16_t  q4[2][128];       // grouped 11-level values by (digit, 7-bit code)
@@ -71,6 +78,7 @@ struct DecodeParams {
     const uint64_t* frame_off;
     const uint32_t* stream_first;
     int             nstreams;
+    int             nframes;         // entries of frame_off
     int             req_flags;
     float           bias;
     int             drc_off;

@@ -74,6 +74,7 @@ struct __align__(16) GroupCtl {
     int      frame_ok;         // frame header valid
     int      err;              // error raised inside the current block
     int      tr_ticket;        // transform jobs of the pending block handed out so far
+    float    wg2[12];          // wt[o][ch] * gain[ch] of outputs 0 and 1 ([0..4] and [5..9]): the stereo mix fast path
     // what the last full locate pass left for blocks that repeat its baps, ranges and flags
     uint32_t loc_ta, loc_tb, loc_tz, loc_mant, loc_bitpos;
     uint8_t  loc_valid, loc_dithflag, loc_chincpl, repeat;
@@ -92,7 +93,7 @@ struct __align__(16) GroupCtl {
     uint32_t cplbndstrc;
     uint8_t  rematflg, csnroffst, cplfleak, cplsleak;
     uint8_t  endmant[5];
-    uint8_t  expstr[7];        // this block's strategies (0 = reuse)
+    alignas(4) uint8_t expstr[7];   // this block's strategies (0 = reuse)
     uint16_t bai;
     uint8_t  chbai[7];
     uint8_t  deltbae[7];
@@ -137,29 +138,30 @@ constexpr int kListEntries = 1504;   // >= 5*253 + 216 + 7 mantissa slots per bl
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline int warp_smem_bytes(int fbuf_bytes, int nplanes)
-{
-    int n = 0;
-    n += align16((int)sizeof(GroupCtl));
-    n += 7 * 256 * 2;
-    n += align16(kListEntries * 2);
-    n += nplanes * 256 * 4;
-    n += fbuf_bytes;
-    n += 16;
-    return n;
-}
+// The lists and the planes come first in a pair's shared memory, which starts 128-byte aligned: the paired
+// transform of the stereo fast path works in place on planes 0 and 1 and XORs address bits 4..6.
+constexpr int kListBytes = (kListEntries * 2 + 127) & ~127;
+__host__ __device__ inline int align128(int x) { return (x + 127) & ~127; }
 
-__device__ inline WarpPtrs carve(uint8_t* base, int fbuf_bytes, int nplanes)
+// Layout of a pair's shared memory.  Every offset but the size of the staged frame (last) is a compile-time
+// constant of the kernel instantiation (NPL = coefficient planes: 5, or 6 when the LFE channel is requested), so
+// all of a pair's addresses are one register plus an immediate.
+template <int NPL>
+struct PairLayout {
+    static constexpr int list = 0;
+    static constexpr int plane = list + kListBytes;                    // [NPL][256] float, 128-byte aligned
+    static constexpr int delay = plane + NPL * 1024;                   // [NPL][128] float overlap-add tails
+    static constexpr int ctl = delay + NPL * 512;
+    static constexpr int exp = ctl + (((int)sizeof(GroupCtl) + 15) & ~15);
+    static constexpr int bap = exp + 7 * 256;
+    static constexpr int xch = bap + 7 * 256;                          // [2][8] scan totals of the two warps
+    static constexpr int mbar = xch + 64;
+    static constexpr int fbuf = mbar + 16;                             // staged frame, fbuf_bytes
+};
+
+__host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
 {
-    WarpPtrs g;
-    g.ctl = reinterpret_cast<GroupCtl*>(base);  base += align16((int)sizeof(GroupCtl));
-    g.exp = base;                               base += 7 * 256;
-    g.bap = base;                               base += 7 * 256;
-    g.list = reinterpret_cast<uint16_t*>(base); base += align16(kListEntries * 2);
-    g.plane = reinterpret_cast<float*>(base);   base += nplanes * 256 * 4;
-    g.fbuf = reinterpret_cast<uint32_t*>(base); base += fbuf_bytes;
-    g.mbar = reinterpret_cast<uint64_t*>(base);
-    return g;
+    return align128((nplanes == 6 ? PairLayout<6>::fbuf : PairLayout<5>::fbuf) + fbuf_bytes);
 }
 
 // ---------------------------------------------------------------------------
@@ -241,11 +243,19 @@ struct BitReader {
 
 // bytes to stage for frame f: from the 16-byte aligned address at or below its
 // offset up to the start of the next frame (or the end of the buffer), capped
+// end of frame f's bytes: the start of the next frame of the table, or the end of the buffer (for the last frame of
+// the table, and for tables that are not ascending: frames of different streams may lie in any order)
+__device__ __forceinline__ uint64_t frame_end(const DecodeParams& P, uint32_t f, uint64_t off)
+{
+    const uint64_t nxt = (f + 1 < (uint32_t)P.nframes) ? P.frame_off[f + 1] : P.es_bytes;
+    return (nxt > off) ? nxt : P.es_bytes;
+}
+
 __device__ __forceinline__ uint32_t stage_bytes(const DecodeParams& P, uint32_t f)
 {
-    uint64_t off = P.frame_off[f], nxt = P.frame_off[f + 1];
+    uint64_t off = P.frame_off[f];
     uint64_t a0 = off & ~(uint64_t)15;
-    uint64_t end = (nxt > off) ? nxt : P.es_bytes;
+    uint64_t end = frame_end(P, f, off);
     uint64_t n = ((end - a0) + 15) & ~(uint64_t)15;
     uint64_t cap = (uint64_t)P.fbuf_bytes - 16;
     return (uint32_t)(n < cap ? n : cap);
@@ -261,7 +271,7 @@ __device__ __forceinline__ float pow2neg(int k)   // 2^-k, k in [0, 126]
 // run by one thread of the group
 // ---------------------------------------------------------------------------
 __device__ int parse_frame_header(GroupCtl* c, const uint32_t* w, uint32_t base_bit,
-                                  const DecodeParams& P, uint32_t avail_bytes)
+                                  const DecodeParams& P, uint32_t avail_bytes, uint32_t cap_bytes)
 {
     BitReader br{w, base_bit, base_bit + avail_bytes * 8};
     uint32_t sync = br.get(16);
@@ -275,6 +285,9 @@ __device__ int parse_frame_header(GroupCtl* c, const uint32_t* w, uint32_t base_
     int kbps = c_bitrate[frmsizecod >> 1];
     int bytes = (fscod == 0) ? 4 * kbps : (fscod == 2) ? 6 * kbps
               : 2 * (320 * kbps / 147 + (int)(frmsizecod & 1));
+    // a frame longer than the staging buffer (a52_batch_set_max_frame_bytes told us less than the stream holds)
+    // cannot be decoded: refuse it instead of decoding a truncated copy
+    if ((uint32_t)bytes > cap_bytes) return 2;                 // A52_ST_BAD_FRAME
     if ((uint32_t)bytes > avail_bytes) bytes = avail_bytes;
     c->limit_bit = base_bit + bytes * 8;
     br.limit = c->limit_bit;
@@ -399,6 +412,8 @@ __device__ void compute_gains(GroupCtl* c)
         c->gain[ch] = g;
     }
     c->gain[5] = level;     // lfe: state->dynrng (parse.c:869-870)
+    for (int o = 0; o < 2; o++)
+        for (int ch = 0; ch < 5; ch++) c->wg2[o * 5 + ch] = c->wt[o][ch] * ((ch < c->nfchans) ? c->gain[ch] : 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -409,12 +424,43 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     BitReader br{w, c->bitpos, c->limit_bit};
     const int nfchans = c->nfchans;
     const int acmod = c->acmod;
+    const uint32_t chmask = (1u << nfchans) - 1;
+    uint32_t blksw, dith, do_alloc = 0;
 
+    // A block that keeps everything - coupling strategy and coordinates, rematrixing, every exponent set, the
+    // bit allocation parameters, no dynrng word, no skip field - is, after blksw / dithflag, a run of zero
+    // flag bits whose length follows from what is already known (parse.c:578-804 with every `if` not taken).
+    // One 64-bit window and one compare recognise it; anything else takes the field-by-field parse below.
+    bool fast = false;
+    if (c->loc_valid && !c->segs_dirty && c->bitpos + 96 <= c->limit_bit) {
+        const uint32_t p0 = c->bitpos, wi = p0 >> 5, sft = p0 & 31;
+        const uint32_t w0 = w[wi], w1 = w[wi + 1], w2 = w[wi + 2];
+        const uint32_t hi = __funnelshift_l(w1, w0, sft), lo = __funnelshift_l(w2, w1, sft);
+        const uint32_t nb = 2 * nfchans;
+        const uint32_t cpl = c->chincpl;
+        // dynrnge (x2 for 1+1) | cplstre | cplcoe per coupled channel | rematstr (2/0) | cplexpstr | chexpstr |
+        // lfeexpstr | baie | snroffste | cplleake | deltbaie | skiple
+        const uint32_t nz = (acmod ? 1u : 2u) + 1u + (cpl ? (uint32_t)__popc(cpl) + 3u : 0u) + (acmod == 2 ? 1u : 0u)
+                          + nb + c->lfeon + 4u;
+        const uint32_t rest = __funnelshift_l(lo, hi, nb);          // the bits after blksw / dithflag
+        if ((rest >> (32 - nz)) == 0) {
+            fast = true;
+            const uint32_t v = hi >> (32 - nb);
+            blksw = __brev(v >> nfchans) >> (32 - nfchans);
+            dith = __brev(v & chmask) >> (32 - nfchans);
+            c->blksw = blksw;
+            c->dithflag = dith;
+            reinterpret_cast<uint32_t*>(c->expstr)[0] = 0;           // expstr[0..3]
+            c->expstr[4] = 0; c->expstr[5] = 0; c->expstr[6] = 0;
+            c->zero_alloc = 0;
+            br.pos = p0 + nb + nz;
+        }
+    }
+    if (!fast) {
     uint32_t v = br.get(2 * nfchans);          // blksw[nfchans], dithflag[nfchans]
     // the fields are sent channel 0 first (msb): bit-reverse them so that bit i = channel i
-    const uint32_t chmask = (1u << nfchans) - 1;
-    const uint32_t blksw = __brev(v >> nfchans) >> (32 - nfchans);
-    const uint32_t dith = __brev(v & chmask) >> (32 - nfchans);
+    blksw = __brev(v >> nfchans) >> (32 - nfchans);
+    dith = __brev(v & chmask) >> (32 - nfchans);
     c->blksw = blksw;
     c->dithflag = dith;
 
@@ -500,7 +546,6 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         }
 
     // exponent fields: remember where they are, decode later in parallel
-    uint32_t do_alloc = 0;
     if (expstr[6]) {
         int ngrp = (c->cplendmant - c->cplstrtmant) / (3 << (expstr[6] - 1));
         do_alloc |= 64;
@@ -583,13 +628,15 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         }
         do_alloc = m;
     }
-    c->do_alloc = do_alloc;
 
     if (br.get(1)) {                           // skip field (parse.c:800-804)
         uint32_t n = br.get(9);
         br.skip(8 * n);
     }
+    }   // !fast
+    c->do_alloc = do_alloc;
     c->bitpos = br.pos;
+    const uint32_t chincpl = c->chincpl;
 
     if (c->gains_dirty) {
         compute_gains(c);
@@ -1237,6 +1284,175 @@ __device__ __noinline__ void imdct256_warp(const Tables& T, float* plane, int la
 }
 
 // ---------------------------------------------------------------------------
+// Stereo fast path: the two mixed planes travel as ONE plane of (L, R) pairs and every arithmetic
+// instruction of the transform and of the overlap-add is a packed fma/add/mul.f32x2 (sm_100a), so one warp
+// transforms both channels in the instruction count of one.  Same factorisation as imdct512_warp
+// (imdct.c:258-345); the radix-2 pass is folded into the post-twiddle.
+// ---------------------------------------------------------------------------
+struct C2 { float2 re, im; };            // one complex point of both channels: re = (re L, re R)
+
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, f2neg(b)); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ C2 lds_c2(uint32_t a)
+{
+    const float4 v = lds_f4(a);
+    return C2{make_float2(v.x, v.y), make_float2(v.z, v.w)};
+}
+__device__ __forceinline__ void sts_c2(uint32_t a, const C2& v) { sts_f4(a, make_float4(v.re.x, v.re.y, v.im.x, v.im.y)); }
+
+__device__ __forceinline__ C2 c2add(const C2& a, const C2& b) { return C2{f2add(a.re, b.re), f2add(a.im, b.im)}; }
+__device__ __forceinline__ C2 c2sub(const C2& a, const C2& b) { return C2{f2sub(a.re, b.re), f2sub(a.im, b.im)}; }
+// a * w, w = (wr, wr, wi, wi)
+__device__ __forceinline__ C2 c2mul_tw(const C2& a, const float4 w)
+{
+    const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+    return C2{f2fma(f2neg(a.im), wi, f2mul(a.re, wr)), f2fma(a.re, wi, f2mul(a.im, wr))};
+}
+__device__ __forceinline__ void bfly4_c2(C2& x0, C2& x1, C2& x2, C2& x3)
+{
+    const C2 t0 = c2add(x0, x2), t1 = c2sub(x0, x2), t2 = c2add(x1, x3), d = c2sub(x1, x3);
+    // t3 = d * (-j) = (d.im, -d.re)
+    x0 = c2add(t0, t2);
+    x2 = c2sub(t0, t2);
+    x1 = C2{f2add(t1.re, d.im), f2sub(t1.im, d.re)};
+    x3 = C2{f2sub(t1.re, d.im), f2add(t1.im, d.re)};
+}
+
+// x_sa: shared address (128-byte aligned) of 256 (L, R) coefficient pairs in mix2_pairs' order.  On exit the same 2 KB hold, as
+// float4 units, [i] = (U_L[2i], U_R[2i], U_L[2i+1], U_R[2i+1]) and [64 + i] = the same of V (i < 64), U / V
+// as imdct512_warp leaves them per plane.
+__device__ __forceinline__ void imdct512_pair(uint32_t tab_base, uint32_t x_sa, int lane)
+{
+    const uint32_t pre_t = tab_base + (uint32_t)offsetof(Tables, pre1d) + 16u * lane;
+    const uint32_t wf_t = tab_base + (uint32_t)offsetof(Tables, wfftd);
+    const uint4 A = lds_v4(tab_base + (uint32_t)offsetof(Tables, fftaddr) + 16u * lane);
+    const uint32_t e1 = x_sa + (A.x & 0xffffu), e2 = x_sa + (A.x >> 16), e3 = x_sa + (A.y & 0xffffu);
+    const uint32_t ep1 = x_sa + (A.y >> 16), ep2 = x_sa + (A.z & 0xffffu);
+    C2 x[4];
+    // pre-twiddle: lane owns m = lane + 32 q; a = X[2m], b = X[255 - 2m]
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        // X[k] sits at ((k >> 6) & 1) * 1024 + (k >> 7) * 512 + (k & 63) * 8 (see mix2_pairs)
+        const uint32_t qa = (q & 1) * 1024u + (q >> 1) * 512u, qb = ((3 - q) & 1) * 1024u + ((3 - q) >> 1) * 512u;
+        const float2 a = lds_f2(x_sa + 16u * lane + qa);
+        const float2 b = lds_f2(x_sa + 504u - 16u * lane + qb);
+        const float4 t = lds_f4(pre_t + 512u * q);
+        const float2 tx = make_float2(t.x, t.y), ty = make_float2(t.z, t.w);
+        x[q].re = f2fma(ty, b, f2mul(tx, a));
+        x[q].im = f2fma(f2neg(ty), a, f2mul(tx, b));
+    }
+    __syncwarp();
+    // pass 1: radix 4, stride 32, twiddle W128^(lane p)
+    bfly4_c2(x[0], x[1], x[2], x[3]);
+    sts_c2(e1, x[0]);
+    sts_c2((e1 ^ 0x20u) + 512u, c2mul_tw(x[1], lds_f4(wf_t + 16u * lane)));
+    sts_c2((e1 ^ 0x40u) + 1024u, c2mul_tw(x[2], lds_f4(wf_t + 32u * lane)));
+    sts_c2((e1 ^ 0x60u) + 1536u, c2mul_tw(x[3], lds_f4(wf_t + 16u * ((3u * lane) & 127u))));
+    __syncwarp();
+    // pass 2: 4 blocks of 32, stride 8, twiddle W128^(4 j p)
+    {
+        const uint32_t j = lane & 7;
+        const uint32_t i0 = e2, i1 = (e2 ^ 0x30u) + 128u, i2 = (e2 ^ 0x40u) + 256u, i3 = (e2 ^ 0x70u) + 384u;
+        C2 y0 = lds_c2(i0), y1 = lds_c2(i1), y2 = lds_c2(i2), y3 = lds_c2(i3);
+        bfly4_c2(y0, y1, y2, y3);
+        __syncwarp();
+        sts_c2(i0, y0);
+        sts_c2(i1, c2mul_tw(y1, lds_f4(wf_t + 64u * j)));
+        sts_c2(i2, c2mul_tw(y2, lds_f4(wf_t + 128u * j)));
+        sts_c2(i3, c2mul_tw(y3, lds_f4(wf_t + 192u * j)));
+    }
+    __syncwarp();
+    // pass 3: 16 blocks of 8, stride 2, twiddle W128^(16 j p)
+    {
+        const uint32_t j = lane & 1;
+        const uint32_t i0 = e3, i1 = e3 ^ 0x20u, i2 = e3 ^ 0x40u, i3 = e3 ^ 0x60u;
+        C2 y0 = lds_c2(i0), y1 = lds_c2(i1), y2 = lds_c2(i2), y3 = lds_c2(i3);
+        bfly4_c2(y0, y1, y2, y3);
+        __syncwarp();
+        sts_c2(i0, y0);
+        sts_c2(i1, c2mul_tw(y1, lds_f4(wf_t + 256u * j)));
+        sts_c2(i2, c2mul_tw(y2, lds_f4(wf_t + 512u * j)));
+        sts_c2(i3, c2mul_tw(y3, lds_f4(wf_t + 768u * j)));
+    }
+    __syncwarp();
+    // radix-2 pass + post-twiddle: B[i] = z[pos] + z[pos + 1] (i < 64), B[127 - i] = z[pos' - 1] - z[pos']
+    float4 uo[2], vo[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t a1 = ep1 ^ (0x40u * r), a2 = ep2 ^ (0x40u * (1 - r));
+        const C2 B1 = c2add(lds_c2(a1), lds_c2(a1 ^ 0x10u));
+        const C2 B2 = c2sub(lds_c2(a2), lds_c2(a2 ^ 0x10u));
+        const float4 p = lds_f4(tab_base + (uint32_t)offsetof(Tables, post1d) + 16u * lane + 512u * r);
+        const float2 px = make_float2(p.x, p.y), py = make_float2(p.z, p.w);
+        const float2 u0 = f2fma(py, B1.im, f2mul(px, B1.re));              // U[2i]   =  p.x B1.re + p.y B1.im
+        const float2 v0 = f2fma(f2neg(px), B1.im, f2mul(py, B1.re));       // V[2i]   =  p.y B1.re - p.x B1.im
+        const float2 u1 = f2neg(f2fma(px, B2.im, f2mul(py, B2.re)));       // U[2i+1] = -(p.y B2.re + p.x B2.im)
+        const float2 v1 = f2fma(f2neg(py), B2.im, f2mul(px, B2.re));       // V[2i+1] =  p.x B2.re - p.y B2.im
+        uo[r] = make_float4(u0.x, u0.y, u1.x, u1.y);
+        vo[r] = make_float4(v0.x, v0.y, v1.x, v1.y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        sts_f4(x_sa + 16u * lane + 512u * r, uo[r]);
+        sts_f4(x_sa + 1024u + 16u * lane + 512u * r, vo[r]);
+    }
+    __syncwarp();
+}
+
+// Coefficient-domain downmix to two outputs, written as (L, R) pairs over planes 0 and 1: thread t owns bins
+// 4t .. 4t+3.  Warp w reads the w-th halves of the five planes and writes only into the w-th halves of planes 0
+// and 1 (pair k at ((k >> 6) & 1) * 1024 + (k >> 7) * 512 + (k & 63) * 8), so a __syncwarp between its loads and
+// its stores is all the ordering the in-place mix needs.
+__device__ __forceinline__ void mix2_pairs(const float* plane, uint32_t x_sa, const GroupCtl* c, int t)
+{
+    const float4* p4 = reinterpret_cast<const float4*>(plane);
+    float4 in[5];
+#pragma unroll
+    for (int ch = 0; ch < 5; ch++) in[ch] = p4[ch * 64 + t];          // planes past nfchans are zero
+    const float4* wq = reinterpret_cast<const float4*>(c->wg2);
+    const float4 w0 = wq[0], w1 = wq[1], w2 = wq[2];
+    const float wl[5] = {w0.x, w0.y, w0.z, w0.w, w1.x}, wr[5] = {w1.y, w1.z, w1.w, w2.x, w2.y};
+    float L[4], R[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float v0 = j == 0 ? in[0].x : j == 1 ? in[0].y : j == 2 ? in[0].z : in[0].w;
+        L[j] = wl[0] * v0;
+        R[j] = wr[0] * v0;
+#pragma unroll
+        for (int ch = 1; ch < 5; ch++) {
+            const float v = j == 0 ? in[ch].x : j == 1 ? in[ch].y : j == 2 ? in[ch].z : in[ch].w;
+            L[j] = fmaf(wl[ch], v, L[j]);
+            R[j] = fmaf(wr[ch], v, R[j]);
+        }
+    }
+    __syncwarp();
+    const uint32_t o = x_sa + ((t >> 4) & 1) * 1024u + (t >> 5) * 512u + (t & 15) * 32u;
+    sts_f4(o, make_float4(L[0], R[0], L[1], R[1]));
+    sts_f4(o + 16u, make_float4(L[2], R[2], L[3], R[3]));
+}
+
+// ---------------------------------------------------------------------------
 // the kernel: one warp per stream
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const WarpPtrs& G, uint32_t f)
@@ -1248,7 +1464,7 @@ __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const Wa
     tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
 }
 
-static_assert(sizeof(GroupCtl) <= 1200, "GroupCtl grew: check the shared-memory budget per stream");
+static_assert(sizeof(GroupCtl) <= 1248, "GroupCtl grew: check the shared-memory budget per stream");
 
 // ===========================================================================
 // The decode kernel: TWO warps (64 threads, a "pair") walk one stream.  The two warps split every
@@ -1260,18 +1476,20 @@ struct PairPtrs : WarpPtrs {
     uint32_t* xch;     // [2][8] scan totals of the two warps
 };
 
-__host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
+template <int NPL>
+__device__ __forceinline__ PairPtrs carve_pair(uint8_t* base)
 {
-    return warp_smem_bytes(fbuf_bytes, nplanes) + nplanes * 128 * 4 + 64;
-}
-
-__device__ inline PairPtrs carve_pair(uint8_t* base, int fbuf_bytes, int nplanes)
-{
+    using Lay = PairLayout<NPL>;
     PairPtrs g;
-    static_cast<WarpPtrs&>(g) = carve(base, fbuf_bytes, nplanes);
-    uint8_t* p = reinterpret_cast<uint8_t*>(g.mbar) + 16;
-    g.delay = reinterpret_cast<float*>(p);   p += nplanes * 128 * 4;
-    g.xch = reinterpret_cast<uint32_t*>(p);
+    g.list = reinterpret_cast<uint16_t*>(base + Lay::list);
+    g.plane = reinterpret_cast<float*>(base + Lay::plane);
+    g.delay = reinterpret_cast<float*>(base + Lay::delay);
+    g.ctl = reinterpret_cast<GroupCtl*>(base + Lay::ctl);
+    g.exp = base + Lay::exp;
+    g.bap = base + Lay::bap;
+    g.xch = reinterpret_cast<uint32_t*>(base + Lay::xch);
+    g.mbar = reinterpret_cast<uint64_t*>(base + Lay::mbar);
+    g.fbuf = reinterpret_cast<uint32_t*>(base + Lay::fbuf);
     return g;
 }
 
@@ -1447,6 +1665,7 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
 
 constexpr int kMaxPairsPerCta = 12;
 
+template <int NPL>
 __global__ void __launch_bounds__(kMaxPairsPerCta * 64, 1)
 a52_decode_kernel(const DecodeParams P)
 {
@@ -1460,7 +1679,7 @@ a52_decode_kernel(const DecodeParams P)
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
         for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    PairPtrs G = carve_pair(smem + align16((int)sizeof(Tables)) + pair * P.warp_bytes, P.fbuf_bytes, P.nplanes);
+    const PairPtrs G = carve_pair<NPL>(smem + align128((int)sizeof(Tables)) + pair * P.warp_bytes);
     GroupCtl* c = G.ctl;
     uint32_t* const W = G.fbuf;
     uint32_t* const planeU = reinterpret_cast<uint32_t*>(G.plane);
@@ -1477,9 +1696,9 @@ a52_decode_kernel(const DecodeParams P)
     asm volatile("mov.u32 %0, %1;" : "=r"(list_sa) : "r"(smem_u32(G.list)));
     asm volatile("mov.u32 %0, %1;" : "=r"(plane_sa) : "r"(smem_u32(G.plane)));
     uint32_t phase = 0;
-    const int ndelay = P.nplanes;            // tails: planes 0..4 main, 5 LFE
+    constexpr int ndelay = NPL;              // tails: planes 0..4 main, 5 LFE
     // this pair's scratch in global memory: the image of the planes after a full locate pass
-    uint4* const snap = P.snap + (size_t)(blockIdx.x * (blockDim.x >> 6) + pair) * (P.nplanes * 64);
+    uint4* const snap = P.snap + (size_t)(blockIdx.x * (blockDim.x >> 6) + pair) * (NPL * 64);
 
     // Work units are SLICES of streams (P.slice_frames frames), handed out slice-major from one ticket
     // counter: all first slices, then all second slices, ...  A slice starts from the carry record its
@@ -1497,7 +1716,7 @@ a52_decode_kernel(const DecodeParams P)
         const uint32_t fs0 = P.stream_first[s], fs1 = P.stream_first[s + 1];
         uint32_t f0 = fs0 + slice * (uint32_t)P.slice_frames;
         if (f0 > fs1) f0 = fs1;
-        const uint32_t f1 = (P.nslices > 1 && fs1 - f0 > (uint32_t)P.slice_frames) ? f0 + P.slice_frames : fs1;
+        const uint32_t f1 = (slice + 1 < (uint32_t)P.nslices && fs1 - f0 > (uint32_t)P.slice_frames) ? f0 + P.slice_frames : fs1;
         if (slice > 0) {
             if (gt == 0) {
                 volatile int* done = P.slice_done + s;
@@ -1513,7 +1732,11 @@ a52_decode_kernel(const DecodeParams P)
             if (gt == 0) c->per_channel = (__ldcg(&P.carry[s].per_channel) != 0);
             for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = __ldcg(&P.carry[s].delay[i >> 7][i & 127]);
         } else {
-            if (gt == 0) c->per_channel = 0;
+            // a fresh stream: liba52 starts from a52_init's state; so do the parse state (exponents, baps, coupling
+            // and allocation parameters a damaged first frame might "reuse") and the tails
+            // (not the first four words: the ticket other threads of the pair may still be reading)
+            for (int i = 4 + gt; i < (int)(sizeof(GroupCtl) / 4); i += NT) reinterpret_cast<uint32_t*>(c)[i] = 0;
+            for (int i = gt; i < 7 * 256 * 2 / 4; i += NT) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
             for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = 0.f;
         }
         if (gt == 0 && f0 < f1) issue_frame_load(P, G, f0);
@@ -1528,14 +1751,14 @@ a52_decode_kernel(const DecodeParams P)
             sync();
             if (gt == 0) {
                 uint32_t base_bit = (uint32_t)(off & 15) * 8;
-                uint32_t avail = P.fbuf_bytes - 16 - (uint32_t)(off & 15);
+                const uint32_t cap = P.fbuf_bytes - 16 - (uint32_t)(off & 15);     // what the staging buffer holds
+                uint32_t avail = cap;
                 {
-                    uint64_t nxt = P.frame_off[f + 1];
-                    uint64_t end = (nxt > off) ? nxt : P.es_bytes;
+                    const uint64_t end = frame_end(P, f, off);
                     if (end - off < avail) avail = (uint32_t)(end - off);
                 }
                 c->base_bit = base_bit;
-                int st = parse_frame_header(c, W, base_bit, P, avail);
+                int st = parse_frame_header(c, W, base_bit, P, avail, cap);
                 c->frame_ok = (st == 0);
                 c->err = st;
                 if (P.frame_flags) P.frame_flags[f] = st ? 0 : c->output;
@@ -1562,7 +1785,7 @@ a52_decode_kernel(const DecodeParams P)
             bool pend = false;
             int p_blk = 0;
             uint32_t p_live = 0, p_blksw = 0;
-            bool p_uniform = false;
+            bool p_uniform = false, p_fast = false;
             if (frame_ok)
             for (;; blk++) {
                 const bool more = blk < 6;
@@ -1573,7 +1796,13 @@ a52_decode_kernel(const DecodeParams P)
                 // ================= P (block blk) | T (block blk - 1) =================
                 if (more && gt == 0) c->err = parse_block(c, W, P);
                 __syncwarp();
-                if (pend) {
+                if (pend && p_fast) {
+                    // both mixed planes in one packed transform; whichever warp gets here first takes it
+                    int j = 0;
+                    if (lane == 0) j = atomicAdd(&c->tr_ticket, 1);
+                    j = __shfl_sync(0xffffffffu, j, 0);
+                    if (j == 0) imdct512_pair(tab_base, plane_sa, lane);
+                } else if (pend) {
                     const int njobs = __popc(p_live);
                     for (;;) {
                         int j = 0;
@@ -1593,7 +1822,39 @@ a52_decode_kernel(const DecodeParams P)
                 if (pend) {
                     const int nmain = c->nout, lfe_on = c->out_lfe, nfch = c->nfchans;
                     // thread q = gt owns positions p = 2q, 2q+1 (and their mirrors 254-p, 255-p) of every plane
-                    if (p_uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt != 0) {
+                    if (p_fast) {
+                        // stereo fast path: (L, R) pairs all the way, packed arithmetic
+                        const int q = gt;
+                        const float4 Uq = lds_f4(plane_sa + 16u * q), Vq = lds_f4(plane_sa + 1024u + 16u * q);
+                        float2* delay2 = reinterpret_cast<float2*>(G.delay);
+                        const float2 DL = delay2[q], DR = delay2[64 + q];
+                        const float4 WL = lds_f4(tab_base + (uint32_t)offsetof(Tables, win2d) + 16u * q);
+                        const float4 WH = lds_f4(tab_base + (uint32_t)offsetof(Tables, win2d) + 16u * (127 - q));
+                        const float2 U0 = make_float2(Uq.x, Uq.y), U1 = make_float2(Uq.z, Uq.w);
+                        const float2 D0 = make_float2(DL.x, DR.x), D1 = make_float2(DL.y, DR.y);
+                        const float2 wlx = make_float2(WL.x, WL.y), wly = make_float2(WL.z, WL.w);
+                        const float2 whx = make_float2(WH.x, WH.y), why = make_float2(WH.z, WH.w);
+                        const float2 bias2 = make_float2(P.bias, P.bias);
+                        const float2 y0 = f2fma(f2neg(U0), wlx, f2mul(D0, why));      // sample p
+                        const float2 y1 = f2fma(f2neg(U1), wly, f2mul(D1, whx));      // sample p + 1
+                        const float2 y3 = f2fma(U0, why, f2mul(D0, wlx));             // sample 255 - p
+                        const float2 y2 = f2fma(U1, whx, f2mul(D1, wly));             // sample 254 - p
+                        delay2[q] = make_float2(Vq.x, Vq.z);
+                        delay2[64 + q] = make_float2(Vq.y, Vq.w);
+                        if (P.out_fmt == 1) {
+                            const float2 a0 = f2add(y0, bias2), a1 = f2add(y1, bias2), a2 = f2add(y2, bias2), a3 = f2add(y3, bias2);
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_frame) + (size_t)p_blk * 512);
+                            dst[q] = make_float4(a0.x, a0.y, a1.x, a1.y);
+                            dst[127 - q] = make_float4(a2.x, a2.y, a3.x, a3.y);
+                        } else {
+                            auto two = [](float2 v) {
+                                return (uint32_t)(uint16_t)s16_of(v.x, true) | ((uint32_t)(uint16_t)s16_of(v.y, true) << 16);
+                            };
+                            uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<int16_t*>(out_frame) + (size_t)p_blk * 512);
+                            dst[q] = make_uint2(two(y0), two(y1));
+                            dst[127 - q] = make_uint2(two(y2), two(y3));
+                        }
+                    } else if (p_uniform && !c->per_channel && nmain == 2 && !lfe_on && P.out_fmt != 0) {
                         // the common request: two mixed planes, tails already downmixed, interleaved float or
                         // int16 out (two channels: libao's WAV order is liba52's)
                         const float bias = P.bias;
@@ -1683,11 +1944,11 @@ a52_decode_kernel(const DecodeParams P)
                 uint32_t ta, tb, tz, mant_bits, pos_delta = 0;
                 uint4* const plane4 = reinterpret_cast<uint4*>(G.plane);
                 if (rep) {
-                    for (int i = gt; i < P.nplanes * 64; i += NT) plane4[i] = __ldcg(snap + i);
+                    for (int i = gt; i < NPL * 64; i += NT) plane4[i] = __ldcg(snap + i);
                     ta = c->loc_ta; tb = c->loc_tb; tz = c->loc_tz; mant_bits = c->loc_mant;
                     pos_delta = bitpos - c->loc_bitpos;
                 } else {
-                    for (int i = gt; i < P.nplanes * 256 / 4; i += NT)
+                    for (int i = gt; i < NPL * 256 / 4; i += NT)
                         reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
                     const uint32_t K = c->plan_K;
                     const uint32_t cpl_dith = chincpl & c->dithflag;
@@ -1824,7 +2085,7 @@ a52_decode_kernel(const DecodeParams P)
                         }
                     }
                     sync();
-                    for (int i = gt; i < P.nplanes * 64; i += NT) __stcg(snap + i, plane4[i]);
+                    for (int i = gt; i < NPL * 64; i += NT) __stcg(snap + i, plane4[i]);
                     if (gt == 0) {
                         c->loc_ta = ta; c->loc_tb = tb; c->loc_tz = tz; c->loc_mant = mant_bits;
                         c->loc_bitpos = bitpos;
@@ -1940,7 +2201,11 @@ a52_decode_kernel(const DecodeParams P)
                 const int nmain = c->nout;
                 const bool uniform = c->uniform_path;
                 const int lfe_on = c->out_lfe;
-                if (uniform) {
+                const bool fast2 = uniform && nmain == 2 && !lfe_on && c->blksw == 0 && !c->per_channel &&
+                                   P.out_fmt != 0;      // (two channels: libao's WAV order is liba52's)
+                if (fast2) {
+                    mix2_pairs(G.plane, plane_sa, c, gt);
+                } else if (uniform) {
                     switch (nmain) {
                     case 1: mix_planes<1, NT>(G.plane, c, gt); break;
                     case 2: mix_planes<2, NT>(G.plane, c, gt); break;
@@ -1961,6 +2226,7 @@ a52_decode_kernel(const DecodeParams P)
                     p_live = live;
                     p_blksw = c->blksw;
                     p_uniform = uniform;
+                    p_fast = fast2;
                     p_blk = blk;
                     pend = true;
                 }
@@ -1974,6 +2240,13 @@ a52_decode_kernel(const DecodeParams P)
                 size_t from = (size_t)blk * 256 * nout * ssz;
                 size_t to = (size_t)6 * 256 * nout * ssz;
                 for (size_t i = from + gt * 4; i < to; i += NT * 4)
+                    *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
+            }
+            if (frame_ok && !(P.req_flags & 0x100)) {
+                // a frame granted fewer channels than the request's stride holds: the rest of its slot is silence
+                const int ssz = (P.out_fmt >= 2) ? 2 : 4;
+                const size_t used = (size_t)1536 * (c->nout + c->out_lfe) * ssz;
+                for (size_t i = used + gt * 4; i < P.frame_stride; i += NT * 4)
                     *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
             }
             if (gt == 0 && P.status) P.status[f] = frame_status;

@@ -204,6 +204,34 @@ static void build_tables(Tables* T)
     }
     for (int i = 0; i < 32; i++)
         T->post2[i] = make_float2((float)cos((M_PI / 128) * (i + 0.5)), (float)sin((M_PI / 128) * (i + 0.5)));
+    // operands of the packed two-channel transform: every factor twice
+    for (int m = 0; m < 128; m++) {
+        T->pre1d[m] = make_float4(T->pre1[m].x, T->pre1[m].x, T->pre1[m].y, T->pre1[m].y);
+        T->wfftd[m] = make_float4(T->wfft[m].x, T->wfft[m].x, T->wfft[m].y, T->wfft[m].y);
+        T->win2d[m] = make_float4(T->window[2 * m], T->window[2 * m], T->window[2 * m + 1], T->window[2 * m + 1]);
+    }
+    for (int i = 0; i < 64; i++) T->post1d[i] = make_float4(T->post1[i].x, T->post1[i].x, T->post1[i].y, T->post1[i].y);
+    // Scratch addressing of the paired transform.  A point is 16 bytes (re L, re R, im L, im R); point i lives at
+    // sw(i) = i ^ 3 b3 ^ 4 b4 ^ 2 b5 ^ 4 b6 (b_k = bit k of i), which keeps every access pattern of the
+    // radix-4 passes and of the post-twiddle on eight different 16-byte bank groups per quarter warp.  All
+    // addresses of a lane are one of five lane constants XOR / plus compile-time constants.
+    {
+        auto sw = [](int i) { return i ^ (((i >> 3) & 1) * 3) ^ (((i >> 4) & 1) * 4) ^ (((i >> 5) & 1) * 2) ^ (((i >> 6) & 1) * 4); };
+        for (int l = 0; l < 32; l++) {
+            const int e1 = sw(l);                                         // pass 1 stores: (e1 ^ {0,2,4,6}) + 32 p
+            const int b2 = l >> 3, j2 = l & 7;
+            const int e2 = (b2 * 32 + j2) ^ ((b2 & 1) * 2) ^ ((b2 >> 1) * 4);   // pass 2: (e2 ^ {0,3,4,7}) + 8 k
+            const int b3 = l >> 1, j3 = l & 1;
+            const int s3 = ((b3 & 1) * 3) ^ (((b3 >> 1) & 1) * 4) ^ (((b3 >> 2) & 1) * 2) ^ (((b3 >> 3) & 1) * 4);
+            const int e3 = 8 * b3 + (j3 ^ s3);                            // pass 3: e3 ^ 2 k
+            const int p0 = 32 * (l & 3) + 8 * ((l >> 2) & 3) + 2 * (l >> 4);
+            const int nl = (~l) & 31;
+            const int p0b = 32 * (nl & 3) + 8 * ((nl >> 2) & 3) + 2 * ((nl >> 4) & 1);
+            T->fftaddr[l] = make_uint4((uint32_t)(e1 * 16) | ((uint32_t)(e2 * 16) << 16),
+                                       (uint32_t)(e3 * 16) | ((uint32_t)(sw(p0) * 16) << 16),
+                                       (uint32_t)(sw(p0b) * 16), 0u);
+        }
+    }
     for (int c = 0; c < 32; c++)
         for (int d = 0; d < 3; d++) {
             int dig[3] = {c / 9, (c / 3) % 3, c % 3};
@@ -432,7 +460,9 @@ a52_batch_t* a52_batch_create(int device)
     ok = ok && cudaMalloc(&ctx->d_dither, seq.size() * 2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(a52::a52_decode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024) == cudaSuccess;
     if (!ok) {
         a52_batch_destroy(ctx);
@@ -583,10 +613,10 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.nplanes = (P.req_flags & M_LFE) ? 6 : 5;
     const bool pair = ctx->pair_kernel != 0;
     P.group_threads = pair ? 64 : 32;
-    P.warp_bytes = pair ? pair_smem_bytes(P.fbuf_bytes, P.nplanes) : warp_smem_bytes(P.fbuf_bytes, P.nplanes);
+    P.warp_bytes = pair_smem_bytes(P.fbuf_bytes, P.nplanes);
     P.dither_seq = ctx->d_dither;
     P.work_counter = ctx->d_counter + counter_slot;
-    const int tables = align16((int)sizeof(Tables));
+    const int tables = align128((int)sizeof(Tables));
     int fit = (227 * 1024 - tables) / P.warp_bytes;
     const int fit_max = kMaxPairsPerCta;
     if (fit > fit_max) fit = fit_max;
@@ -632,7 +662,8 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used], e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
     A52_CUDA(cudaEventRecord(e0, st));
-    a52_decode_kernel<<<grid, threads, smem, st>>>(P);
+    if (P.nplanes == 6) a52_decode_kernel<6><<<grid, threads, smem, st>>>(P);
+    else a52_decode_kernel<5><<<grid, threads, smem, st>>>(P);
     A52_CUDA(cudaEventRecord(e1, st));
     A52_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -662,6 +693,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
     memset(&P, 0, sizeof(P));
     P.es_bytes = es_bytes;
     P.nstreams = nstreams;
+    P.nframes = nframes;
     P.req_flags = req_flags;
     P.bias = bias;
     P.drc_off = (drc_mode == A52_DRC_OFF);

@@ -6,9 +6,11 @@
 
 Workload (BASELINE.json configs[1]): 4096 independent 10 s streams (313 frames each) of
 5.1 / 48 kHz / 448 kb/s AC-3 per GPU, full path (exponents, bit allocation, dequantisation,
-IMDCT-512, stereo downmix), float32 stereo PCM out.  The bitstreams are the committed
-reference-encoded fixture (tests/golden/c2_fixture.npz: 4 unique streams x 64 frames of synthetic
-multitone + noise) tiled to the batch shape with per-stream frame rotation.
+IMDCT-512, stereo downmix), float32 stereo PCM out.  The corpus is SURVEY.md section 8(d)'s: 256 UNIQUE
+streams (tests/corpus.py: 3 sines + white noise per channel, LCG-seeded, integer arithmetic so that any host
+and the GPU synthesise the same samples), encoded at 448 kb/s - by this repo's encoder on the GPU in the
+CUDA arm, by the unmodified reference encoder in the CPU arms; both must reproduce the committed digest
+tests/golden/c2_corpus.json - and tiled x16 with a rotation of 7 frames per copy.
 A "step" is one pass of the decode over the whole batch.  One line of JSON is printed by rank 0.
 
   value      : audio-s/s, bitstream already resident in HBM, PCM left in HBM (CUDA events, max over ranks)
@@ -18,6 +20,9 @@ A "step" is one pass of the decode over the whole batch.  One line of JSON is pr
                written per frame) / mean kernel time measured live with CUDA events
   cpu_baseline: the unmodified reference (oracle/_ref, liba52 compiled from /root/reference) or the
                oracle port, one process per host core, on a bounded sample of the same workload
+  extra      : supplementary figures measured the same way (device resident), each with its own roofline
+               fraction: int16 output, the config-3 corpus (5.1 @ 640 kb/s with block switching, coupling,
+               dynrng, delta bit allocation: tests/golden/c3_fixture.npz) to stereo and to 5.1, config 4 (encode)
 """
 import argparse
 import json
@@ -45,13 +50,77 @@ ENC_ALGO_BYTES_PER_FRAME = 1536 * 6 * 2 + 1792      # int16 5.1 PCM in + frame o
 UNIT = "audio-s/s"
 
 
-def build_corpus(nstreams, nframes):
-    """[nstreams, nframes, 1792] uint8: fixture streams tiled, stream s starts at frame 7*s of base s%4."""
-    fx = np.load(os.path.join(ROOT, "tests", "golden", "c2_fixture.npz"))["frames"]
-    nb, nf = fx.shape[0], fx.shape[1]
-    idx = (np.arange(nframes)[None, :] + 7 * np.arange(nstreams)[:, None]) % nf
-    base = np.arange(nstreams) % nb
-    return fx[base[:, None], idx]
+CACHE = os.environ.get("A52_BENCH_CACHE", "/tmp/a52_bench_c2_corpus.npy")
+
+
+def _corpus_mod():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import corpus
+    return corpus
+
+
+def _cached_frames():
+    """uint8 [256][313][1792] from the cache file when it reproduces the committed digest, else None."""
+    corpus = _corpus_mod()
+    try:
+        fr = np.load(CACHE)
+        if fr.shape == (corpus.UNIQUE, corpus.FRAMES, FRAME_BYTES) and corpus.digest_of(fr) == corpus.load_digest()["sha256"]:
+            return fr
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def _store_cache(fr):
+    try:
+        tmp = CACHE + ".%d.tmp.npy" % os.getpid()
+        np.save(tmp, fr)
+        os.replace(tmp, CACHE)
+    except OSError:
+        pass
+
+
+def unique_frames_cpu():
+    """The 256 unique encoded streams, made on the host cores by the reference encoder (CPU arms)."""
+    corpus = _corpus_mod()
+    fr = _cached_frames()
+    if fr is None:
+        fr = corpus.encode_cpu(range(corpus.UNIQUE))
+        assert corpus.digest_of(fr) == corpus.load_digest()["sha256"], "CPU-built corpus differs from the committed digest"
+        _store_cache(fr)
+    return fr
+
+
+def unique_frames_gpu(eng, dev):
+    """The same 256 streams made on the GPU: torch integer synthesis + this repo's batched encoder."""
+    import torch
+    corpus = _corpus_mod()
+    fr = _cached_frames()
+    if fr is not None:
+        return torch.from_numpy(fr).to(dev)
+    pcm = corpus.synth_torch(range(corpus.UNIQUE), dev)                        # int16 [256][313*1536][6]
+    out = torch.zeros((corpus.UNIQUE, corpus.FRAMES, FRAME_BYTES), dtype=torch.uint8, device=dev)
+    status = torch.zeros((corpus.UNIQUE, corpus.FRAMES), dtype=torch.int32, device=dev)
+    enc = eng.BatchEncoder(dev.index or 0)
+    enc.encode_device(pcm.data_ptr(), corpus.UNIQUE, corpus.FRAMES, 48000, 448000, 6, out.data_ptr(),
+                      status_ptr=status.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    enc.close()
+    assert int((status != 0).sum().item()) == 0
+    host = out.cpu().numpy()
+    assert corpus.digest_of(host) == corpus.load_digest()["sha256"], "GPU-built corpus differs from the committed digest"
+    _store_cache(host)
+    return out
+
+
+def tile_corpus(frames, nstreams, nframes):
+    """[nstreams][nframes][1792]: stream s = unique stream s % 256 starting 7 * (s // 256) frames in (numpy or torch)."""
+    corpus = _corpus_mod()
+    base, idx = corpus.tile_index(nstreams, nframes)
+    if isinstance(frames, np.ndarray):
+        return frames[base[:, None], idx]
+    import torch
+    return frames[torch.from_numpy(base).to(frames.device)[:, None], torch.from_numpy(idx).to(frames.device)]
 
 
 # ---------------------------------------------------------------------------
@@ -64,8 +133,8 @@ def _cpu_init(kind):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refbind
     _cpu["lib"] = refbind.RefA52() if kind == "reference" else refbind.Oracle()
-    _cpu["es"] = build_corpus(4, 313).reshape(4, -1)
     _cpu["out"] = np.zeros((313 * 6 + 8, 2, 256), np.float32)
+    _cpu["first"] = (os.getpid() * 37) % _cpu["es"].shape[0]          # workers start at different streams
 
 
 def _cpu_work(nstreams):
@@ -75,8 +144,9 @@ def _cpu_work(nstreams):
     t0 = time.perf_counter()
     frames = 0
     out = _cpu["out"]
+    nu = _cpu["es"].shape[0]
     for s in range(nstreams):
-        es = _cpu["es"][s % 4]
+        es = _cpu["es"][(_cpu["first"] + s) % nu]
         nf = fn(None, es.ctypes.data_as(C.POINTER(C.c_uint8)), len(es), REQ_FLAGS, 1.0, 0.0,
                 out.ctypes.data_as(C.POINTER(C.c_float)), 2, 0)
         assert nf == 313, nf
@@ -130,6 +200,7 @@ class CpuArm:
         self.work = _cpu_work
 
     def _init_decode(self):
+        _cpu["es"] = unique_frames_cpu().reshape(256, -1)           # inherited by the forked workers
         self.pool = self.mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
         self.pool.map(_cpu_work, [1] * self.cores)               # warm: page in, tables
 
@@ -155,6 +226,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # the workers (forked, one per core) dlopen the reference themselves; load it here too, so that what this
+    # arm runs is visible in the parent's maps as well
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refbind
+    _keep = (refbind.RefA52(), refbind.RefAc3Enc()) if refbind.have_ref() else (refbind.Oracle(),)
     arm = CpuArm(args.workload)
     k = arm.calibrate(2.0)                                   # ~2 s of CPU work per core per step
     for _ in range(args.warmup):
@@ -282,12 +358,11 @@ def run_gpu(args):
 
     S, F = args.streams, args.frames
     nframes = S * F
-    corpus = build_corpus(S, F)                                # weak scaling: every rank decodes S streams
-    es_host = torch.from_numpy(corpus.reshape(-1))
-    es_bytes = es_host.numel()
     dev = torch.device("cuda", local)
+    uniq = unique_frames_gpu(eng, dev)                         # [256][313][1792] on the device, digest-checked
+    es_bytes = nframes * FRAME_BYTES
     es = torch.zeros(es_bytes + 64, dtype=torch.uint8, device=dev)
-    es[:es_bytes].copy_(es_host)
+    es[:es_bytes].copy_(tile_corpus(uniq, S, F).reshape(-1))   # weak scaling: every rank decodes S streams
     off = torch.arange(nframes + 1, dtype=torch.int64, device=dev) * FRAME_BYTES
     first = (torch.arange(S + 1, dtype=torch.int64, device=dev) * F).to(torch.int32)
     s16 = args.pcm == "s16"
@@ -335,18 +410,22 @@ def run_gpu(args):
     audio_s_per_step = nframes * FRAME_SECONDS * world
     value = audio_s_per_step * args.steps / (ms / 1e3)
 
-    # checksum of the device result against the fixture digest (cheap sanity: sum of squares of stream 0)
-    fx = np.load(os.path.join(ROOT, "tests", "golden", "c2_fixture.npz"))
-    if F >= 64:
-        got = float(((pcm[: 64 * 3072].double() / (32768.0 if s16 else 1.0)) ** 2).sum().item())
-        want = float(fx["digest"][0][1])
-        # int16 rounding adds about 2^-32 / 12 per sample on top of the float tolerance
-        assert abs(got - want) / want < (1e-3 if s16 else 1e-5), ("stream 0 energy differs from the reference digest", got, want)
+    # sanity of the device result against the committed digest: energy of the first four unique streams as the
+    # UNMODIFIED reference decoder produced them (tests/golden/c2_corpus.json)
+    if F == 313 and S >= 4:
+        want = _corpus_mod().load_digest()["energy_stereo_first4"]
+        for k in range(4):
+            got = float(((pcm[k * F * 3072:(k + 1) * F * 3072].double() / (32768.0 if s16 else 1.0)) ** 2).sum().item())
+            assert abs(got - want[k]) / want[k] < (1e-3 if s16 else 1e-5), ("stream energy differs from the reference digest", k, got, want[k])
+
+    extra = None
+    if not args.no_extra and not s16:
+        extra = run_extras(args, eng, dec, es, es_bytes, off, first, status, shard, barrier, world, dev)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, eng, dec, corpus, shard, barrier, world)
+        e2e = run_e2e(args, eng, dec, es[:es_bytes], shard, barrier, world)
 
     if sampler:
         sampler.stop()
@@ -376,6 +455,7 @@ def run_gpu(args):
                          "kernel": "a52_decode_kernel", "kernel_ms": kms, "kernel_launches_timed": kn,
                          "algorithmic_bytes_per_launch": nframes * algo},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "extra": extra,
         }
         print(json.dumps(line))
     dec.close()
@@ -509,6 +589,101 @@ def run_gpu_encode(args):
     return 0
 
 
+def _timed(step, steps, warmup, barrier, shard):
+    import torch
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    return shard.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+def run_extras(args, eng, dec, es, es_bytes, off, first, status, shard, barrier, world, dev):
+    """Supplementary figures, device resident, same timing discipline (CUDA events, max over ranks, inputs and
+    outputs larger than L2), each against the HBM roofline with its own algorithmic bytes."""
+    import torch
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except (OSError, ValueError, KeyError):
+        pass
+    S, F = args.streams, args.frames
+    nframes = S * F
+    stream = torch.cuda.current_stream().cuda_stream
+    n, w = args.extra_steps, 2
+    out = {}
+
+    def fig(ms, frames, algo_bytes, note):
+        return {"value": frames * FRAME_SECONDS * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+                "roofline_frac": frames * algo_bytes / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_frame": algo_bytes,
+                "workload": note}
+
+    # (1) the headline corpus with int16 stereo out (what a52dec -o wav and the ACM wrapper deliver)
+    pcm16 = torch.empty(nframes * 1536 * 2, dtype=torch.int16, device=dev)
+    ms = _timed(lambda: dec.decode_device(es.data_ptr(), es_bytes, off.data_ptr(), nframes, first.data_ptr(), S, REQ_FLAGS,
+                                          pcm16.data_ptr(), status_ptr=status.data_ptr(), out_fmt=eng.PCM_S16_INTERLEAVED,
+                                          stream=stream), n, w, barrier, shard)
+    assert int((status != 0).sum().item()) == 0
+    out["pcm_s16"] = fig(ms, nframes, FRAME_BYTES + PCM_BYTES // 2, "configs[1] corpus, int16 stereo interleaved out")
+    del pcm16
+
+    # (2) config 3: 5.1 @ 640 kb/s, block switching / coupling / dynrng / delta bit allocation in most blocks
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "c3_fixture.npz"))
+    c3 = torch.from_numpy(fx["frames"]).to(dev)                                  # [8][32][2560]
+    nu, nf3, fb3 = c3.shape
+    S3 = S
+    F3 = 96                                                                      # 3.07 s per stream: 3 passes over a unique stream
+    base = torch.arange(S3, device=dev) % nu
+    idx = (torch.arange(F3, device=dev)[None, :] + 5 * (torch.arange(S3, device=dev) // nu)[:, None]) % nf3
+    n3 = S3 * F3
+    es3 = torch.zeros(n3 * fb3 + 64, dtype=torch.uint8, device=dev)
+    es3[:n3 * fb3].copy_(c3[base[:, None], idx].reshape(-1))
+    off3 = torch.arange(n3 + 1, dtype=torch.int64, device=dev) * fb3
+    first3 = (torch.arange(S3 + 1, dtype=torch.int64, device=dev) * F3).to(torch.int32)
+    st3 = torch.zeros(n3, dtype=torch.int32, device=dev)
+    dec.set_max_frame_bytes(fb3)
+    dec.set_max_stream_frames(F3)
+    for key, flags, nout, ekey in (("config3_stereo", REQ_FLAGS, 2, "energy_stereo"), ("config3_51", 7 | 16, 6, "energy_51")):
+        pcm3 = torch.empty(n3 * 1536 * nout, dtype=torch.float32, device=dev)
+        ms = _timed(lambda: dec.decode_device(es3.data_ptr(), n3 * fb3, off3.data_ptr(), n3, first3.data_ptr(), S3, flags,
+                                              pcm3.data_ptr(), status_ptr=st3.data_ptr(), out_fmt=eng.PCM_F32_INTERLEAVED,
+                                              stream=stream), n, w, barrier, shard)
+        assert int((st3 != 0).sum().item()) == 0
+        # stream 0 is unique stream 0 from its first frame: its first 32 frames against the reference decoder's energy
+        got = float((pcm3[: nf3 * 1536 * nout].double() ** 2).sum().item())
+        want = float(fx[ekey][0])
+        assert abs(got - want) / want < 1e-5, ("config-3 energy differs from the reference digest", key, got, want)
+        out[key] = fig(ms, n3, fb3 + 1536 * nout * 4,
+                       "configs[2]: %d streams x %d frames of 5.1 640 kb/s (8 unique x 32 frames of tests/golden/c3_fixture.npz), "
+                       "float %s out" % (S3, F3, "stereo" if nout == 2 else "5.1 + LFE"))
+        del pcm3
+    dec.set_max_frame_bytes(FRAME_BYTES)
+    dec.set_max_stream_frames(F)
+    del es3
+
+    # (3) config 4: batched encode of the corpus PCM (the first 256 streams' samples, tiled)
+    corpus = _corpus_mod()
+    Fe = 64
+    pcm_u = corpus.synth_torch(range(64), dev, Fe * 1536).reshape(64, Fe, 1536 * 6)
+    pcm_e = pcm_u[torch.arange(S, device=dev) % 64].contiguous()                   # [S][Fe][1536*6] int16
+    out_e = torch.zeros((S, Fe, FRAME_BYTES), dtype=torch.uint8, device=dev)
+    st_e = torch.zeros((S, Fe), dtype=torch.int32, device=dev)
+    enc = eng.BatchEncoder(dev.index or 0)
+    ms = _timed(lambda: enc.encode_device(pcm_e.data_ptr(), S, Fe, 48000, 448000, 6, out_e.data_ptr(),
+                                          status_ptr=st_e.data_ptr(), stream=stream), n, w, barrier, shard)
+    assert int((st_e != 0).sum().item()) == 0
+    enc.close()
+    out["config4_encode"] = fig(ms, S * Fe, ENC_ALGO_BYTES_PER_FRAME,
+                                "configs[3]: %d streams x %d frames of 5.1 int16 PCM -> 448 kb/s (64 unique)" % (S, Fe))
+    out["config4_encode"]["metric"] = METRIC_ENC
+    return out
+
+
 def run_e2e(args, eng, dec, corpus, shard, barrier, world):
     import torch
     S, F = args.streams, args.frames
@@ -524,7 +699,7 @@ def run_e2e(args, eng, dec, corpus, shard, barrier, world):
     while s_e2e > 64 and s_e2e * per_stream > budget:
         s_e2e //= 2
     nframes = s_e2e * F
-    es_h = torch.from_numpy(corpus[:s_e2e].reshape(-1).copy()).pin_memory()
+    es_h = corpus[:nframes * FRAME_BYTES].cpu().pin_memory()
     s16 = args.pcm == "s16"
     pcm_h = torch.empty(nframes * 1536 * 2, dtype=torch.int16 if s16 else torch.float32).pin_memory()
     status_h = torch.zeros(nframes, dtype=torch.int32).pin_memory()
@@ -568,6 +743,8 @@ def main():
                          "bytes per frame); s16 = what the ACM wrapper and `a52dec -o wav` deliver (int16 stereo, "
                          "7 936 bytes per frame) - a supplementary line, never the default")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the supplementary figures (int16, config 3, config 4)")
+    ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="decode", choices=["decode", "encode"],
                     help="decode = BASELINE.json configs[1] (the headline metric); encode = configs[3]")

@@ -1,18 +1,22 @@
-"""Summarise an ncu source-page CSV: executed warp instructions and stall samples per source line,
-grouped into ranges of the kernel source.  Usage: ncu_lines.py src.csv file.cu [nframes]"""
-import csv, sys, collections
+"""Summarise an ncu source-page CSV: executed warp instructions and stall samples per source line of ONE file
+(the kernel source: instructions inlined from headers are attributed to their call sites in that file's table; the
+other files' tables repeat them), grouped into ranges of the kernel source.
+Usage: ncu_lines.py src.csv file.cu [nframes]"""
+import csv, sys, collections, os
 rows = list(csv.reader(open(sys.argv[1])))
-hdr = None
+want = os.path.basename(sys.argv[2])
+hdr = None; cur = None
 per_line = collections.Counter(); samp = collections.Counter(); thr = collections.Counter()
 for r in rows:
+    if r and r[0] == "File Path":
+        cur = os.path.basename(r[1]); continue
     if r and r[0] == "Line No":
-        hdr = r; continue
-    if hdr is None or len(r) < 10: continue
+        hdr = r; ie = hdr.index("Instructions Executed"); ns = hdr.index("# Samples"); te = hdr.index("Thread Instructions Executed"); continue
+    if hdr is None or len(r) < 10 or cur != want: continue
     try:
         ln = int(r[0])
     except ValueError:
         continue
-    ie = hdr.index("Instructions Executed"); ns = hdr.index("# Samples"); te = hdr.index("Thread Instructions Executed")
     try:
         per_line[ln] += int(r[ie]); samp[ln] += int(r[ns]); thr[ln] += int(r[te])
     except ValueError:
@@ -24,7 +28,7 @@ print("total warp-instr %.3g (%.0f per frame), samples %d" % (tot, tot / nfr, ts
 # group by marker comments
 marks = []
 for i, l in enumerate(src, 1):
-    if "=================" in l or l.startswith("__device__") or l.startswith("__global__"):
+    if "=================" in l or l.startswith("__device__") or l.startswith("__global__") or l.startswith("template <"):
         marks.append((i, l.strip()[:70]))
 marks.append((len(src) + 1, "end"))
 for (a, name), (b, _) in zip(marks, marks[1:]):
