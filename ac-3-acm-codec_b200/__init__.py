@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liba52_b200.so")
+# (A52_B200_LIB: developer knob for A/B builds of the library; the default is the in-tree build)
+LIB_PATH = os.environ.get("A52_B200_LIB") or os.path.join(_HERE, "liba52_b200.so")
 
 A52_CHANNEL, A52_MONO, A52_STEREO, A52_3F, A52_2F1R, A52_3F1R, A52_2F2R, A52_3F2R = range(8)
 A52_CHANNEL1, A52_CHANNEL2, A52_DOLBY = 8, 9, 10
@@ -20,7 +21,8 @@ A52_CHANNEL_MASK, A52_LFE, A52_ADJUST_LEVEL = 15, 16, 32
 PCM_F32_PLANAR, PCM_F32_INTERLEAVED, PCM_S16_INTERLEAVED, PCM_S16_WAV = 0, 1, 2, 3
 REQ_AS_CODED = 0x100          # include/a52_batch.h: every frame in its own coded mode (libao wav6)
 DEVICE_PTRS = 1
-DRC_STREAM, DRC_OFF = 0, 1
+DRC_STREAM, DRC_OFF, DRC_TABLE = 0, 1, 2
+SLICES_AUTO, SLICES_CHAINED, SLICES_INDEPENDENT = 0, 1, 2
 ST_OK, ST_BAD_SYNC, ST_BAD_FRAME, ST_BAD_BLOCK = 0, 1, 2, 16
 _NFCH = [2, 1, 2, 3, 3, 4, 4, 5, 1, 1, 2]
 
@@ -28,7 +30,7 @@ EXPORTS = [
     "a52_init", "a52_samples", "a52_syncinfo", "a52_frame", "a52_dynrng", "a52_block", "a52_free",
     "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index", "a52_batch_index_device",
     "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes", "a52_batch_set_max_stream_frames",
-    "a52_batch_launch_count", "a52_batch_kernel_ms",
+    "a52_batch_launch_count", "a52_batch_kernel_ms", "a52_batch_scan", "a52_batch_set_drc_table", "a52_batch_set_slice_mode",
     "AC3_encode_init", "AC3_encode_frame",
     "ac3_batch_create", "ac3_batch_destroy", "ac3_batch_last_error", "ac3_batch_frame_bytes",
     "ac3_batch_encode", "ac3_batch_launch_count", "ac3_batch_kernel_ms",
@@ -40,6 +42,13 @@ EXPORTS = [
 class CarryStruct(C.Structure):
     _fields_ = [("dither_index", C.c_uint32), ("per_channel", C.c_uint32), ("reserved", C.c_uint32 * 2),
                 ("delay", (C.c_float * 128) * 6)]
+
+
+class FrameScanStruct(C.Structure):
+    _fields_ = [("dither_draws", C.c_uint32), ("dynrng", (C.c_int16 * 2) * 6), ("status", C.c_int32)]
+
+
+SCAN_DTYPE = np.dtype([("dither_draws", np.uint32), ("dynrng", np.int16, (6, 2)), ("status", np.int32)])
 
 
 class DebugStruct(C.Structure):
@@ -82,6 +91,10 @@ def load_library():
         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
         C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.a52_batch_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p]
+    L.a52_batch_set_drc_table.argtypes = [C.c_void_p, C.c_void_p]
+    L.a52_batch_set_slice_mode.argtypes = [C.c_void_p, C.c_int]
     L.a52_init.restype = C.c_void_p
     L.a52_init.argtypes = [C.c_uint32]
     L.a52_samples.restype = C.POINTER(C.c_float)
@@ -192,6 +205,26 @@ class BatchDecoder:
         self._check(rc)
         out.update(pcm=pcm, status=status, flags=flags, carry=cbuf)
         return out
+
+    def scan_host(self, es, frame_off, stream_first, req_flags):
+        """a52_batch_scan with host buffers: numpy record array (dither_draws, dynrng[6][2], status) per frame."""
+        es = np.ascontiguousarray(es, dtype=np.uint8)
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        stream_first = np.ascontiguousarray(stream_first, dtype=np.uint32)
+        out = np.zeros(len(frame_off), SCAN_DTYPE)
+        assert SCAN_DTYPE.itemsize == C.sizeof(FrameScanStruct) == 32
+        rc = self.L.a52_batch_scan(self.ctx, es.ctypes.data, len(es), frame_off.ctypes.data, len(frame_off),
+                                   stream_first.ctypes.data, len(stream_first) - 1, req_flags, out.ctypes.data, 0, None)
+        self._check(rc)
+        return out
+
+    def set_drc_table(self, ranges):
+        """float32 [nframes][6][2] for the next DRC_TABLE call (kept alive here), or None."""
+        self._drc = None if ranges is None else np.ascontiguousarray(ranges, dtype=np.float32)
+        self.L.a52_batch_set_drc_table(self.ctx, self._drc.ctypes.data if self._drc is not None else None)
+
+    def set_slice_mode(self, mode):
+        self.L.a52_batch_set_slice_mode(self.ctx, mode)
 
     def decode_host_into(self, es_ptr, es_bytes, frame_off, stream_first, req_flags, pcm_ptr, status_ptr=0,
                          flags_ptr=0, level=1.0, bias=0.0, drc=DRC_STREAM, out_fmt=PCM_F32_INTERLEAVED):

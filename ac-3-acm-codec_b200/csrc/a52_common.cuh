@@ -12,6 +12,7 @@
 namespace a52 {
 
 constexpr int kDitherPeriod = 65535;
+constexpr int kDitherWrap = 4096;
 
 // output mode ids == liba52's A52_* flag values (include/a52.h)
 enum { M_CHANNEL = 0, M_MONO, M_STEREO, M_3F, M_2F1R, M_3F1R, M_2F2R, M_3F2R,
@@ -39,10 +40,9 @@ struct __align__(16) Tables {
     int16_t  q4[2][128];       // grouped 11-level values by (digit, 7-bit code)
     int16_t  q35[24];          // 7-level at [0..7], 15-level at [8..23]
     uint16_t dither_lut[256];  // CRC-16/0xA011 byte step (tables.h:213-246)
-    uint16_t jump_hi[256];     // dither generator advanced 32 steps: contribution of the high byte
-    uint16_t jump_lo[256];     //                                      and of the low byte
     uint32_t cnt_lut32[20];    // per bap: 5-bit counters n1 | n2 << 5 | n4 << 10 | zero << 15, plain field bits << 20
     uint4    emit_lut[32];     // per bap (+16: bap-0 mantissas of this run are dithered), see build_tables()
+    uint4    emit_lut2[32];    // same index: where a mantissa's plan entry goes and what its position word holds
     uint16_t hth[3 * 50];
     uint8_t  masktab[256];
     uint8_t  latab[256];
@@ -72,6 +72,12 @@ struct StreamCarry {          // == a52_stream_carry_t (include/a52_batch.h)
     float    delay[6][128];
 };
 
+struct FrameScan {            // == a52_frame_scan_t (include/a52_batch.h)
+    uint32_t dither_draws;
+    int16_t  dynrng[6][2];    // -1: the block carries no word
+    int32_t  status;
+};
+
 struct DecodeParams {
     const uint8_t*  es;
     uint64_t        es_bytes;
@@ -89,7 +95,10 @@ struct DecodeParams {
     int32_t*        status;
     int32_t*        frame_flags;
     StreamCarry*    carry;
-    const uint16_t* dither_seq;      // state after n dither_gen() calls from seed 1, n = 0..65534
+    const StreamCarry* carry_in;     // where the initial state is read (frame-independent slices: a copy, since the
+                                     // last slice of a stream writes carry[] while its first may not have started)
+    const uint16_t* dither_seq;      // state after n dither_gen() calls from seed 1, n = 0..65534, then wrapped
+                                     // (kDitherWrap more entries) so that a block never takes a modulo
     int*            work_counter;
     int             fbuf_bytes;      // bytes of the staged-frame buffer (multiple of 16)
     int             warp_bytes;      // shared-memory bytes per warp
@@ -98,8 +107,20 @@ struct DecodeParams {
     int             slice_frames;    // pair kernel: frames per work unit
     int             nslices;         // pair kernel: work units per stream (1 = whole streams)
     int             carry_init;      // carry[] holds the caller's initial state (else streams start fresh)
-    uint4*          snap;            // [resident pairs][nplanes * 64]: plane image after a full locate pass
+    uint8_t*        plan;            // [resident pairs][kPlanBytes]: plan of the last full locate pass
     int*            slice_done;      // [nstreams] slices completed per stream
+    // scan pass (a52_batch_scan): side information, exponents, bit allocation and the locate counts only - what
+    // the dither generator drew in every frame and which dynrng words its blocks carry; no PCM
+    int             scan_only;
+    FrameScan*      scan;            // [nframes]
+    // frame-independent slices: every slice of a stream starts on its own, one frame early (that frame rebuilds the
+    // overlap-add tails and the tail representation; its PCM goes to a scratch frame), with the dither generator
+    // position a scan pass and a prefix sum gave it.  No slice waits for another.
+    int             indep;
+    const uint32_t* slice_dither;    // [nstreams][nslices] generator position at the slice's first decoded frame
+    uint8_t*        scratch_pcm;     // [resident pairs][frame_stride]
+    // dynamic range control by table: the range every dynrng word of the batch stands for (a52_dynrng callbacks)
+    const float*    drc_ranges;      // [nframes][6][2] or NULL
     // optional dumps
     uint8_t*        dbg_exp;
     uint8_t*        dbg_bap;

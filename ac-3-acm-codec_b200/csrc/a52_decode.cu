@@ -75,6 +75,9 @@ struct __align__(16) GroupCtl {
     int      err;              // error raised inside the current block
     int      tr_ticket;        // transform jobs of the pending block handed out so far
     float    wg2[12];          // wt[o][ch] * gain[ch] of outputs 0 and 1 ([0..4] and [5..9]): the stereo mix fast path
+    uint32_t cur_blk;          // 6 * frame + block being parsed (index into the per-block tables of the launch)
+    int16_t  dynw[2];          // the block's dynrng words as coded (-1: none)
+    uint32_t pad1;
     // what the last full locate pass left for blocks that repeat its baps, ranges and flags
     uint32_t loc_ta, loc_tb, loc_tz, loc_mant, loc_bitpos;
     uint8_t  loc_valid, loc_dithflag, loc_chincpl, repeat;
@@ -128,19 +131,16 @@ struct WarpPtrs {
     GroupCtl* ctl;
     uint8_t*  exp;     // [7][256]
     uint8_t*  bap;     // [7][256]  standard numbering 0..15
-    uint16_t* list;    // [kListEntries] per-class work lists of plane slots
     float*    plane;   // [nplanes][256]: 5 fbw planes (+ the LFE plane when it is an output)
     uint32_t* fbuf;    // staged frame (native-endian 32-bit words after the swap pass)
     uint64_t* mbar;
 };
 
-constexpr int kListEntries = 1504;   // >= 5*253 + 216 + 7 mantissa slots per block
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-// The lists and the planes come first in a pair's shared memory, which starts 128-byte aligned: the paired
-// transform of the stereo fast path works in place on planes 0 and 1 and XORs address bits 4..6.
-constexpr int kListBytes = (kListEntries * 2 + 127) & ~127;
+// The planes come first in a pair's shared memory, which starts 128-byte aligned: the paired transform of the
+// stereo fast path works in place on planes 0 and 1 and XORs address bits 4..6.
 __host__ __device__ inline int align128(int x) { return (x + 127) & ~127; }
 
 // Layout of a pair's shared memory.  Every offset but the size of the staged frame (last) is a compile-time
@@ -148,9 +148,9 @@ __host__ __device__ inline int align128(int x) { return (x + 127) & ~127; }
 // all of a pair's addresses are one register plus an immediate.
 template <int NPL>
 struct PairLayout {
-    static constexpr int list = 0;
-    static constexpr int plane = list + kListBytes;                    // [NPL][256] float, 128-byte aligned
-    static constexpr int delay = plane + NPL * 1024;                   // [NPL][128] float overlap-add tails
+    static constexpr int plane = 0;                                    // [NPL][256] float, 128-byte aligned
+    static constexpr int dump = plane + NPL * 1024;                    // where the missing members of a short group go
+    static constexpr int delay = dump + 16;                            // [NPL][128] float overlap-add tails
     static constexpr int ctl = delay + NPL * 512;
     static constexpr int exp = ctl + (((int)sizeof(GroupCtl) + 15) & ~15);
     static constexpr int bap = exp + 7 * 256;
@@ -158,6 +158,12 @@ struct PairLayout {
     static constexpr int mbar = xch + 64;
     static constexpr int fbuf = mbar + 16;                             // staged frame, fbuf_bytes
 };
+
+// The pair's plan in global memory (see the locate stage): 16-byte group entries, 8-byte plain entries,
+// 4-byte zero entries.  A block has at most 1504 coded mantissas and 1287 coefficient slots.
+constexpr int kPlanGroups = 768, kPlanPlain = 1536, kPlanZeros = 2560;
+constexpr int kPlanPlainOff = kPlanGroups * 16, kPlanZeroOff = kPlanPlainOff + kPlanPlain * 8;
+constexpr int kPlanBytes = kPlanZeroOff + kPlanZeros * 4;
 
 __host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
 {
@@ -456,6 +462,8 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             br.pos = p0 + nb + nz;
         }
     }
+    c->dynw[0] = -1;
+    c->dynw[1] = -1;
     if (!fast) {
     uint32_t v = br.get(2 * nfchans);          // blksw[nfchans], dithflag[nfchans]
     // the fields are sent channel 0 first (msb): bit-reverse them so that bit i = channel i
@@ -464,12 +472,16 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     c->blksw = blksw;
     c->dithflag = dith;
 
-    int reps = acmod ? 1 : 2;                  // dynrng (parse.c:578-598)
-    while (reps--) {
+    const int nrep = acmod ? 1 : 2;            // dynrng (parse.c:578-598)
+    for (int rep = 0; rep < nrep; rep++) {
         if (br.get(1)) {
             int d = br.get_signed(8);
+            c->dynw[rep] = (int16_t)(d & 0xff);
             if (!P.drc_off) {
                 float range = (float)(((d & 0x1f) | 0x20) << 13) * pow2neg(15 + 3 - (d >> 5));
+                // the caller's own mapping of this word (a52_dynrng with a callback, run on the host between
+                // a scan pass and this one)
+                if (P.drc_ranges) range = P.drc_ranges[(size_t)c->cur_blk * 2 + rep];
                 c->dynrng = c->level * range;
                 c->gains_dirty = 1;
             }
@@ -972,16 +984,6 @@ __device__ __forceinline__ uint32_t field_at(const uint32_t* w, uint32_t pos, ui
     return (pos + n <= limit) ? peek_bits(w, pos, n) : 0u;
 }
 
-// dither generator (parse.c:310-319) advanced 32 steps: the step is linear over GF(2), so
-// state * x^256 = J_hi[state >> 8] ^ J_lo[state & 255]
-__device__ __forceinline__ uint32_t lfsr_jump32(uint32_t tab_base, uint32_t s)
-{
-    uint32_t hi, lo;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(tab_base + (uint32_t)offsetof(Tables, jump_hi) + (s >> 8) * 2));
-    asm("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(tab_base + (uint32_t)offsetof(Tables, jump_lo) + (s & 255) * 2));
-    return hi ^ lo;
-}
-
 // ---------------------------------------------------------------------------
 // mantissa descriptors.  A 32-bit word per coded mantissa, written into the
 // coefficient-plane slot the coefficient itself will occupy:
@@ -1035,37 +1037,36 @@ __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, uint32_t p
                  :: "r"(addr), "r"(v), "r"(pred) : "memory");
 }
 
+__device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, uint32_t pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f32 [%0], %1;\n}\n"
+                 :: "r"(addr), "f"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void stg_u32_if(void* addr, uint32_t v, uint32_t pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.cg.u32 [%0], %1;\n}\n"
+                 :: "l"(addr), "r"(v), "r"(pred) : "memory");
+}
+// read-only shared-memory loads (tables, the staged frame) through 32-bit shared addresses
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t a)
+{
+    int v;
+    asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
 // peek without a limit check: descriptor positions are clamped to the frame end at emit time
 // and the words past the frame end are zero
 __device__ __forceinline__ uint32_t peek_nz(const uint32_t* w, uint32_t pos, uint32_t n)
 {
     uint32_t i = pos >> 5, s = pos & 31;
     return __funnelshift_l(w[i + 1], w[i], s) >> (32 - n);
-}
-
-// 3-, 5- and 11-level groups: one lane per group code (parse.c:368-421)
-template <int PER, int WBITS, int QSTRIDE, int NT = 32>
-__device__ __forceinline__ void unpack_groups(const WarpPtrs& G, const uint32_t* W, uint32_t base, uint32_t n,
-                                              const int16_t* qtab, int lane, uint32_t pos_delta, uint32_t limit)
-{
-    uint32_t* planeU = reinterpret_cast<uint32_t*>(G.plane);
-    const uint32_t ng = (n + PER - 1) / PER;
-    for (uint32_t g = lane; g < ng; g += NT) {
-        const uint32_t k0 = g * PER;
-        uint32_t slot[PER], d[PER];
-#pragma unroll
-        for (int dg = 0; dg < PER; dg++) {
-            const uint32_t k = min(k0 + dg, n - 1);          // the last group may be partial
-            slot[dg] = G.list[base + k];
-            d[dg] = planeU[slot[dg]];
-        }
-        const uint32_t code = peek_nz(W, min(((d[0] >> 10) & 0x7fff) + pos_delta, limit), WBITS);
-#pragma unroll
-        for (int dg = PER - 1; dg >= 0; dg--) {                // descending: a clamped duplicate is overwritten
-            const int q = qtab[dg * QSTRIDE + code];
-            if (k0 + dg < n) G.plane[slot[dg]] = (float)q * pow2neg(15 + (d[dg] & 31));
-        }
-    }
 }
 
 // coefficient-domain downmix: out[o] = sum over coded channels of wg[o][ch] * in[ch]
@@ -1464,7 +1465,7 @@ __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const Wa
     tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
 }
 
-static_assert(sizeof(GroupCtl) <= 1248, "GroupCtl grew: check the shared-memory budget per stream");
+static_assert(sizeof(GroupCtl) <= 1264, "GroupCtl grew: check the shared-memory budget per stream");
 
 // ===========================================================================
 // The decode kernel: TWO warps (64 threads, a "pair") walk one stream.  The two warps split every
@@ -1481,7 +1482,6 @@ __device__ __forceinline__ PairPtrs carve_pair(uint8_t* base)
 {
     using Lay = PairLayout<NPL>;
     PairPtrs g;
-    g.list = reinterpret_cast<uint16_t*>(base + Lay::list);
     g.plane = reinterpret_cast<float*>(base + Lay::plane);
     g.delay = reinterpret_cast<float*>(base + Lay::delay);
     g.ctl = reinterpret_cast<GroupCtl*>(base + Lay::ctl);
@@ -1663,7 +1663,10 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
         }
 }
 
-constexpr int kMaxPairsPerCta = 12;
+#ifndef A52_PAIRS_PER_CTA
+#define A52_PAIRS_PER_CTA 14
+#endif
+constexpr int kMaxPairsPerCta = A52_PAIRS_PER_CTA;      // named barriers 1..15 serve the pairs: at most 15
 
 template <int NPL>
 __global__ void __launch_bounds__(kMaxPairsPerCta * 64, 1)
@@ -1672,7 +1675,8 @@ a52_decode_kernel(const DecodeParams P)
     extern __shared__ __align__(128) uint8_t smem[];
     Tables& T = *reinterpret_cast<Tables*>(smem);
     const int tid = threadIdx.x;
-    const int pair = tid >> 6, gt = tid & 63, w = gt >> 5, lane = tid & 31;
+    const int wid = tid >> 5, lane = tid & 31, pair = wid >> 1, w = wid & 1;
+    const int gt = w * 32 + lane;
     constexpr int NT = 64;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
@@ -1682,7 +1686,6 @@ a52_decode_kernel(const DecodeParams P)
     const PairPtrs G = carve_pair<NPL>(smem + align128((int)sizeof(Tables)) + pair * P.warp_bytes);
     GroupCtl* c = G.ctl;
     uint32_t* const W = G.fbuf;
-    uint32_t* const planeU = reinterpret_cast<uint32_t*>(G.plane);
     const PairSync sync{pair + 1};
     if (gt == 0) {
         mbar_init(G.mbar, 1);
@@ -1691,14 +1694,14 @@ a52_decode_kernel(const DecodeParams P)
     for (int i = gt; i < (int)(sizeof(GroupCtl) / 4); i += NT) reinterpret_cast<uint32_t*>(c)[i] = 0;
     for (int i = gt; i < 7 * 256 * 2 / 4; i += NT) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
     __syncthreads();
-    uint32_t tab_base, list_sa, plane_sa;
+    uint32_t tab_base, plane_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(tab_base) : "r"(smem_u32(&T)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(list_sa) : "r"(smem_u32(G.list)));
     asm volatile("mov.u32 %0, %1;" : "=r"(plane_sa) : "r"(smem_u32(G.plane)));
+    constexpr uint32_t kDumpWord = (uint32_t)(PairLayout<NPL>::dump - PairLayout<NPL>::plane);   // scale bits 0: stores 0.0f
     uint32_t phase = 0;
     constexpr int ndelay = NPL;              // tails: planes 0..4 main, 5 LFE
-    // this pair's scratch in global memory: the image of the planes after a full locate pass
-    uint4* const snap = P.snap + (size_t)(blockIdx.x * (blockDim.x >> 6) + pair) * (NPL * 64);
+    // this pair's scratch in global memory: the plan of the last full locate pass
+    uint8_t* const plan = P.plan + (size_t)(blockIdx.x * (blockDim.x >> 6) + pair) * kPlanBytes;
 
     // Work units are SLICES of streams (P.slice_frames frames), handed out slice-major from one ticket
     // counter: all first slices, then all second slices, ...  A slice starts from the carry record its
@@ -1717,7 +1720,8 @@ a52_decode_kernel(const DecodeParams P)
         uint32_t f0 = fs0 + slice * (uint32_t)P.slice_frames;
         if (f0 > fs1) f0 = fs1;
         const uint32_t f1 = (slice + 1 < (uint32_t)P.nslices && fs1 - f0 > (uint32_t)P.slice_frames) ? f0 + P.slice_frames : fs1;
-        if (slice > 0) {
+        const bool chained = !P.indep && !P.scan_only;
+        if (slice > 0 && chained) {
             if (gt == 0) {
                 volatile int* done = P.slice_done + s;
                 while (*done < (int)slice) __nanosleep(200);
@@ -1725,12 +1729,16 @@ a52_decode_kernel(const DecodeParams P)
             }
             sync();
         }
-        const bool have_state = P.carry && (slice > 0 || P.carry_init);
+        // a slice on its own decodes one frame of look-back first (not in a scan: nothing is carried there)
+        const bool lookback = P.indep && slice > 0 && f0 < f1;
+        const uint32_t fl = lookback ? f0 - 1 : f0;
+        const bool have_state = P.carry && !P.scan_only && (chained ? (slice > 0 || P.carry_init) : (slice == 0 && P.carry_init));
         uint32_t dither_index = 0;
         if (have_state) {
-            dither_index = __ldcg(&P.carry[s].dither_index) % kDitherPeriod;
-            if (gt == 0) c->per_channel = (__ldcg(&P.carry[s].per_channel) != 0);
-            for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = __ldcg(&P.carry[s].delay[i >> 7][i & 127]);
+            const StreamCarry* cin = (P.carry_in ? P.carry_in : P.carry) + s;
+            dither_index = __ldcg(&cin->dither_index) % kDitherPeriod;
+            if (gt == 0) c->per_channel = (__ldcg(&cin->per_channel) != 0);
+            for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = __ldcg(&cin->delay[i >> 7][i & 127]);
         } else {
             // a fresh stream: liba52 starts from a52_init's state; so do the parse state (exponents, baps, coupling
             // and allocation parameters a damaged first frame might "reuse") and the tails
@@ -1739,10 +1747,16 @@ a52_decode_kernel(const DecodeParams P)
             for (int i = gt; i < 7 * 256 * 2 / 4; i += NT) reinterpret_cast<uint32_t*>(G.exp)[i] = 0;
             for (int i = gt; i < ndelay * 128; i += NT) G.delay[i] = 0.f;
         }
-        if (gt == 0 && f0 < f1) issue_frame_load(P, G, f0);
+        if (P.indep && f0 < f1) {
+            // generator position at frame fl (carry of the call included by the host's prefix sum)
+            dither_index = __ldg(P.slice_dither + (size_t)s * P.nslices + slice) % kDitherPeriod;
+        }
+        if (gt == 0 && fl < f1) issue_frame_load(P, G, fl);
         sync();
 
-        for (uint32_t f = f0; f < f1; f++) {
+        for (uint32_t f = fl; f < f1; f++) {
+            const bool shadow = lookback && f == fl;          // decoded for its state only
+            uint32_t frame_draws = 0;
             const uint64_t off = P.frame_off[f];
             bool next_issued = false;
             mbar_wait(G.mbar, phase);
@@ -1761,12 +1775,13 @@ a52_decode_kernel(const DecodeParams P)
                 int st = parse_frame_header(c, W, base_bit, P, avail, cap);
                 c->frame_ok = (st == 0);
                 c->err = st;
-                if (P.frame_flags) P.frame_flags[f] = st ? 0 : c->output;
+                if (P.frame_flags && !shadow) P.frame_flags[f] = st ? 0 : c->output;
             }
             sync();
             int frame_status = c->err;
             const bool frame_ok = c->frame_ok;
-            uint8_t* out_frame = P.pcm + (size_t)f * P.frame_stride;
+            uint8_t* out_frame = shadow ? P.scratch_pcm + (size_t)(blockIdx.x * (blockDim.x >> 6) + pair) * P.frame_stride
+                                        : P.pcm + (size_t)f * P.frame_stride;
             if (frame_ok) {
                 uint32_t lim = c->limit_bit;
                 for (uint32_t i = (lim >> 5) + gt; i < (uint32_t)P.fbuf_bytes / 4; i += NT) {
@@ -1789,12 +1804,15 @@ a52_decode_kernel(const DecodeParams P)
             if (frame_ok)
             for (;; blk++) {
                 const bool more = blk < 6;
-                // dither states of this block's first rows (row r of the zero list goes to warp r & 1);
-                // requested early so that the L2 latency hides behind the side information
-                uint32_t ring = 0;
-                if (more) ring = P.dither_seq[(dither_index + 1 + 32 * w + lane) % kDitherPeriod];
                 // ================= P (block blk) | T (block blk - 1) =================
-                if (more && gt == 0) c->err = parse_block(c, W, P);
+                if (more && gt == 0) {
+                    c->cur_blk = f * 6u + (uint32_t)blk;
+                    c->err = parse_block(c, W, P);
+                    if (P.scan_only && !c->err) {
+                        P.scan[f].dynrng[blk][0] = c->dynw[0];
+                        P.scan[f].dynrng[blk][1] = c->dynw[1];
+                    }
+                }
                 __syncwarp();
                 if (pend && p_fast) {
                     // both mixed planes in one packed transform; whichever warp gets here first takes it
@@ -1926,30 +1944,30 @@ a52_decode_kernel(const DecodeParams P)
                         for (int a = 0; a < 7; a++)
                             if ((c->do_alloc >> a) & 1) reinterpret_cast<uint32_t*>(G.bap + a * 256)[gt] = 0;
                     } else {
-                        int16_t* scratch = reinterpret_cast<int16_t*>(G.list);
+                        int16_t* scratch = reinterpret_cast<int16_t*>(G.plane);     // (the planes are rebuilt by the locate stage)
                         bit_allocate_block<NT>(T, c, c->do_alloc, G.exp, G.bap, scratch, scratch + 7 * 50, gt, sync);
                     }
                     sync();
                 }
 
                 // ================= L =================
-                // What the locate passes produce - descriptors in the coefficient slots, the work lists, the
-                // class totals - is a function of the baps, the coded ranges and the dither / coupling flags,
-                // up to one common shift of the bit positions.  A block that changes none of them (every
-                // exponent set and allocation reused: the rule, not the exception) restores the image of the
-                // planes the last full pass left in the pair's scratch (global memory, L2-resident), keeps the
-                // lists as they are and lets the unpack stage add the shift.
+                // What the locate passes produce is a PLAN of the block's mantissas: for every class (3-, 5- and
+                // 11-level groups, plain fields, dithered zeros) the list of its members in coded order, each with
+                // the shared-memory slot of its coefficient, its scale 2^-(15 + exponent) and the bit position of
+                // its field.  The plan is a function of the baps, the coded ranges and the dither / coupling flags,
+                // up to one common shift of the bit positions, and it lives in the pair's scratch in global memory
+                // (L2-resident, read back coalesced).  A block that changes none of its inputs (every exponent set
+                // and allocation reused: the rule, not the exception) skips the passes altogether and lets the
+                // unpack stage add the shift.
                 const bool rep = c->repeat != 0;
                 const uint32_t bitpos = c->bitpos;
                 uint32_t ta, tb, tz, mant_bits, pos_delta = 0;
-                uint4* const plane4 = reinterpret_cast<uint4*>(G.plane);
+                for (int i = gt; i < NPL * 256 / 4; i += NT)
+                    reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
                 if (rep) {
-                    for (int i = gt; i < NPL * 64; i += NT) plane4[i] = __ldcg(snap + i);
                     ta = c->loc_ta; tb = c->loc_tb; tz = c->loc_tz; mant_bits = c->loc_mant;
                     pos_delta = bitpos - c->loc_bitpos;
                 } else {
-                    for (int i = gt; i < NPL * 256 / 4; i += NT)
-                        reinterpret_cast<uint4*>(G.plane)[i] = make_uint4(0, 0, 0, 0);
                     const uint32_t K = c->plan_K;
                     const uint32_t cpl_dith = chincpl & c->dithflag;
                     const uint32_t ncpl_dith = __popc(cpl_dith);
@@ -2018,33 +2036,41 @@ a52_decode_kernel(const DecodeParams P)
                     sync();
                     mant_bits = G.xch[3] + G.xch[11];
                     if (w) ibits += G.xch[3];
-                    const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
-                    {
+                    const uint32_t ng1 = (t1 + 2) / 3, ng2 = (t2 + 2) / 3;
+                    if (!P.scan_only) {
                         uint32_t pos = min(bitpos + ibits - mybits, limit);
-                        const uint32_t base_lo = e1 | ((L2 + e2) << 16), base_hi = (L4 + e4) | ((LP + ep) << 16);
-                        const uint32_t base_z = LZ + ez;
-                        const uint32_t phase0 = p1 | (p2 << 8) | (p4 << 16);
+                        // exclusive occurrence counts of my run, per class, as 16-bit fields
+                        const uint32_t base_lo = e1 | (e2 << 16), base_hi = e4 | (ep << 16);
+                        const uint32_t base_z = ez;
+                        // first group of each group class inside the one group section: 0, ng1, ng1 + ng2
+                        const uint32_t gb_lo = ng1 << 16, gb_hi = ng1 + ng2;
                         uint32_t run_a = 0, run_z = 0;
                         const uint32_t lut_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut);
+                        const uint32_t lut2_addr = tab_base + (uint32_t)offsetof(Tables, emit_lut2);
                         const uint32_t zrow4 = (zmode == 1) ? 0x10101010u : 0u;
                         const uint32_t emit_bit = mute ? 0u : 0x1000000u;
-                        // four mantissas per trip: one funnelled bap word and one exponent word, their four LUT
-                        // rows fetched together, then the four updates in coded order
-                        // emit_lut row: x: cursor increment (classes 1, 2, 4, plain); y: base selector A |
-                        // width << 16 | emit << 24; z: base selector B | 256/period << 16; w: count selector |
-                        // period << 16 | zero-list increment << 24
-                        auto emit_one = [&](uint32_t b, uint32_t e, uint32_t slot, const uint4& L) {
+                        // four mantissas per trip: one funnelled bap word and one exponent word, their LUT rows
+                        // fetched together, then the four updates in coded order
+                        // emit_lut row: x: counter increment (classes 1, 2, 4, plain); y: count selector A |
+                        // width << 16 | emit << 24; z: count selector B; w: run-counter selector | period << 16 |
+                        // zero-class increment << 24
+                        // emit_lut2 row: x: 2^17 / period; y: byte offset of the class's plan section; z: entry
+                        // stride | offset of the member word << 8 | group-base selector << 16; w: constant bits of
+                        // the entry's position word (class, 32 - width, value table), bit 31 = has a position word
+                        auto emit_one = [&](uint32_t e, uint32_t slot, const uint4& L, const uint4& M) {
                             const uint32_t cls_cnt = prmt(run_a, run_z, L.w);
-                            const uint32_t li = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
-                            // starts a field / group code when (phase0 + occurrences so far) % period == 0
-                            const uint32_t x = prmt(phase0, 0, L.w) + cls_cnt;
+                            const uint32_t occ = prmt(prmt(base_lo, base_hi, L.y), base_z, L.z) + cls_cnt;
                             const uint32_t per = prmt(L.w, 0, 0x4442);
-                            const uint32_t r = x - per * ((x * (L.z >> 16)) >> 8);
+                            const uint32_t g = (occ * M.x) >> 17;               // occ / period (occ < 2^15)
+                            const uint32_t r = occ - g * per;
+                            const uint32_t u = prmt(gb_lo, gb_hi, M.z >> 16) + g;
+                            const uint32_t eb = M.y + u * (M.z & 0xffu);        // the entry
+                            const uint32_t ea = eb + ((M.z >> 8) & 0xffu) + 4u * r;   // this member's word
                             run_a += L.x;
                             run_z += L.w >> 24;
                             const uint32_t emit = L.y & emit_bit;
-                            sts_u16_if(list_sa + 2 * li, slot, emit);
-                            sts_u32_if(plane_sa + 4 * slot, make_desc(e, b, pos), emit);
+                            stg_u32_if(plan + ea, (slot << 2) | ((112u - e) << 23), emit);
+                            stg_u32_if(plan + eb, pos | M.w, (r == 0 && (int32_t)M.w < 0) ? emit : 0u);
                             pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
                         };
                         uint32_t bw_lo = bapw[wi0], ew_lo = expw[wi0];
@@ -2054,14 +2080,17 @@ a52_decode_kernel(const DecodeParams P)
                                 const uint32_t bv = __funnelshift_r(bw_lo, bw_hi, bsh), ev = __funnelshift_r(ew_lo, ew_hi, bsh);
                                 bw_lo = bw_hi;
                                 ew_lo = ew_hi;
-                                uint4 Lr[4];
+                                uint4 Lr[4], Mr[4];
                                 // mantissas past my run take the row of an undithered zero: nothing moves
                                 const uint32_t rows = (bv + zrow4) & run_mask(run_n, k0);
     #pragma unroll
-                                for (int t = 0; t < 4; t++) Lr[t] = lds_v4(lut_addr + prmt(rows, 0, 0x4440 + t) * 16);
+                                for (int t = 0; t < 4; t++) {
+                                    Lr[t] = lds_v4(lut_addr + prmt(rows, 0, 0x4440 + t) * 16);
+                                    Mr[t] = lds_v4(lut2_addr + prmt(rows, 0, 0x4440 + t) * 16);
+                                }
     #pragma unroll
                                 for (int t = 0; t < 4; t++)
-                                    emit_one((bv >> (8 * t)) & 0xff, (ev >> (8 * t)) & 0xff, run_slot + k0 + t, Lr[t]);
+                                    emit_one((ev >> (8 * t)) & 0xff, run_slot + k0 + t, Lr[t], Mr[t]);
                             }
                         } else {
                             // coupling channel with dither: a bap-0 bin takes one dither value per coupled
@@ -2074,18 +2103,24 @@ a52_decode_kernel(const DecodeParams P)
                                         const uint32_t ch = __ffs(m) - 1;
                                         m &= m - 1;
                                         const uint32_t s2 = ch * 256 + (slot & 255);
-                                        G.list[base_z + run_z] = (uint16_t)s2;
+                                        stg_u32_if(plan + kPlanZeroOff + 4u * (base_z + run_z), (s2 << 2) | ((112u - e) << 23), 1u);
                                         run_z++;
-                                        planeU[s2] = e;
                                     }
                                 } else {
-                                    emit_one(b, e, slot, lds_v4(lut_addr + b * 16));
+                                    emit_one(e, slot, lds_v4(lut_addr + b * 16), lds_v4(lut2_addr + b * 16));
                                 }
                             }
                         }
                     }
-                    sync();
-                    for (int i = gt; i < NPL * 64; i += NT) __stcg(snap + i, plane4[i]);
+                    // the last group of a class may be short: its missing members unpack into a dump word
+                    if (gt < 3 && !P.scan_only) {
+                        const uint32_t tcl = gt == 0 ? t1 : gt == 1 ? t2 : t4, per = gt == 2 ? 2u : 3u;
+                        const uint32_t gb = gt == 0 ? 0u : gt == 1 ? ng1 : ng1 + ng2;
+                        const uint32_t full = tcl / per, rem = tcl - full * per;
+                        if (rem)
+                            for (uint32_t rr = rem; rr < per; rr++)
+                                stg_u32_if(plan + 16u * (gb + full) + 4u + 4u * rr, kDumpWord, 1u);
+                    }
                     if (gt == 0) {
                         c->loc_ta = ta; c->loc_tb = tb; c->loc_tz = tz; c->loc_mant = mant_bits;
                         c->loc_bitpos = bitpos;
@@ -2094,36 +2129,84 @@ a52_decode_kernel(const DecodeParams P)
                 }
                 sync();
                 if (gt == 0) c->bitpos = bitpos + mant_bits;
+                frame_draws += tz;
+                if (P.scan_only) continue;        // a scan stops here: the counts are all it wants of the block
                 const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
-                const uint32_t L2 = t1, L4 = L2 + t2, LP = L4 + t4, LZ = LP + tp;
 
                 // ================= U =================
-                if (tz) {
-                    // rows of 32 zeros alternate between the warps; a warp's states advance 64 steps per own row
-                    for (uint32_t r0 = 32 * w; r0 < tz; r0 += 64) {
-                        const uint32_t k = r0 + lane;
-                        if (k < tz) {
-                            const uint32_t slot = G.list[LZ + k];
-                            const uint32_t e = planeU[slot];
-                            const int dv = (3 * (int)(int16_t)ring) >> 2;
-                            G.plane[slot] = (float)dv * pow2neg(15 + e);
+                // Every class reads its part of the plan back in coalesced 16-byte (groups, pairs of plain fields) or
+                // 4-byte (zeros: one row of 32 per load, eight rows in flight) loads; a member word is
+                // slot << 2 | scale bits, so a coefficient costs a table or shift dequantisation, one multiply and
+                // one store.
+                {
+                    // every first load of the three classes is issued before anything is used: one exposure of the
+                    // L2 latency per block instead of three
+                    const uint32_t ngroups = (t1 + 2) / 3 + (t2 + 2) / 3 + (t4 + 1) / 2;
+                    const uint4* gp = reinterpret_cast<const uint4*>(plan) + gt;
+                    const uint4* pp = reinterpret_cast<const uint4*>(plan + kPlanPlainOff) + gt;
+                    const uint32_t* zp = reinterpret_cast<const uint32_t*>(plan + kPlanZeroOff) + 32 * w + lane;
+                    const uint16_t* ds = P.dither_seq + dither_index + 1 + 32 * w + lane;
+                    uint4 Gn = make_uint4(0, 0, 0, 0), Pn = make_uint4(0, 0, 0, 0);
+                    if (gt < ngroups) Gn = __ldcg(gp);
+                    if (2 * gt < tp) Pn = __ldcg(pp);
+
+                    // zeros: rows of 32 alternate between the warps; zero k takes value dither_index + 1 + k of the
+                    // generator's sequence (parse.c:310-319), read from the (wrapped) table
+                    const uint32_t nrows = (tz + 31) >> 5;
+                    for (uint32_t r0 = w; r0 < nrows; r0 += 16, zp += 512, ds += 512) {
+                        uint32_t E[8], D[8];
+    #pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            E[i] = __ldcg(zp + 64 * i);
+                            D[i] = __ldg(ds + 64 * i);
                         }
-                        ring = lfsr_jump32(tab_base, lfsr_jump32(tab_base, ring));
+    #pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t k = 32 * (r0 + 2 * i) + lane;
+                            const int dv = (3 * (int)(int16_t)D[i]) >> 2;
+                            const float v = (float)dv * __uint_as_float(E[i] & 0x7f800000u);
+                            sts_f32_if(plane_sa + (E[i] & 0x1fffu), v, k < tz ? 1u : 0u);
+                        }
                     }
                     dither_index = (dither_index + tz) % kDitherPeriod;
-                }
-                if (t1) unpack_groups<3, 5, 32, NT>(G, W, 0, t1, &T.q1[0][0], gt, pos_delta, limit);
-                if (t2) unpack_groups<3, 7, 128, NT>(G, W, L2, t2, &T.q2[0][0], gt, pos_delta, limit);
-                if (t4) unpack_groups<2, 7, 128, NT>(G, W, L4, t4, &T.q4[0][0], gt, pos_delta, limit);
-                for (uint32_t k = gt; k < tp; k += NT) {
-                    const uint32_t slot = G.list[LP + k];
-                    const uint32_t d = planeU[slot];
-                    const uint32_t b = (d >> 5) & 15;
-                    const uint32_t wbits = T.bap_bits[b];
-                    const uint32_t raw = peek_nz(W, min(((d >> 10) & 0x7fff) + pos_delta, limit), wbits);
-                    int q = ((int)(raw << (32 - wbits))) >> 16;
-                    if (b <= 5) q = T.q35[(b & 4) * 2 + raw];
-                    G.plane[slot] = (float)q * pow2neg(15 + (d & 31));
+
+                    const uint32_t w_sa = smem_u32(W);
+                    auto window = [&](uint32_t pw) {          // the 32 bits at the entry's (shifted, clamped) position
+                        const uint32_t pos = min((pw & 0x7fffu) + pos_delta, limit);
+                        const uint32_t a = w_sa + ((pos >> 5) << 2);
+                        return __funnelshift_l(lds_u32(a + 4), lds_u32(a), pos);
+                    };
+                    // groups: position word (pos | class << 15 | (32 - width) << 19 | table << 24) + three member words
+                    const uint32_t q_sa = tab_base + (uint32_t)offsetof(Tables, q1);
+                    for (uint32_t g = gt; g < ngroups; g += NT) {
+                        const uint4 E = Gn;
+                        if (g + NT < ngroups) Gn = __ldcg(gp + (g + NT - gt));
+                        const uint32_t code = window(E.x) >> ((E.x >> 19) & 31u);
+                        const uint32_t ta0 = q_sa + ((E.x >> 24) & 0x7fu) * 64u + code * 2u;
+                        const uint32_t st = (E.x & 0x18000u) ? 256u : 64u;       // digit stride of the value table
+                        const float v0 = (float)lds_s16(ta0) * __uint_as_float(E.y & 0x7f800000u);
+                        const float v1 = (float)lds_s16(ta0 + st) * __uint_as_float(E.z & 0x7f800000u);
+                        sts_f32_if(plane_sa + (E.y & 0x1fffu), v0, 1u);
+                        sts_f32_if(plane_sa + (E.z & 0x1fffu), v1, 1u);
+                        if ((E.x & 0x18000u) != 0x10000u) {                        // 11-level codes hold two values
+                            const float v2 = (float)lds_s16(ta0 + 2 * st) * __uint_as_float(E.w & 0x7f800000u);
+                            sts_f32_if(plane_sa + (E.w & 0x1fffu), v2, 1u);
+                        }
+                    }
+                    // plain fields, two entries per load: position word (.. | bit 30: value table) + member word
+                    const uint32_t q35_sa = tab_base + (uint32_t)offsetof(Tables, q35);
+                    auto plain_one = [&](uint32_t pw, uint32_t mw, uint32_t pred) {
+                        const uint32_t v = window(pw), sh = (pw >> 19) & 31u;
+                        int q = ((int)(v & (0xffffffffu << sh))) >> 16;
+                        if (pw & 0x40000000u) q = lds_s16(q35_sa + ((pw >> 24) & 0x3fu) * 2u + (v >> sh) * 2u);
+                        sts_f32_if(plane_sa + (mw & 0x1fffu), (float)q * __uint_as_float(mw & 0x7f800000u), pred);
+                    };
+                    for (uint32_t k = 2 * gt; k < tp; k += 2 * NT) {
+                        const uint4 E = Pn;
+                        if (k + 2 * NT < tp) Pn = __ldcg(pp + ((k >> 1) + NT - gt));
+                        plain_one(E.x, E.y, 1u);
+                        plain_one(E.z, E.w, k + 1 < tp ? 1u : 0u);
+                    }
                 }
                 sync();
                 if (blk == 5 && f + 1 < f1) {
@@ -2234,7 +2317,12 @@ a52_decode_kernel(const DecodeParams P)
             }   // blocks
 
             if (frame_ok && blk < 6) frame_status = 16 + blk;
-            if (frame_status) {
+            if (P.scan_only) {
+                if (gt == 0) {
+                    P.scan[f].dither_draws = frame_draws;
+                    P.scan[f].status = frame_status;
+                }
+            } else if (frame_status) {
                 int nout = frame_ok ? (c->nout + c->out_lfe) : P.nout_req;
                 int ssz = (P.out_fmt >= 2) ? 2 : 4;
                 size_t from = (size_t)blk * 256 * nout * ssz;
@@ -2242,27 +2330,29 @@ a52_decode_kernel(const DecodeParams P)
                 for (size_t i = from + gt * 4; i < to; i += NT * 4)
                     *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
             }
-            if (frame_ok && !(P.req_flags & 0x100)) {
+            if (frame_ok && !(P.req_flags & 0x100) && !P.scan_only) {
                 // a frame granted fewer channels than the request's stride holds: the rest of its slot is silence
                 const int ssz = (P.out_fmt >= 2) ? 2 : 4;
                 const size_t used = (size_t)1536 * (c->nout + c->out_lfe) * ssz;
                 for (size_t i = used + gt * 4; i < P.frame_stride; i += NT * 4)
                     *reinterpret_cast<uint32_t*>(out_frame + i) = 0;
             }
-            if (gt == 0 && P.status) P.status[f] = frame_status;
+            if (gt == 0 && P.status && !shadow && !P.scan_only) P.status[f] = frame_status;
             sync();
             if (!next_issued && f + 1 < f1 && gt == 0) issue_frame_load(P, G, f + 1);
             sync();
         }   // frames
 
-        if (P.carry) {
+        // the state after the unit's last frame: for the next slice of the chain, or (frame-independent slices: from
+        // the slice that holds the stream's last frame) for the caller
+        if (P.carry && !P.scan_only && (chained || (f1 == fs1 && (f0 < f1 || slice == 0)))) {
             for (int i = gt; i < ndelay * 128; i += NT) P.carry[s].delay[i >> 7][i & 127] = G.delay[i];
             if (gt == 0) {
                 P.carry[s].dither_index = dither_index;
                 P.carry[s].per_channel = c->per_channel;
             }
         }
-        if (P.nslices > 1) {
+        if (P.nslices > 1 && chained) {
             __threadfence();
             sync();
             if (gt == 0) atomicExch(P.slice_done + s, (int)slice + 1);

@@ -255,16 +255,6 @@ static void build_tables(Tables* T)
     for (int i = 0; i < 51; i++) T->bndtab[i] = ac3_bndtab[i];
     T->bndtab[51] = 253;
     for (int i = 0; i < 16; i++) T->bap_bits[i] = ac3_bap_bits[i];
-    // dither generator, 32 steps at once: linear over GF(2), so split by byte
-    for (int v = 0; v < 256; v++) {
-        uint16_t hi = (uint16_t)(v << 8), lo = (uint16_t)v;
-        for (int k = 0; k < 32; k++) {
-            hi = (uint16_t)(ac3_dither_lut[hi >> 8] ^ (uint16_t)(hi << 8));
-            lo = (uint16_t)(ac3_dither_lut[lo >> 8] ^ (uint16_t)(lo << 8));
-        }
-        T->jump_hi[v] = hi;
-        T->jump_lo[v] = lo;
-    }
     for (int b = 0; b < 16; b++) {
         T->cnt_lut32[b] = (b == 1 ? 1u : 0u) | (b == 2 ? 1u << 5 : 0u) | (b == 4 ? 1u << 10 : 0u) | (b == 0 ? 1u << 15 : 0u) |
                           ((b != 0 && b != 1 && b != 2 && b != 4) ? (uint32_t)ac3_bap_bits[b] << 20 : 0u);
@@ -291,7 +281,30 @@ static void build_tables(Tables* T)
             uint32_t incz = (cls == 4 && z) ? 1 : 0;
             T->emit_lut[z * 16 + b] = make_uint4(x, selA[cls] | (width << 16) | (emit << 24),
                                                  selB | (recip << 16), selC | (per << 16) | (incz << 24));
+            // emit_lut2: the mantissa's place in the pair's plan (a52_decode.cu, locate stage)
+            //   x: 2^17 / period (rounded up): (n * x) >> 17 == n / period for n < 2^15
+            //   y: byte offset of the class's section; z: [7:0] entry stride, [15:8] offset of the first member
+            //      word, [31:16] byte selector of the class's first group out of (ng1 << 16, ng1 + ng2)
+            //   w: constant bits of the position word: class << 15, (32 - width) << 19, value table << 24
+            //      (groups: offset from q1 in 64-byte units; plain: index into q35, bit 30 = use it), bit 31 = the
+            //      entry has a position word (not for zeros)
+            const uint32_t recip17 = per == 3 ? 43691u : per == 2 ? 65536u : 131072u;
+            const uint32_t sec = cls < 3 ? 0u : cls == 3 ? (uint32_t)kPlanPlainOff : (uint32_t)kPlanZeroOff;
+            const uint32_t stride = cls < 3 ? 16u : cls == 3 ? 8u : 4u, offa = cls < 4 ? 4u : 0u;
+            static const uint32_t selG[5] = {0x7610, 0x7632, 0x7654, 0x7676, 0x7676};
+            uint32_t pw = 0;
+            if (cls < 3) {
+                const uint32_t tbl = cls == 0 ? 0u : cls == 1 ? (uint32_t)sizeof(T->q1) / 64u
+                                                              : (uint32_t)(sizeof(T->q1) + sizeof(T->q2)) / 64u;
+                pw = 0x80000000u | ((uint32_t)cls << 15) | ((32u - width) << 19) | (tbl << 24);
+            } else if (cls == 3) {
+                pw = 0x80000000u | (3u << 15) | ((32u - width) << 19);
+                if (b == 3 || b == 5) pw |= 0x40000000u | ((uint32_t)((b & 4) * 2) << 24);
+            }
+            T->emit_lut2[z * 16 + b] = make_uint4(recip17, sec, stride | (offa << 8) | (selG[cls] << 16), pw);
         }
+    static_assert(offsetof(Tables, q2) == offsetof(Tables, q1) + sizeof(T->q1) &&
+                  offsetof(Tables, q4) == offsetof(Tables, q2) + sizeof(T->q2), "value tables must be contiguous");
 }
 
 static int nout_of_flags(int flags)
@@ -353,6 +366,29 @@ __global__ void a52_index_kernel(const uint8_t* es, const uint64_t* stream_off, 
     if (count) count[s] = n;
 }
 
+// Frame-independent slices: position of the dither generator at the first frame every slice decodes (its
+// look-back frame), from the per-frame draw counts of a scan pass.  One warp per stream.
+__global__ void a52_slice_dither_kernel(const FrameScan* scan, const uint32_t* stream_first, int nstreams, int nslices,
+                                        int slice_frames, const StreamCarry* carry_in, uint32_t* slice_dither)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= nstreams) return;
+    const uint32_t fs0 = stream_first[s], fs1 = stream_first[s + 1];
+    uint32_t run = carry_in ? carry_in[s].dither_index % kDitherPeriod : 0u;       // position at the stream's first frame
+    for (int j = 0; j < nslices; j++) {
+        uint32_t f0 = fs0 + (uint32_t)j * slice_frames;
+        if (f0 > fs1) f0 = fs1;
+        const uint32_t f1 = (j + 1 < nslices && fs1 - f0 > (uint32_t)slice_frames) ? f0 + slice_frames : fs1;
+        if (lane == 0)
+            slice_dither[(size_t)s * nslices + j] =
+                (j > 0 && f0 < fs1) ? (run + kDitherPeriod - scan[f0 - 1].dither_draws % kDitherPeriod) % kDitherPeriod : run;
+        uint32_t sum = 0;
+        for (uint32_t f = f0 + lane; f < f1; f += 32) sum += scan[f].dither_draws;
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        run = (run + sum) % kDitherPeriod;
+    }
+}
+
 // longest stream (frames) of a device-resident batch
 __global__ void a52_maxstream_kernel(const uint32_t* first, int nstreams, int* out)
 {
@@ -375,6 +411,8 @@ struct a52_batch_s {
     int max_frame_hint = 0;
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
+    int slice_mode = 0;            // 0 = choose, 1 = slices of a stream chained by the carry record, 2 = frame-independent
+    const float* drc_table = nullptr;   // a52_batch_set_drc_table: ranges for the next A52_DRC_TABLE call
     uint16_t* d_dither = nullptr;
     int host_chunk_streams = 128;  // streams per pipelined chunk of a host-pointer call (A52_B200_HOST_CHUNK_STREAMS)
     int host_chunk_env = 0;
@@ -395,7 +433,7 @@ struct a52_batch_s {
     a52::ModeEntry mode_tab[9 * 16];   // the request's grant / level table, copied into every launch's parameters
     // host-mode scratch
     struct Buf { void* p = nullptr; size_t cap = 0; } b_es, b_off, b_first, b_pcm, b_status, b_flags,
-        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo, b_slice, b_done, b_snap;
+        b_carry, b_dexp, b_dbap, b_dcoef, b_dinfo, b_slice, b_done, b_snap, b_scan, b_sdith, b_spcm, b_cin, b_ranges;
 };
 
 #define A52_CUDA(call)                                                                       \
@@ -437,6 +475,8 @@ a52_batch_t* a52_batch_create(int device)
     if (g) ctx->warps_per_cta = atoi(g);
     const char* sf = getenv("A52_B200_SLICE_FRAMES");
     if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
+    const char* sm = getenv("A52_B200_SLICE_MODE");
+    if (sm && atoi(sm) >= 0 && atoi(sm) <= 2) ctx->slice_mode = atoi(sm);
     const char* hc = getenv("A52_B200_HOST_CHUNK_STREAMS");
     if (hc && atoi(hc) > 0) { ctx->host_chunk_streams = atoi(hc); ctx->host_chunk_env = 1; }
     const char* hq = getenv("A52_B200_HOST_CONCURRENCY");
@@ -451,12 +491,13 @@ a52_batch_t* a52_batch_create(int device)
     a52::build_mix_table(mix);
     ok = ok && cudaMemcpyToSymbol(a52::c_mix, mix, sizeof(mix)) == cudaSuccess;
     // dither sequence: state after n calls from seed 1 (parse.c:310-319)
-    std::vector<uint16_t> seq(a52::kDitherPeriod);
+    std::vector<uint16_t> seq(a52::kDitherPeriod + a52::kDitherWrap);
     uint16_t s = 1;
     for (int n = 0; n < a52::kDitherPeriod; n++) {
         seq[n] = s;
         s = (uint16_t)(ac3_dither_lut[s >> 8] ^ (uint16_t)(s << 8));
     }
+    for (int n = 0; n < a52::kDitherWrap; n++) seq[a52::kDitherPeriod + n] = seq[n];
     ok = ok && cudaMalloc(&ctx->d_dither, seq.size() * 2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dither, seq.data(), seq.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) == cudaSuccess;
@@ -477,7 +518,8 @@ void a52_batch_destroy(a52_batch_t* ctx)
     cudaSetDevice(ctx->device);
     a52_batch_s::Buf* bufs[] = {&ctx->b_es, &ctx->b_off, &ctx->b_first, &ctx->b_pcm, &ctx->b_status,
                                 &ctx->b_flags, &ctx->b_carry, &ctx->b_dexp, &ctx->b_dbap, &ctx->b_dcoef,
-                                &ctx->b_dinfo, &ctx->b_slice, &ctx->b_done, &ctx->b_snap};
+                                &ctx->b_dinfo, &ctx->b_slice, &ctx->b_done, &ctx->b_snap, &ctx->b_scan, &ctx->b_sdith,
+                                &ctx->b_spcm, &ctx->b_cin, &ctx->b_ranges};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_dither) cudaFree(ctx->d_dither);
@@ -579,9 +621,11 @@ double a52_batch_kernel_ms(a52_batch_t* ctx, int* nlaunches)
 
 // scratch_base / scratch_total: position of this launch's streams inside the per-stream scratch arrays when
 // several launches of one call are in flight at once (host pipeline); 0 / 0 = a launch on its own
+enum { RUN_CHAINED = 0, RUN_SCAN = 1, RUN_INDEP = 2 };
+
 static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int max_frame_bytes,
                          float level, cudaStream_t st, int counter_slot = 0, int max_stream_frames = 0,
-                         int scratch_base = 0, int scratch_total = 0, int snap_streams = 0)
+                         int scratch_base = 0, int scratch_total = 0, int snap_streams = 0, int run_mode = RUN_CHAINED)
 {
     using namespace a52;
     // work units of the pair kernel: slices of streams (see a52_decode_kernel)
@@ -589,7 +633,11 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.nslices = 1;
     P.carry_init = P.carry != nullptr;
     P.slice_done = nullptr;
-    if (ctx->pair_kernel && max_stream_frames > ctx->slice_frames) {
+    P.scan_only = run_mode == RUN_SCAN;
+    P.indep = run_mode == RUN_INDEP;
+    if (run_mode != RUN_CHAINED) {
+        if (max_stream_frames > ctx->slice_frames) P.nslices = (max_stream_frames + ctx->slice_frames - 1) / ctx->slice_frames;
+    } else if (ctx->pair_kernel && max_stream_frames > ctx->slice_frames) {
         P.nslices = (max_stream_frames + ctx->slice_frames - 1) / ctx->slice_frames;
         const size_t total = scratch_total ? (size_t)scratch_total : (size_t)P.nstreams;
         if (ensure(ctx, ctx->b_done, total * sizeof(int))) return -1;
@@ -626,26 +674,34 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     }
     int G = fit;
     if (ctx->warps_per_cta > 0 && ctx->warps_per_cta < G) G = ctx->warps_per_cta;
-    // small batches: spread the streams over all SMs
-    int per_sm = (P.nstreams + ctx->num_sms - 1) / ctx->num_sms;
-    if (per_sm < G) G = per_sm < 1 ? 1 : per_sm;
+    // small batches: spread the work over all SMs.  What runs side by side: whole streams when their slices are
+    // chained, every slice when they are independent of each other
+    const long long par = run_mode == RUN_CHAINED ? (long long)P.nstreams : (long long)P.nstreams * P.nslices;
+    long long per_sm = (par + ctx->num_sms - 1) / ctx->num_sms;
+    if (per_sm < G) G = per_sm < 1 ? 1 : (int)per_sm;
     const int threads = G * P.group_threads;
     const size_t smem = (size_t)tables + (size_t)G * P.warp_bytes;
-    int grid = (P.nstreams + G - 1) / G;
+    long long grid_ll = (par + G - 1) / G;
+    int grid = grid_ll > ctx->num_sms ? ctx->num_sms : (int)grid_ll;
     if (grid > ctx->num_sms) grid = ctx->num_sms;
     if (grid < 1) grid = 1;
     A52_CUDA(cudaMemsetAsync(ctx->d_counter + counter_slot, 0, sizeof(int), st));
-    // scratch of the locate stage: one plane image per resident pair.  Launches of one host-pointer call run
-    // side by side: each takes the region of its counter slot, all regions sized for the largest chunk.
+    // scratch of the locate stage: one plan per resident pair.  Launches of one host-pointer call run side by
+    // side: each takes the region of its counter slot, all regions sized for the largest chunk.
     {
-        const int nmax = scratch_total ? snap_streams : P.nstreams;
+        const long long nmax = scratch_total ? snap_streams : par;
         size_t pairs = (size_t)nmax + ctx->num_sms;
         const size_t cap = (size_t)ctx->num_sms * fit;
         if (pairs > cap) pairs = cap;
-        const size_t region = pairs * P.nplanes * 1024;
+        const size_t region = pairs * (size_t)kPlanBytes;
         const int regions = scratch_total ? 32 : 1;
         if (ensure(ctx, ctx->b_snap, region * regions)) return -1;
-        P.snap = (uint4*)((uint8_t*)ctx->b_snap.p + region * (scratch_total ? counter_slot : 0));
+        P.plan = (uint8_t*)ctx->b_snap.p + region * (scratch_total ? counter_slot : 0);
+        if (run_mode == RUN_INDEP) {
+            // where the look-back frame of every slice puts its PCM
+            if (ensure(ctx, ctx->b_spcm, pairs * P.frame_stride)) return -1;
+            P.scratch_pcm = (uint8_t*)ctx->b_spcm.p;
+        }
     }
     // timing events
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
@@ -668,6 +724,128 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     A52_CUDA(cudaGetLastError());
     ctx->launches++;
     (void)nframes;
+    return 0;
+}
+
+// Frame-independent slices of device-resident streams: scan pass, prefix sum of the dither draws, decode.
+static int launch_indep(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int maxlen, int maxstream, float level,
+                        cudaStream_t st)
+{
+    using namespace a52;
+    const int nstreams = P.nstreams;
+    if (ensure(ctx, ctx->b_scan, (size_t)nframes * sizeof(FrameScan))) return -1;
+    const int nslices = (maxstream + ctx->slice_frames - 1) / ctx->slice_frames;
+    if (ensure(ctx, ctx->b_sdith, (size_t)nstreams * nslices * sizeof(uint32_t))) return -1;
+    DecodeParams Ps = P;
+    Ps.pcm = nullptr; Ps.status = nullptr; Ps.frame_flags = nullptr; Ps.carry = nullptr;
+    Ps.dbg_exp = nullptr; Ps.dbg_bap = nullptr; Ps.dbg_coef = nullptr; Ps.dbg_info = nullptr;
+    Ps.scan = (FrameScan*)ctx->b_scan.p;
+    int rc = launch_decode(ctx, Ps, nframes, maxlen, level, st, 0, maxstream, 0, 0, 0, RUN_SCAN);
+    if (rc) return rc;
+    const StreamCarry* cin = nullptr;
+    if (P.carry) {
+        if (ensure(ctx, ctx->b_cin, (size_t)nstreams * sizeof(StreamCarry))) return -1;
+        A52_CUDA(cudaMemcpyAsync(ctx->b_cin.p, P.carry, (size_t)nstreams * sizeof(StreamCarry), cudaMemcpyDeviceToDevice, st));
+        cin = (const StreamCarry*)ctx->b_cin.p;
+    }
+    a52_slice_dither_kernel<<<(nstreams + 3) / 4, 128, 0, st>>>((const FrameScan*)ctx->b_scan.p, P.stream_first, nstreams,
+                                                               nslices, ctx->slice_frames, cin, (uint32_t*)ctx->b_sdith.p);
+    A52_CUDA(cudaGetLastError());
+    ctx->launches++;
+    P.carry_in = cin;
+    P.slice_dither = (const uint32_t*)ctx->b_sdith.p;
+    return launch_decode(ctx, P, nframes, maxlen, level, st, 0, maxstream, 0, 0, 0, RUN_INDEP);
+}
+
+void a52_batch_set_slice_mode(a52_batch_t* ctx, int mode)
+{
+    if (mode >= 0 && mode <= 2) ctx->slice_mode = mode;
+}
+
+void a52_batch_set_drc_table(a52_batch_t* ctx, const float* ranges) { ctx->drc_table = ranges; }
+
+int a52_batch_scan(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const uint64_t* frame_off, int nframes,
+                   const uint32_t* stream_first, int nstreams, int req_flags, a52_frame_scan_t* scan, int mem_flags,
+                   void* cuda_stream)
+{
+    using namespace a52;
+    static_assert(sizeof(a52_frame_scan_t) == sizeof(FrameScan), "scan record layout");
+    if (!ctx) return -1;
+    ctx->err[0] = 0;
+    if (nframes < 0 || nstreams < 0 || (req_flags & M_MASK) > M_DOLBY || !scan) {
+        snprintf(ctx->err, sizeof(ctx->err), "bad argument");
+        return -3;
+    }
+    if (nframes == 0 || nstreams == 0) return 0;
+    A52_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DecodeParams P;
+    memset(&P, 0, sizeof(P));
+    P.es_bytes = es_bytes;
+    P.nstreams = nstreams;
+    P.nframes = nframes;
+    P.req_flags = req_flags;
+    P.out_fmt = A52_PCM_F32_PLANAR;
+    P.nout_req = nout_of_flags(req_flags);
+    P.frame_stride = a52_batch_frame_stride(req_flags, A52_PCM_F32_PLANAR);
+    int maxlen = 0, maxstream = 0;
+    if (mem_flags & A52_BATCH_DEVICE_PTRS) {
+        if (((uintptr_t)es & 15) != 0) {
+            snprintf(ctx->err, sizeof(ctx->err), "device bitstream pointer must be 16-byte aligned");
+            return -3;
+        }
+        P.es = es;
+        P.frame_off = frame_off;
+        P.stream_first = stream_first;
+        P.scan = (FrameScan*)scan;
+        maxstream = ctx->max_stream_hint;
+        if (maxstream <= 0) {
+            A52_CUDA(cudaMemsetAsync(ctx->d_counter + 62, 0, sizeof(int), st));
+            a52_maxstream_kernel<<<(nstreams + 255) / 256, 256, 0, st>>>(stream_first, nstreams, ctx->d_counter + 62);
+            A52_CUDA(cudaMemcpyAsync(&maxstream, ctx->d_counter + 62, sizeof(int), cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaStreamSynchronize(st));
+            ctx->launches++;
+        }
+        maxlen = ctx->max_frame_hint;
+        if (maxlen <= 0) {
+            A52_CUDA(cudaMemsetAsync(ctx->d_counter + 63, 0, sizeof(int), st));
+            a52_maxlen_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(es, frame_off, nframes, ctx->d_counter + 63);
+            A52_CUDA(cudaMemcpyAsync(&maxlen, ctx->d_counter + 63, sizeof(int), cudaMemcpyDeviceToHost, st));
+            A52_CUDA(cudaStreamSynchronize(st));
+            ctx->launches++;
+        }
+        A52_CUDA(cudaMemsetAsync(scan, 0xff, (size_t)nframes * sizeof(FrameScan), st));
+        return launch_decode(ctx, P, nframes, maxlen, 1.0f, st, 0, maxstream, 0, 0, 0, RUN_SCAN);
+    }
+    // host pointers: stage in, scan, stage out (synchronous)
+    for (int i = 0; i < nframes; i++) {
+        int fl, sr, br;
+        if (frame_off[i] + 7 <= es_bytes) {
+            int len = host_syncinfo(es + frame_off[i], &fl, &sr, &br);
+            if (len > maxlen) maxlen = len;
+        }
+    }
+    for (int q = 0; q < nstreams; q++) {
+        int n = (int)(stream_first[q + 1] - stream_first[q]);
+        if (n > maxstream) maxstream = n;
+    }
+    if (ensure(ctx, ctx->b_es, es_bytes + 64)) return -1;
+    if (ensure(ctx, ctx->b_off, (size_t)(nframes + 1) * 8)) return -1;
+    if (ensure(ctx, ctx->b_first, (size_t)(nstreams + 1) * 4)) return -1;
+    if (ensure(ctx, ctx->b_scan, (size_t)nframes * sizeof(FrameScan))) return -1;
+    A52_CUDA(cudaMemsetAsync((uint8_t*)ctx->b_es.p + es_bytes, 0, 64, st));
+    A52_CUDA(cudaMemcpyAsync(ctx->b_es.p, es, es_bytes, cudaMemcpyHostToDevice, st));
+    A52_CUDA(cudaMemcpyAsync(ctx->b_off.p, frame_off, (size_t)nframes * 8, cudaMemcpyHostToDevice, st));
+    A52_CUDA(cudaMemcpyAsync(ctx->b_first.p, stream_first, (size_t)(nstreams + 1) * 4, cudaMemcpyHostToDevice, st));
+    A52_CUDA(cudaMemsetAsync(ctx->b_scan.p, 0xff, (size_t)nframes * sizeof(FrameScan), st));
+    P.es = (const uint8_t*)ctx->b_es.p;
+    P.frame_off = (const uint64_t*)ctx->b_off.p;
+    P.stream_first = (const uint32_t*)ctx->b_first.p;
+    P.scan = (FrameScan*)ctx->b_scan.p;
+    int rc = launch_decode(ctx, P, nframes, maxlen, 1.0f, st, 0, maxstream, 0, 0, 0, RUN_SCAN);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    A52_CUDA(cudaMemcpyAsync(scan, ctx->b_scan.p, (size_t)nframes * sizeof(FrameScan), cudaMemcpyDeviceToHost, st));
+    A52_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -730,7 +908,16 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             A52_CUDA(cudaStreamSynchronize(st));
             ctx->launches++;
         }
-        return launch_decode(ctx, P, nframes, maxlen, level, st, 0, maxstream);
+        if (drc_mode == A52_DRC_TABLE) P.drc_ranges = ctx->drc_table;        // (device pointer in this mode)
+        // few long streams: chained slices would leave most of the GPU idle (a stream is one pair at a time), so
+        // the slices are made independent of each other: a scan pass counts what the dither generator draws in
+        // every frame, a prefix sum turns that into every slice's starting position, and every slice rebuilds the
+        // overlap-add state by decoding one frame of look-back
+        const long long resident = (long long)ctx->num_sms * kMaxPairsPerCta;
+        const bool indep = ctx->slice_mode == 2 ||
+                           (ctx->slice_mode == 0 && 2LL * nstreams <= resident && maxstream >= 4 * ctx->slice_frames);
+        if (!indep || maxstream <= ctx->slice_frames) return launch_decode(ctx, P, nframes, maxlen, level, st, 0, maxstream);
+        return launch_indep(ctx, P, nframes, maxlen, maxstream, level, st);
     }
 
     // ---- host pointers: stage in, decode, stage out (synchronous for the caller) ----
@@ -777,6 +964,11 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         A52_CUDA(cudaMemcpyAsync(ctx->b_carry.p, carry, sizeof(StreamCarry) * (size_t)nstreams, cudaMemcpyHostToDevice, s_run));
     }
     const size_t nblk = (size_t)nframes * 6;
+    if (drc_mode == A52_DRC_TABLE && ctx->drc_table) {
+        if (ensure(ctx, ctx->b_ranges, nblk * 2 * sizeof(float))) return -1;
+        A52_CUDA(cudaMemcpyAsync(ctx->b_ranges.p, ctx->drc_table, nblk * 2 * sizeof(float), cudaMemcpyHostToDevice, s_run));
+        P.drc_ranges = (const float*)ctx->b_ranges.p;
+    }
     if (debug) {
         if (debug->exp && debug->bap) {
             if (ensure(ctx, ctx->b_dexp, nblk * 7 * 256) || ensure(ctx, ctx->b_dbap, nblk * 7 * 256)) return -1;
@@ -806,6 +998,16 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
     int nchunks = nstreams / chunk_streams;
     if (nchunks > 32) nchunks = 32;
     if (nchunks < 1) nchunks = 1;
+    int longest = 0;
+    for (int q = 0; q < nstreams; q++) {
+        int n = (int)(stream_first[q + 1] - stream_first[q]);
+        if (n > longest) longest = n;
+    }
+    // few long streams: frame-independent slices (see the device-pointer path), the whole batch in one go
+    const bool indep = longest > ctx->slice_frames &&
+                       (ctx->slice_mode == 2 || (ctx->slice_mode == 0 && 2LL * nstreams <= (long long)ctx->num_sms * kMaxPairsPerCta &&
+                                                 longest >= 4 * ctx->slice_frames));
+    if (indep) nchunks = 1;
     std::vector<size_t> cb0(nchunks), cb1(nchunks);
     size_t span_total = 0;
     for (int cidx = 0; cidx < nchunks; cidx++) {
@@ -853,8 +1055,9 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
             int n = (int)(stream_first[q + 1] - stream_first[q]);
             if (n > chunk_max) chunk_max = n;
         }
-        int rc = launch_decode(ctx, Pc, nframes, maxlen, level, s_k, cidx, chunk_max, s0, nstreams,
-                               (nstreams + nchunks - 1) / nchunks + 1);
+        int rc = indep ? launch_indep(ctx, Pc, nframes, maxlen, chunk_max, level, s_k)
+                       : launch_decode(ctx, Pc, nframes, maxlen, level, s_k, cidx, chunk_max, s0, nstreams,
+                                       (nstreams + nchunks - 1) / nchunks + 1);
         if (rc) return rc;
         A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_k));
         A52_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_run[cidx], 0));
@@ -895,6 +1098,8 @@ struct a52_state_s {
     int out_flags;
     float level_in, bias;
     int drc_off;
+    level_t (*drc_call)(level_t, void*);   // a52_dynrng's callback (NULL: compression as coded)
+    void* drc_data;
     int blk;                    // next block to hand out
     int decoded;                // frame_pcm valid for the staged frame
     int status;
@@ -953,7 +1158,9 @@ int a52_frame(a52_state_t* s, uint8_t* buf, int* flags, level_t* level, sample_t
     *level = lv;
     s->out_flags = out;
     s->bias = bias;
-    s->drc_off = 0;
+    s->drc_off = 0;              // a52_frame re-arms compression as coded, without a callback (parse.c:170-171)
+    s->drc_call = nullptr;
+    s->drc_data = nullptr;
     s->frame = buf;
     int fl, sr, br;
     s->frame_len = host_syncinfo(buf, &fl, &sr, &br);
@@ -966,11 +1173,13 @@ int a52_frame(a52_state_t* s, uint8_t* buf, int* flags, level_t* level, sample_t
 
 void a52_dynrng(a52_state_t* s, level_t (*call)(level_t, void*), void* data)
 {
-    // NULL callback = dynamic range compression off (parse.c:207-216).  A user
-    // callback would have to run on the host between the GPU's parse and
-    // dequantisation stages; it is accepted and treated as "compression as coded".
-    (void)data;
+    // NULL callback = dynamic range compression off; otherwise every dynrng word of the frame goes through the
+    // callback before it is applied (parse.c:207-216, 586-595).  The words are coded inside the audio blocks, so the
+    // first a52_block of the frame scans the frame for them, runs the callback on the host in block order and
+    // decodes with the ranges it returned (a52_batch_scan + A52_DRC_TABLE).
     s->drc_off = (call == nullptr);
+    s->drc_call = call;
+    s->drc_data = data;
 }
 
 int a52_block(a52_state_t* s)
@@ -980,10 +1189,27 @@ int a52_block(a52_state_t* s)
         uint64_t off[2] = {0, (uint64_t)s->frame_len};
         uint32_t first[2] = {0, 1};
         int32_t status = 0, fflags = 0;
+        int drc_mode = s->drc_off ? A52_DRC_OFF : A52_DRC_STREAM;
+        float ranges[6][2];
+        if (s->drc_call) {
+            a52_frame_scan_t sc;
+            if (a52_batch_scan(s->ctx, s->frame, (size_t)s->frame_len, off, 1, first, 1, s->req_flags, &sc, 0, nullptr)) return 1;
+            for (int b = 0; b < 6; b++)
+                for (int k = 0; k < 2; k++) {
+                    ranges[b][k] = 1.0f;
+                    if (sc.dynrng[b][k] < 0) continue;
+                    const int d = (int)(int8_t)sc.dynrng[b][k];
+                    // parse.c:586-591: (((dynrng & 0x1f) | 0x20) << 13) * scale_factor[3 - (dynrng >> 5)]
+                    const float range = (float)(((d & 0x1f) | 0x20) << 13) * ldexpf(1.0f, -(15 + 3 - (d >> 5)));
+                    ranges[b][k] = s->drc_call(range, s->drc_data);
+                }
+            a52_batch_set_drc_table(s->ctx, &ranges[0][0]);
+            drc_mode = A52_DRC_TABLE;
+        }
         int rc = a52_batch_decode(s->ctx, s->frame, (size_t)s->frame_len, off, 1, first, 1, s->req_flags,
-                                  s->level_in, s->bias, s->drc_off ? A52_DRC_OFF : A52_DRC_STREAM,
-                                  A52_PCM_F32_PLANAR, s->frame_pcm, &status, &fflags, &s->carry, nullptr, 0,
-                                  nullptr);
+                                  s->level_in, s->bias, drc_mode, A52_PCM_F32_PLANAR, s->frame_pcm, &status, &fflags,
+                                  &s->carry, nullptr, 0, nullptr);
+        a52_batch_set_drc_table(s->ctx, nullptr);
         if (rc) return 1;
         s->status = status;
         s->decoded = 1;

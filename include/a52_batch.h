@@ -47,6 +47,9 @@ typedef struct a52_batch_s a52_batch_t;
 /* dynamic range control */
 #define A52_DRC_STREAM          0   /* apply the stream's dynrng words (liba52 default) */
 #define A52_DRC_OFF             1   /* == a52_dynrng (state, NULL, NULL) */
+#define A52_DRC_TABLE           2   /* every dynrng word stands for the range a52_batch_set_drc_table() gave it:
+				       == a52_dynrng (state, call, data) with the callback run by the caller
+				       between a52_batch_scan() and a52_batch_decode() */
 
 /* per-frame status written to frame_status[] */
 #define A52_ST_OK               0
@@ -98,6 +101,36 @@ int a52_batch_index (const uint8_t * es, size_t es_bytes, uint64_t * frame_off, 
  * (frame table too small, CUDA error). */
 int a52_batch_index_device (a52_batch_t * ctx, const uint8_t * es, const uint64_t * stream_off, int nstreams,
 			    uint64_t * frame_off, int max_frames, uint32_t * stream_first, void * cuda_stream);
+
+/* What a frame holds without decoding it to PCM: a pass over the side information, the exponents and the bit
+ * allocation only (parse.c:558-804 + the counting half of :336-433). */
+typedef struct {
+    uint32_t dither_draws;	/* dither_gen() calls the frame makes (parse.c:310-319) */
+    int16_t  dynrng[6][2];	/* the 8-bit dynrng word(s) of every block as coded (parse.c:578-598; [1] is the
+				   second word of a 1+1 frame), -1 = the block carries none */
+    int32_t  status;		/* A52_ST_* the decode would report */
+} a52_frame_scan_t;
+
+/* Scan nframes frames (arguments as for a52_batch_decode; scan[nframes] is a device pointer under
+ * A52_BATCH_DEVICE_PTRS).  Returns 0 or a negative error. */
+int a52_batch_scan (a52_batch_t * ctx, const uint8_t * es, size_t es_bytes,
+		    const uint64_t * frame_off, int nframes,
+		    const uint32_t * stream_first, int nstreams, int req_flags,
+		    a52_frame_scan_t * scan, int mem_flags, void * cuda_stream);
+
+/* The ranges calls with drc_mode A52_DRC_TABLE apply: float [nframes][6][2], entry [f][b][k] for word k of block b
+ * of frame f as a52_batch_scan() reported it (entries of absent words are not read).  The range of a word d
+ * (signed 8 bit) as liba52 computes it before the callback is (((d & 0x1f) | 0x20) << 13) * 2^-(18 - (d >> 5))
+ * (parse.c:586-591).  Host pointer, or device pointer for A52_BATCH_DEVICE_PTRS calls; must stay valid until the
+ * decode call has consumed it. */
+void a52_batch_set_drc_table (a52_batch_t * ctx, const float * ranges);
+
+/* How a stream longer than a work unit (32 frames) is cut: 0 = choose (default), 1 = slices chained by the carry
+ * record (a stream is decoded by one pair of warps at a time: best when streams outnumber the GPU's resident
+ * pairs), 2 = frame-independent slices (all slices of a stream run side by side after a scan pass and a prefix
+ * sum of the dither draws; every slice decodes one frame of look-back for the overlap-add state: best for few
+ * long streams).  Both give the same PCM for conforming streams. */
+void a52_batch_set_slice_mode (a52_batch_t * ctx, int mode);
 
 /* bytes one decoded frame occupies in pcm_out for a request (req_flags as for
  * a52_frame): 1536 * nout_requested * sample size */
