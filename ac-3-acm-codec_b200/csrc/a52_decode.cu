@@ -56,6 +56,17 @@ __constant__ int16_t   c_floor[8]  = {0x2f0, 0x2b0, 0x270, 0x230, 0x1f0, 0x170, 
 
 __device__ Tables g_tables;                // filled by the host once per context
 
+// Bounds-checked build (-DA52_BOUNDS_CHECK, tools/gpu_checked.sh): every computed shared-memory store address,
+// plan index, bit-window word and staged-frame size is checked against its region; the first violation's code is
+// kept in g_violation and read back through a52_batch_violations().  (compute-sanitizer is not available on the
+// B200 pool this repository is measured on; the checked build runs the whole GPU suite instead.)
+__device__ int g_violation[4];
+#ifdef A52_BOUNDS_CHECK
+#define A52_CHECK(cond, code) do { if (!(cond)) atomicCAS(&g_violation[0], 0, (code)); } while (0)
+#else
+#define A52_CHECK(cond, code) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------
 // per-group shared state
 // ---------------------------------------------------------------------------
@@ -223,6 +234,7 @@ __device__ __forceinline__ uint32_t peek_bits(const uint32_t* w, uint32_t pos, u
 {
     // n in 1..32
     uint32_t i = pos >> 5, s = pos & 31;
+    A52_CHECK(i + 1 < (3840u + 64u) / 4u && n >= 1 && n <= 32, 401);
     uint32_t hi = w[i], lo = w[i + 1];
     uint32_t v = __funnelshift_l(lo, hi, s);
     return v >> (32 - n);
@@ -1462,6 +1474,7 @@ __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const Wa
     uint32_t nb = stage_bytes(P, f);
     fence_proxy_async();
     mbar_expect_tx(G.mbar, nb);
+    A52_CHECK(nb <= (uint32_t)P.fbuf_bytes && (nb & 15) == 0 && a0 + nb <= ((P.es_bytes + 64 + 15) & ~(uint64_t)15), 301);
     tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
 }
 
@@ -2025,7 +2038,7 @@ a52_decode_kernel(const DecodeParams P)
                     if (w) { ia += G.xch[0]; ib += G.xch[1]; iz += G.xch[2]; }
                     const uint32_t e1 = (ia - pa) & 0xffff, e2 = (ia - pa) >> 16;
                     const uint32_t e4 = (ib - pb) & 0xffff, ep = (ib - pb) >> 16, ez = iz - nz;
-                    const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
+                    const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff;
                     const uint32_t p1 = e1 % 3, p2 = e2 % 3, p4 = e4 & 1;
                     const uint32_t s1 = (p1 + n1 + 2) / 3 - (p1 != 0);
                     const uint32_t s2 = (p2 + n2 + 2) / 3 - (p2 != 0);
@@ -2069,6 +2082,9 @@ a52_decode_kernel(const DecodeParams P)
                             run_a += L.x;
                             run_z += L.w >> 24;
                             const uint32_t emit = L.y & emit_bit;
+                            A52_CHECK(!emit || (ea < (uint32_t)kPlanBytes && eb < (uint32_t)kPlanBytes && slot < NPL * 256u && e <= 24u &&
+                                               (eb < (uint32_t)kPlanPlainOff ? u < (uint32_t)kPlanGroups
+                                                : eb < (uint32_t)kPlanZeroOff ? occ < (uint32_t)kPlanPlain : occ < (uint32_t)kPlanZeros)), 101);
                             stg_u32_if(plan + ea, (slot << 2) | ((112u - e) << 23), emit);
                             stg_u32_if(plan + eb, pos | M.w, (r == 0 && (int32_t)M.w < 0) ? emit : 0u);
                             pos = min(pos + (r == 0 ? prmt(L.y, 0, 0x4442) : 0u), limit);
@@ -2103,6 +2119,7 @@ a52_decode_kernel(const DecodeParams P)
                                         const uint32_t ch = __ffs(m) - 1;
                                         m &= m - 1;
                                         const uint32_t s2 = ch * 256 + (slot & 255);
+                                        A52_CHECK(base_z + run_z < (uint32_t)kPlanZeros && s2 < NPL * 256u, 102);
                                         stg_u32_if(plan + kPlanZeroOff + 4u * (base_z + run_z), (s2 << 2) | ((112u - e) << 23), 1u);
                                         run_z++;
                                     }
@@ -2119,7 +2136,10 @@ a52_decode_kernel(const DecodeParams P)
                         const uint32_t full = tcl / per, rem = tcl - full * per;
                         if (rem)
                             for (uint32_t rr = rem; rr < per; rr++)
-                                stg_u32_if(plan + 16u * (gb + full) + 4u + 4u * rr, kDumpWord, 1u);
+                                {
+                                    A52_CHECK(gb + full < (uint32_t)kPlanGroups, 103);
+                                    stg_u32_if(plan + 16u * (gb + full) + 4u + 4u * rr, kDumpWord, 1u);
+                                }
                     }
                     if (gt == 0) {
                         c->loc_ta = ta; c->loc_tb = tb; c->loc_tz = tz; c->loc_mant = mant_bits;
@@ -2165,6 +2185,7 @@ a52_decode_kernel(const DecodeParams P)
                             const uint32_t k = 32 * (r0 + 2 * i) + lane;
                             const int dv = (3 * (int)(int16_t)D[i]) >> 2;
                             const float v = (float)dv * __uint_as_float(E[i] & 0x7f800000u);
+                            A52_CHECK(k >= tz || (E[i] & 0x1fffu) < NPL * 1024u, 201);
                             sts_f32_if(plane_sa + (E[i] & 0x1fffu), v, k < tz ? 1u : 0u);
                         }
                     }
@@ -2174,6 +2195,7 @@ a52_decode_kernel(const DecodeParams P)
                     auto window = [&](uint32_t pw) {          // the 32 bits at the entry's (shifted, clamped) position
                         const uint32_t pos = min((pw & 0x7fffu) + pos_delta, limit);
                         const uint32_t a = w_sa + ((pos >> 5) << 2);
+                        A52_CHECK(a + 8 <= w_sa + (uint32_t)P.fbuf_bytes, 202);
                         return __funnelshift_l(lds_u32(a + 4), lds_u32(a), pos);
                     };
                     // groups: position word (pos | class << 15 | (32 - width) << 19 | table << 24) + three member words
@@ -2186,6 +2208,15 @@ a52_decode_kernel(const DecodeParams P)
                         const uint32_t st = (E.x & 0x18000u) ? 256u : 64u;       // digit stride of the value table
                         const float v0 = (float)lds_s16(ta0) * __uint_as_float(E.y & 0x7f800000u);
                         const float v1 = (float)lds_s16(ta0 + st) * __uint_as_float(E.z & 0x7f800000u);
+#ifdef A52_BOUNDS_CHECK
+                        {
+                            const uint32_t nmem = ((E.x & 0x18000u) != 0x10000u) ? 3u : 2u;      // members of the group
+                            A52_CHECK((E.y & 0x1fffu) <= NPL * 1024u && (E.z & 0x1fffu) <= NPL * 1024u &&
+                                      (nmem < 3 || (E.w & 0x1fffu) <= NPL * 1024u), 203);
+                            A52_CHECK(((E.x >> 24) & 0x7fu) * 64u + code * 2u + (nmem - 1) * st <
+                                      (uint32_t)(sizeof(T.q1) + sizeof(T.q2) + sizeof(T.q4)), 205);
+                        }
+#endif
                         sts_f32_if(plane_sa + (E.y & 0x1fffu), v0, 1u);
                         sts_f32_if(plane_sa + (E.z & 0x1fffu), v1, 1u);
                         if ((E.x & 0x18000u) != 0x10000u) {                        // 11-level codes hold two values
@@ -2199,6 +2230,7 @@ a52_decode_kernel(const DecodeParams P)
                         const uint32_t v = window(pw), sh = (pw >> 19) & 31u;
                         int q = ((int)(v & (0xffffffffu << sh))) >> 16;
                         if (pw & 0x40000000u) q = lds_s16(q35_sa + ((pw >> 24) & 0x3fu) * 2u + (v >> sh) * 2u);
+                        A52_CHECK(!pred || (mw & 0x1fffu) < NPL * 1024u, 204);
                         sts_f32_if(plane_sa + (mw & 0x1fffu), (float)q * __uint_as_float(mw & 0x7f800000u), pred);
                     };
                     for (uint32_t k = 2 * gt; k < tp; k += 2 * NT) {

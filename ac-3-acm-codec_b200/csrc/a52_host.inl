@@ -333,8 +333,13 @@ __global__ void a52_maxlen_kernel(const uint8_t* es, const uint64_t* off, int nf
     if ((threadIdx.x & 31) == 0 && len) atomicMax(out, len);
 }
 
-// Frame indexer on the device: one thread walks one elementary stream with the resync discipline of
+// Frame indexer on the device: one WARP walks one elementary stream with the resync discipline of
 // a52dec.c:240-309 (slide one byte until a52_syncinfo accepts a header, then hop by the frame length).
+// The walk is a chain p -> p + len(p); the warp follows it 32 links at a time by speculation: lane j tests the
+// header at p + j * L (L = the length of the last accepted frame).  Every lane up to the first that does not find
+// a valid header of the same length is exactly where the byte-serial walk would have landed, so those frames are
+// accepted at once; at the first miss the warp falls back to what the reference does there - a different length
+// is taken as it is, a bad header starts the sliding search, 32 byte positions per step (ballot, first hit wins).
 // Pass 0 counts the frames of every stream, pass 1 writes their offsets behind stream_first[s].
 __device__ __forceinline__ int dev_syncinfo_len(const uint8_t* b)
 {
@@ -349,21 +354,48 @@ __device__ __forceinline__ int dev_syncinfo_len(const uint8_t* b)
 __global__ void a52_index_kernel(const uint8_t* es, const uint64_t* stream_off, int nstreams, int* count,
                                  const uint32_t* stream_first, uint64_t* frame_off, int max_frames)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (s >= nstreams) return;
     uint64_t pos = stream_off[s];
     const uint64_t end = stream_off[s + 1];
     int n = 0;
-    uint32_t slot = stream_first ? stream_first[s] : 0;
+    const uint32_t slot = stream_first ? stream_first[s] : 0;
+    uint32_t L = 0;                                      // length of the last accepted frame (0: none yet)
     while (pos + 7 <= end) {
-        const int len = dev_syncinfo_len(es + pos);
-        if (!len) { pos++; continue; }
-        if (pos + len > end) break;
-        if (frame_off && (int)(slot + n) < max_frames) frame_off[slot + n] = pos;
-        n++;
-        pos += len;
+        if (L) {
+            // speculative hop: frames of the same length back to back
+            const uint64_t p = pos + (uint64_t)lane * L;
+            const bool ok = p + 7 <= end && (uint32_t)dev_syncinfo_len(es + p) == L && p + L <= end;
+            const uint32_t miss = ~__ballot_sync(0xffffffffu, ok);
+            const int run = miss ? __ffs(miss) - 1 : 32;
+            if (lane < run && frame_off && (int)(slot + n + lane) < max_frames) frame_off[slot + n + lane] = p;
+            n += run;
+            pos += (uint64_t)run * L;
+            if (run == 32) continue;
+            if (pos + 7 > end) break;
+        }
+        // the walk's next step, as the reference takes it: the header at pos decides
+        const int len = dev_syncinfo_len(es + pos);      // (every lane reads the same 7 bytes)
+        if (len) {
+            if (pos + len > end) break;
+            if (lane == 0 && frame_off && (int)(slot + n) < max_frames) frame_off[slot + n] = pos;
+            n++;
+            pos += len;
+            L = len;
+            continue;
+        }
+        // resync: first byte position after pos that holds a valid header
+        L = 0;
+        for (;;) {
+            const uint64_t p = pos + 1 + lane;
+            const bool hit = p + 7 <= end && dev_syncinfo_len(es + p) != 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) { pos += (uint64_t)__ffs(m); break; }
+            pos += 32;
+            if (pos + 7 > end) break;
+        }
     }
-    if (count) count[s] = n;
+    if (count && lane == 0) count[s] = n;
 }
 
 // Frame-independent slices: position of the dither generator at the first frame every slice decodes (its
@@ -567,7 +599,7 @@ int a52_batch_index_device(a52_batch_t* ctx, const uint8_t* es, const uint64_t* 
     if (ensure(ctx, ctx->b_off, (size_t)(nstreams + 1) * 8)) return -1;
     if (ensure(ctx, ctx->b_done, (size_t)nstreams * sizeof(int))) return -1;
     A52_CUDA(cudaMemcpyAsync(ctx->b_off.p, stream_off, (size_t)(nstreams + 1) * 8, cudaMemcpyHostToDevice, st));
-    const int tpb = 64, grid = (nstreams + tpb - 1) / tpb;
+    const int tpb = 128, grid = (nstreams + 3) / 4;      // one warp per stream
     a52_index_kernel<<<grid, tpb, 0, st>>>(es, (const uint64_t*)ctx->b_off.p, nstreams, (int*)ctx->b_done.p, nullptr,
                                           nullptr, 0);
     std::vector<int> cnt(nstreams);
@@ -755,6 +787,17 @@ static int launch_indep(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, int
     P.carry_in = cin;
     P.slice_dither = (const uint32_t*)ctx->b_sdith.p;
     return launch_decode(ctx, P, nframes, maxlen, level, st, 0, maxstream, 0, 0, 0, RUN_INDEP);
+}
+
+int a52_batch_violations(void)
+{
+    int v[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(v, a52::g_violation, sizeof(v)) != cudaSuccess) return -1;
+#ifdef A52_BOUNDS_CHECK
+    return v[0];
+#else
+    return v[0] ? v[0] : -2;          // -2: this build carries no checks
+#endif
 }
 
 void a52_batch_set_slice_mode(a52_batch_t* ctx, int mode)

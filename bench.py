@@ -113,10 +113,13 @@ def unique_frames_gpu(eng, dev):
     return out
 
 
-def tile_corpus(frames, nstreams, nframes):
-    """[nstreams][nframes][1792]: stream s = unique stream s % 256 starting 7 * (s // 256) frames in (numpy or torch)."""
+def tile_corpus(frames, stream_ids, nframes):
+    """[len(stream_ids)][nframes][1792]: global stream g = unique stream g % 256 starting 7 * (g // 256) frames in
+    (numpy or torch).  stream_ids: the global ids of this rank's shard (an int = the first so many streams)."""
     corpus = _corpus_mod()
-    base, idx = corpus.tile_index(nstreams, nframes)
+    ids = np.arange(stream_ids) if np.isscalar(stream_ids) else np.asarray(stream_ids)
+    base = ids % corpus.UNIQUE
+    idx = (np.arange(nframes)[None, :] + 7 * (ids // corpus.UNIQUE)[:, None]) % corpus.FRAMES
     if isinstance(frames, np.ndarray):
         return frames[base[:, None], idx]
     import torch
@@ -362,7 +365,11 @@ def run_gpu(args):
     uniq = unique_frames_gpu(eng, dev)                         # [256][313][1792] on the device, digest-checked
     es_bytes = nframes * FRAME_BYTES
     es = torch.zeros(es_bytes + 64, dtype=torch.uint8, device=dev)
-    es[:es_bytes].copy_(tile_corpus(uniq, S, F).reshape(-1))   # weak scaling: every rank decodes S streams
+    # weak scaling: the job is world x S streams (global ids 0 .. world*S-1, all of the same cost), cut by the
+    # sharder into one contiguous range per rank; every rank decodes ITS streams, no data-path collective
+    my_ids = shard.partition_streams(np.full(world * S, F, np.int64), world)[rank]
+    assert len(my_ids) == S
+    es[:es_bytes].copy_(tile_corpus(uniq, my_ids, F).reshape(-1))
     off = torch.arange(nframes + 1, dtype=torch.int64, device=dev) * FRAME_BYTES
     first = (torch.arange(S + 1, dtype=torch.int64, device=dev) * F).to(torch.int32)
     s16 = args.pcm == "s16"
@@ -412,7 +419,10 @@ def run_gpu(args):
 
     # sanity of the device result against the committed digest: energy of the first four unique streams as the
     # UNMODIFIED reference decoder produced them (tests/golden/c2_corpus.json)
-    if F == 313 and S >= 4:
+    # per-rank record for the shard report: first / last global stream id, energy of the whole shard's PCM
+    shard_energy = float((pcm.double() ** 2).sum().item()) / ((32768.0 ** 2) if s16 else 1.0)
+    recs = shard.gather_records([float(my_ids[0]), float(my_ids[-1]), shard_energy, float(nframes)])
+    if F == 313 and S >= 4 and rank == 0:
         want = _corpus_mod().load_digest()["energy_stereo_first4"]
         for k in range(4):
             got = float(((pcm[k * F * 3072:(k + 1) * F * 3072].double() / (32768.0 if s16 else 1.0)) ** 2).sum().item())
@@ -456,6 +466,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": nframes * algo},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "extra": extra,
+            "shards": {"partition": "shard.partition_streams: contiguous ranges of global stream ids (equal costs)",
+                       "ranks": [{"streams": [int(r[0]), int(r[1])], "frames": int(r[3]), "pcm_energy": r[2]} for r in recs]},
         }
         print(json.dumps(line))
     dec.close()

@@ -168,6 +168,10 @@ void a52_batch_set_max_frame_bytes (a52_batch_t * ctx, int nbytes);
  * pre-pass to plan the work units (slices of streams); 0 = derive it (default). */
 void a52_batch_set_max_stream_frames (a52_batch_t * ctx, int nframes);
 
+/* Bounds-checked builds (-DA52_BOUNDS_CHECK): code of the first violated address / index check of any decode
+ * launch of this process, 0 = none.  Regular builds carry no checks and return -2. */
+int a52_batch_violations (void);
+
 /* number of kernel launches issued by this context so far (bench bookkeeping) */
 long a52_batch_launch_count (a52_batch_t * ctx);
 /* average device time (ms) of the decode kernel over the launches since the

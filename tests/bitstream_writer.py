@@ -19,6 +19,13 @@ BITRATES = [32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 
 CPL_BAND = [31, 35, 37, 39, 41, 42, 43, 44, 45, 45, 46, 46, 47, 47, 48, 48]
 
 
+class Injected(Exception):
+    """Raised by the writer once a deliberately invalid field has been written: the rest of the frame is padding."""
+
+    def __init__(self, bw):
+        self.bw = bw
+
+
 class BitWriter:
     def __init__(self):
         self.bits = []
@@ -129,8 +136,15 @@ class StreamWriter:
             else:
                 bw.put(n, int(rng.randint(1 << n)))
 
-    def _write_exps(self, bw, arr, strategy, ngrps, start_exp, dest):
+    def _write_exps(self, bw, arr, strategy, ngrps, start_exp, dest, blk=-1):
         rep = 1 << (strategy - 1)
+        if arr == 0 and self._hit(blk, "exp_code"):
+            bw.put(7, 125 + int(self.rng.randint(3)))      # not a group code: exp_1[] adds 25 (parse.c:226-229)
+            raise Injected(bw)
+        if arr == 0 and self._hit(blk, "exp_range"):
+            for _ in range(ngrps):
+                bw.put(7, 124)                             # +2 +2 +2 per group: past 24 within three groups (:227-256)
+            raise Injected(bw)
         vals = _walk_exponents(self.rng, 3 * ngrps, start_exp, 0.4)
         prev = start_exp
         for g in range(ngrps):
@@ -148,14 +162,26 @@ class StreamWriter:
 
     # -- one frame ----------------------------------------------------------------
     def frame(self):
+        self.frame_no = getattr(self, "frame_no", -1) + 1
         for attempt in range(12):
             state = self._save()
             csnr = max(1, int(self.rng.randint(8, 40)) - 4 * attempt)
             try:
                 return self._frame(csnr)
+            except Injected as inj:
+                # the decoder stops at the injected field (a52_block returns 1): what follows is never read
+                if len(inj.bw) <= 8 * frame_bytes(self.fscod, self.frmsizecod):
+                    return inj.bw.tobytes(frame_bytes(self.fscod, self.frmsizecod))
+                self._restore(state)
             except AssertionError:
                 self._restore(state)
         raise RuntimeError("could not fit a frame")
+
+    def _hit(self, blk, site):
+        """inject = (frame, block, site): write an invalid value at that site (one of the `return 1` sites of
+        liba52's a52_block, parse.c:218-294, 600-701)."""
+        inj = getattr(self, "inject", None)
+        return inj is not None and inj == (self.frame_no, blk, site)
 
     def _save(self):
         return (self.rng.get_state(), self.exp.copy(), self.bap.copy(), list(self.endmant), self.cplinu,
@@ -231,6 +257,21 @@ class StreamWriter:
                     bw.put(1, 0)
             # coupling strategy
             cplstre = 1 if blk == 0 else int(rng.rand() < 0.25)
+            if self._hit(blk, "cpl_mono"):                     # coupling in a 1+1 or 1/0 frame (parse.c:611-613)
+                assert acmod < 2
+                bw.put(1, 1); bw.put(1, 1)
+                for ch in range(nfchans):
+                    bw.put(1, 1)
+                raise Injected(bw)
+            if self._hit(blk, "cpl_range"):                    # cplendf + 3 - cplbegf < 0 (parse.c:620-621)
+                assert acmod >= 2
+                bw.put(1, 1); bw.put(1, 1)
+                for ch in range(nfchans):
+                    bw.put(1, 1)
+                if acmod == 2:
+                    bw.put(1, 0)
+                bw.put(4, 12 + int(rng.randint(4))); bw.put(4, int(rng.randint(0, 9)))
+                raise Injected(bw)
             bw.put(1, cplstre)
             if cplstre:
                 cplinu = int(acmod >= 2 and rng.rand() < f["cpl"])
@@ -308,6 +349,9 @@ class StreamWriter:
                     if cplinu and self.chincpl[ch]:
                         self.endmant[ch] = cplstrt
                     else:
+                        if self._hit(blk, "chbwcod"):          # chbwcod > 60 (parse.c:697-698)
+                            bw.put(6, 61 + int(rng.randint(3)))
+                            raise Injected(bw)
                         bwc = int(rng.randint(0, 61))
                         bw.put(6, bwc)
                         self.endmant[ch] = 73 + 3 * bwc
@@ -323,7 +367,7 @@ class StreamWriter:
                     e0 = int(rng.randint(0, 12))
                     bw.put(4, e0)
                     self.exp[ch, 0] = e0
-                    self._write_exps(bw, ch, chexpstr[ch], ngrps, e0, 1)
+                    self._write_exps(bw, ch, chexpstr[ch], ngrps, e0, 1, blk)
                     bw.put(2, int(rng.randint(4)))
             if lfeexpstr:
                 e0 = int(rng.randint(0, 12))
@@ -357,6 +401,15 @@ class StreamWriter:
                     self.cplfleak, self.cplsleak = int(rng.randint(8)), int(rng.randint(8))
                     bw.put(3, self.cplfleak); bw.put(3, self.cplsleak)
                     self.cplleak_sent = True
+            if self._hit(blk, "deltba_len"):                   # a delta segment running past band 50 (parse.c:287-288)
+                bw.put(1, 1)
+                order = ([6] if cplinu else []) + list(range(nfchans))
+                for a in order:
+                    bw.put(2, 1)                               # new info for every array
+                bw.put(3, 1)                                   # two segments
+                bw.put(5, 31); bw.put(4, 3); bw.put(3, 5)      # band 31, 3 bands: fine
+                bw.put(5, 10); bw.put(4, 9); bw.put(3, 2)      # band 44 + 9 >= 50
+                raise Injected(bw)
             if rng.rand() < f["deltba"]:
                 bw.put(1, 1)
                 order = ([6] if cplinu else []) + list(range(nfchans))
@@ -425,8 +478,10 @@ class StreamWriter:
         return bw.tobytes(nbytes)
 
 
-def make_stream(seed, acmod, lfeon, nframes, alloc, fscod=0, frmsizecod=36, bsid=8, features=None):
-    """Concatenated frames of one synthetic stream (uint8 array) and its frame size."""
+def make_stream(seed, acmod, lfeon, nframes, alloc, fscod=0, frmsizecod=36, bsid=8, features=None, inject=None):
+    """Concatenated frames of one synthetic stream (uint8 array) and its frame size.
+    inject = (frame, block, site): that block carries one deliberately invalid field (see StreamWriter._hit)."""
     w = StreamWriter(seed, acmod, lfeon, fscod, frmsizecod, bsid, alloc, features)
+    w.inject = inject
     frames = [w.frame() for _ in range(nframes)]
     return np.concatenate(frames), frame_bytes(fscod, frmsizecod)

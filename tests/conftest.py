@@ -66,3 +66,18 @@ def decoder(engine):
     dec = engine.BatchDecoder(0)
     yield dec
     dec.close()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Under a bounds-checked build of the library (tools/gpu_checked.sh) report what the device checks saw."""
+    if not os.environ.get("A52_B200_LIB"):
+        return
+    try:
+        import __graft_entry__ as ge
+        L = ge.load_engine().load_library()
+        v = L.a52_batch_violations()
+        print("\n[a52_batch_violations] first violated device check: %d (0 = none, -2 = build without checks)" % v)
+        if v not in (0, -2):
+            session.exitstatus = 1
+    except Exception as e:  # noqa
+        print("\n[a52_batch_violations] unavailable: %r" % (e,))

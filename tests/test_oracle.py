@@ -225,3 +225,20 @@ def test_bias_placement_oracle_vs_reference(oracle, ref, acmod, flags):
         n1, a = oracle.decode_stream(es, flags, 1.0, bias)
         n2, b = ref.decode_stream(es, flags, 1.0, bias)
         assert n1 == n2 == 6 and (a.view(np.uint32) == b.view(np.uint32)).all(), (acmod, flags, bias)
+
+
+def test_oracle_error_returns_match_reference_on_crafted_fields():
+    """Every `return 1` site of a52_block (parse.c:218-294, 600-701), hit by a deliberately invalid field: the oracle
+    port stops in the same block as the unmodified reference."""
+    import pytest
+    from refbind import RefA52, Oracle, have_ref, A52_STEREO
+    from bitstream_writer import make_stream
+    if not have_ref():
+        pytest.skip("reference not built")
+    ref, ora = RefA52(), Oracle()
+    for site, acmod, lfe, blk in [("chbwcod", 7, 1, 0), ("exp_code", 2, 0, 0), ("exp_range", 7, 1, 0), ("cpl_range", 5, 0, 3),
+                                  ("cpl_mono", 0, 1, 2), ("cpl_mono", 1, 0, 4), ("deltba_len", 7, 1, 5), ("deltba_len", 2, 0, 0)]:
+        es, fb = make_stream(900 + 7 * acmod + blk, acmod, lfe, 3, ora.bit_allocate, frmsizecod=30, inject=(1, blk, site))
+        a = [f["status"] for f in ref.decode_dump(es, req_flags=A52_STEREO)]
+        b = [f["status"] for f in ora.decode_dump(es, req_flags=A52_STEREO)]
+        assert a == b == [0, 2 + blk, 0], (site, acmod, blk, a, b)

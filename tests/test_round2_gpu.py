@@ -131,3 +131,64 @@ def test_dynrng_callback_like_liba52(engine, oracle):
     assert len(seen["ref"]) > 10 and seen["gpu"] == seen["ref"]
     d = outs["gpu"].astype(np.float64) - outs["ref"]
     assert np.sqrt((d * d).mean()) / np.sqrt((outs["ref"].astype(np.float64) ** 2).mean()) < 1e-5
+
+
+# ---------------------------------------------------------------------------
+# every `return 1` of a52_block, triggered by a crafted field (parse.c:218-294, 600-701)
+# ---------------------------------------------------------------------------
+ERROR_SITES = [
+    ("chbwcod", 7, 1, 0), ("chbwcod", 3, 0, 0), ("exp_code", 7, 1, 0), ("exp_code", 2, 0, 0), ("exp_range", 7, 1, 0),
+    ("exp_range", 1, 0, 0), ("cpl_range", 7, 1, 1), ("cpl_range", 2, 0, 0), ("cpl_range", 5, 0, 3), ("cpl_mono", 1, 0, 4),
+    ("cpl_mono", 0, 0, 0), ("cpl_mono", 0, 1, 2), ("deltba_len", 7, 1, 5), ("deltba_len", 3, 0, 2), ("deltba_len", 2, 0, 0),
+]
+
+
+@pytest.mark.parametrize("site,acmod,lfe,blk", ERROR_SITES)
+def test_every_error_return_of_a52_block(decoder, engine, oracle, site, acmod, lfe, blk):
+    """A frame whose block `blk` carries one invalid field fails exactly there (status 16 + blk, what a52_block
+    returning 1 in that block means), its first `blk` blocks and its neighbours decode as in the reference."""
+    from refbind import RefA52
+    chk = RefA52() if have_ref() else oracle
+    es, fb = make_stream(900 + 7 * acmod + blk, acmod, lfe, 3, oracle.bit_allocate, frmsizecod=30, inject=(1, blk, site))
+    flags = A52_STEREO
+    dump = chk.decode_dump(es, req_flags=flags)
+    want = [0 if f["status"] == 0 else (2 if f["status"] == 1 else 16 + f["status"] - 2) for f in dump]
+    assert want == [0, 16 + blk, 0], (site, want)               # the crafted field is reached and refused
+    off = np.arange(3, dtype=np.uint64) * fb
+    out = decoder.decode_host(es, off, np.array([0, 3], np.uint32), flags)
+    assert out["status"].tolist() == want
+    # frame 0 and the good blocks of frame 1 carry the reference's samples, the rest of frame 1 is silence
+    ref0 = np.stack([b["pcm"] for b in dump[0]["blocks"]])
+    d = out["pcm"][0].reshape(6, 2, 256).astype(np.float64) - ref0
+    assert np.sqrt((d * d).mean()) / max(np.sqrt((ref0.astype(np.float64) ** 2).mean()), 1e-30) < 1e-5
+    got1 = out["pcm"][1].reshape(6, 2, 256)
+    for b in range(blk):
+        r = dump[1]["blocks"][b]["pcm"]
+        dd = got1[b].astype(np.float64) - r
+        assert np.sqrt((dd * dd).mean()) <= 1e-5 * max(np.sqrt((r.astype(np.float64) ** 2).mean()), 1e-30) + 1e-9
+    assert not got1[blk:].any()
+
+
+# ---------------------------------------------------------------------------
+# coefficient bit patterns on feature-rich streams (coupling, rematrixing, block switching, delta bit allocation)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("acmod,lfe,flags,cod", [(7, 1, A52_3F2R | A52_LFE, 36), (2, 0, A52_STEREO, 24), (5, 1, 5 | A52_LFE, 33)])
+def test_feature_stream_coefficients_are_bit_exact(decoder, engine, oracle, acmod, lfe, flags, cod):
+    """No downmix, compression off: every dequantised coefficient (coupled bins and rematrixed bands included) has the
+    reference's bit pattern - the mantissa integers, the dither draws and the coupling arithmetic are the same."""
+    es, fb = make_stream(3100 + acmod, acmod, lfe, 4, oracle.bit_allocate, frmsizecod=cod,
+                         features=dict(blksw=0.4, cpl=0.9, deltba=0.2, dynrng=0.5))
+    off = np.arange(4, dtype=np.uint64) * fb
+    out = decoder.decode_host(es, off, np.array([0, 4], np.uint32), flags, drc=engine.DRC_OFF, want_debug=True)
+    dump = oracle.decode_dump(es, req_flags=flags, dynrng_off=True)
+    assert (out["status"] == 0).all()
+    nfch = [2, 1, 2, 3, 3, 4, 4, 5][acmod]
+    bad = 0
+    for f in range(4):
+        for b in range(6):
+            blk = dump[f]["blocks"][b]
+            g, r = out["coef"][f, b], blk["coef"]
+            for ch in list(range(nfch)) + ([5] if lfe else []):
+                # (value equality: a rematrixed or phase-flipped zero may carry either sign)
+                bad += int((g[ch] != r[ch]).sum())
+    assert bad == 0, bad
