@@ -2396,3 +2396,4 @@ a52_decode_kernel(const DecodeParams P)
 }  // namespace a52
 
 #include "a52_host.inl"
+#include "a52_imdct_ab.inl"

@@ -444,6 +444,8 @@ struct a52_batch_s {
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
     int slice_mode = 0;            // 0 = choose, 1 = slices of a stream chained by the carry record, 2 = frame-independent
+    int zero_copy = 1;             // host-pointer calls: the kernel stores PCM straight into a pinned, mapped caller
+                                   // buffer (A52_B200_ZERO_COPY=0: always stage in device memory and copy)
     const float* drc_table = nullptr;   // a52_batch_set_drc_table: ranges for the next A52_DRC_TABLE call
     uint16_t* d_dither = nullptr;
     int host_chunk_streams = 128;  // streams per pipelined chunk of a host-pointer call (A52_B200_HOST_CHUNK_STREAMS)
@@ -507,6 +509,8 @@ a52_batch_t* a52_batch_create(int device)
     if (g) ctx->warps_per_cta = atoi(g);
     const char* sf = getenv("A52_B200_SLICE_FRAMES");
     if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
+    const char* zc = getenv("A52_B200_ZERO_COPY");
+    if (zc) ctx->zero_copy = atoi(zc);
     const char* sm = getenv("A52_B200_SLICE_MODE");
     if (sm && atoi(sm) >= 0 && atoi(sm) <= 2) ctx->slice_mode = atoi(sm);
     const char* hc = getenv("A52_B200_HOST_CHUNK_STREAMS");
@@ -892,14 +896,43 @@ int a52_batch_scan(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const u
     return 0;
 }
 
+static int batch_decode_impl(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const uint64_t* frame_off,
+                             int nframes, const uint32_t* stream_first, int nstreams, int req_flags, float level,
+                             float bias, int drc_mode, int out_fmt, void* pcm_out, int32_t* frame_status,
+                             int32_t* frame_flags, a52_stream_carry_t* carry, const a52_batch_debug_t* debug,
+                             int mem_flags, void* cuda_stream);
+
 int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const uint64_t* frame_off,
                      int nframes, const uint32_t* stream_first, int nstreams, int req_flags, float level,
                      float bias, int drc_mode, int out_fmt, void* pcm_out, int32_t* frame_status,
                      int32_t* frame_flags, a52_stream_carry_t* carry, const a52_batch_debug_t* debug,
                      int mem_flags, void* cuda_stream)
 {
-    using namespace a52;
     if (!ctx) return -1;
+    const int rc = batch_decode_impl(ctx, es, es_bytes, frame_off, nframes, stream_first, nstreams, req_flags, level, bias,
+                                     drc_mode, out_fmt, pcm_out, frame_status, frame_flags, carry, debug, mem_flags,
+                                     cuda_stream);
+    if (rc && !(mem_flags & A52_BATCH_DEVICE_PTRS)) {
+        // a host-pointer call that fails half way may have copies in flight from / into the caller's buffers:
+        // let them settle before the caller gets its buffers back
+        if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+        if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
+        if (ctx->s_run) cudaStreamSynchronize(ctx->s_run);
+        for (int i = 0; i < 8; i++)
+            if (ctx->s_runs[i]) cudaStreamSynchronize(ctx->s_runs[i]);
+        if (cuda_stream) cudaStreamSynchronize((cudaStream_t)cuda_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int batch_decode_impl(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const uint64_t* frame_off,
+                             int nframes, const uint32_t* stream_first, int nstreams, int req_flags, float level,
+                             float bias, int drc_mode, int out_fmt, void* pcm_out, int32_t* frame_status,
+                             int32_t* frame_flags, a52_stream_carry_t* carry, const a52_batch_debug_t* debug,
+                             int mem_flags, void* cuda_stream)
+{
+    using namespace a52;
     ctx->err[0] = 0;
     if (nframes < 0 || nstreams < 0 || (req_flags & M_MASK) > M_DOLBY || out_fmt < 0 || out_fmt > A52_PCM_S16_WAV) {
         snprintf(ctx->err, sizeof(ctx->err), "bad argument");
@@ -978,18 +1011,35 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         }
     }
     cudaStream_t s_in = ctx->s_in, s_out = ctx->s_out, s_run = st ? st : ctx->s_run;
-    int maxlen = 0;
-    for (int i = 0; i < nframes; i++) {
-        int fl, sr, br;
-        if (frame_off[i] + 7 <= es_bytes) {
-            int len = host_syncinfo(es + frame_off[i], &fl, &sr, &br);
-            if (len > maxlen) maxlen = len;
+    // longest frame of the batch: the caller's bound when there is one (a52_batch_set_max_frame_bytes; a frame
+    // longer than that is refused by the kernel, not truncated), else one pass over the headers - a cache miss per
+    // frame on a large batch, all of it before the first byte moves
+    int maxlen = ctx->max_frame_hint;
+    if (maxlen <= 0)
+        for (int i = 0; i < nframes; i++) {
+            int fl, sr, br;
+            if (frame_off[i] + 7 <= es_bytes) {
+                int len = host_syncinfo(es + frame_off[i], &fl, &sr, &br);
+                if (len > maxlen) maxlen = len;
+            }
         }
-    }
     if (ensure(ctx, ctx->b_es, es_bytes + 64)) return -1;
     if (ensure(ctx, ctx->b_off, (size_t)(nframes + 1) * 8)) return -1;
     if (ensure(ctx, ctx->b_first, (size_t)(nstreams + 1) * 4)) return -1;
-    if (ensure(ctx, ctx->b_pcm, stride * nframes)) return -1;
+    // A pinned (page-locked, hence mapped) caller buffer takes the PCM straight from the kernel's stores: no staging
+    // buffer, no device-to-host copy pass, and the transfer overlaps the decode at the granularity of a block.
+    // (Small batches only - the drop-in a52_block path, short files: there it saves a copy and a synchronisation.
+    // Large ones go through the copy engine, which moves 4 % more per second than the SMs' stores do over the same
+    // link: 301.6 against 311.5 ms for the 18 GB of bench.py's step; A52_B200_ZERO_COPY=2 forces it regardless.)
+    uint8_t* pcm_alias = nullptr;
+    if (ctx->zero_copy == 2 || (ctx->zero_copy && stride * (size_t)nframes <= ((size_t)64 << 20))) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, pcm_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            pcm_alias = (uint8_t*)at.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    if (!pcm_alias && ensure(ctx, ctx->b_pcm, stride * nframes)) return -1;
     if (ensure(ctx, ctx->b_status, (size_t)nframes * 4)) return -1;
     if (ensure(ctx, ctx->b_flags, (size_t)nframes * 4)) return -1;
     A52_CUDA(cudaMemsetAsync((uint8_t*)ctx->b_es.p + es_bytes, 0, 64, s_run));
@@ -999,7 +1049,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
     A52_CUDA(cudaMemcpyAsync(ctx->b_first.p, stream_first, (size_t)(nstreams + 1) * 4, cudaMemcpyHostToDevice, s_run));
     P.es = (const uint8_t*)ctx->b_es.p;
     P.frame_off = (const uint64_t*)ctx->b_off.p;
-    P.pcm = (uint8_t*)ctx->b_pcm.p;
+    P.pcm = pcm_alias ? pcm_alias : (uint8_t*)ctx->b_pcm.p;
     P.status = (int32_t*)ctx->b_status.p;
     P.frame_flags = (int32_t*)ctx->b_flags.p;
     if (carry) {
@@ -1104,7 +1154,7 @@ int a52_batch_decode(a52_batch_t* ctx, const uint8_t* es, size_t es_bytes, const
         if (rc) return rc;
         A52_CUDA(cudaEventRecord(ctx->ev_run[cidx], s_k));
         A52_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_run[cidx], 0));
-        if (fb > fa)
+        if (fb > fa && !pcm_alias)
             A52_CUDA(cudaMemcpyAsync((uint8_t*)pcm_out + (size_t)fa * stride, Pc.pcm + (size_t)fa * stride,
                                      (size_t)(fb - fa) * stride, cudaMemcpyDeviceToHost, s_out));
     }

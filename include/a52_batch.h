@@ -172,6 +172,12 @@ void a52_batch_set_max_stream_frames (a52_batch_t * ctx, int nframes);
  * launch of this process, 0 = none.  Regular builds carry no checks and return -2. */
 int a52_batch_violations (void);
 
+/* Experiment entry (profiles/r02_imdct_tc_ab.json): the IMDCT-512 of nplanes coefficient planes,
+ * global to global, by the production FFT transform (variant 0) or as a 3xTF32 tensor-core GEMM (variant 1; afrag = the
+ * transform matrix in mma fragment order, built by tools/dev_imdct_ab.py).  Not part of the decode path. */
+int a52_ab_imdct (a52_batch_t * ctx, int variant, const float * x, float * y, int nplanes, const void * afrag,
+		  void * cuda_stream);
+
 /* number of kernel launches issued by this context so far (bench bookkeeping) */
 long a52_batch_launch_count (a52_batch_t * ctx);
 /* average device time (ms) of the decode kernel over the launches since the
