@@ -30,7 +30,7 @@ EXPORTS = [
     "a52_init", "a52_samples", "a52_syncinfo", "a52_frame", "a52_dynrng", "a52_block", "a52_free",
     "a52_batch_create", "a52_batch_destroy", "a52_batch_last_error", "a52_batch_index", "a52_batch_index_device",
     "a52_batch_frame_stride", "a52_batch_decode", "a52_batch_set_max_frame_bytes", "a52_batch_set_max_stream_frames",
-    "a52_batch_launch_count", "a52_batch_kernel_ms", "a52_batch_scan", "a52_batch_set_drc_table", "a52_batch_set_slice_mode", "a52_batch_violations", "a52_ab_imdct",
+    "a52_batch_launch_count", "a52_batch_kernel_ms", "a52_batch_scan", "a52_batch_set_drc_table", "a52_batch_set_slice_mode", "a52_batch_violations", "a52_ab_imdct", "a52_ab_fp32_peak",
     "AC3_encode_init", "AC3_encode_frame",
     "ac3_batch_create", "ac3_batch_destroy", "ac3_batch_last_error", "ac3_batch_frame_bytes",
     "ac3_batch_encode", "ac3_batch_launch_count", "ac3_batch_kernel_ms",
@@ -95,6 +95,8 @@ def load_library():
                                  C.c_void_p, C.c_int, C.c_void_p]
     L.a52_batch_set_drc_table.argtypes = [C.c_void_p, C.c_void_p]
     L.a52_batch_set_slice_mode.argtypes = [C.c_void_p, C.c_int]
+    L.a52_ab_fp32_peak.restype = C.c_double
+    L.a52_ab_fp32_peak.argtypes = [C.c_void_p]
     L.a52_init.restype = C.c_void_p
     L.a52_init.argtypes = [C.c_uint32]
     L.a52_samples.restype = C.POINTER(C.c_float)

@@ -116,6 +116,7 @@ struct DecodeParams {
     // frame-independent slices: every slice of a stream starts on its own, one frame early (that frame rebuilds the
     // overlap-add tails and the tail representation; its PCM goes to a scratch frame), with the dither generator
     // position a scan pass and a prefix sum gave it.  No slice waits for another.
+    int             lockstep;        // pairs of a CTA start every frame together (see the frame gate in the kernel)
     int             indep;
     const uint32_t* slice_dither;    // [nstreams][nslices] generator position at the slice's first decoded frame
     uint8_t*        scratch_pcm;     // [resident pairs][frame_stride]

@@ -176,6 +176,8 @@ constexpr int kPlanGroups = 768, kPlanPlain = 1536, kPlanZeros = 2560;
 constexpr int kPlanPlainOff = kPlanGroups * 16, kPlanZeroOff = kPlanPlainOff + kPlanPlain * 8;
 constexpr int kPlanBytes = kPlanZeroOff + kPlanZeros * 4;
 
+constexpr int kTablesBytes = ((int)sizeof(Tables) + 16 + 127) & ~127;       // the tables + the CTA's frame gate word
+
 __host__ __device__ inline int pair_smem_bytes(int fbuf_bytes, int nplanes)
 {
     return align128((nplanes == 6 ? PairLayout<6>::fbuf : PairLayout<5>::fbuf) + fbuf_bytes);
@@ -1687,6 +1689,16 @@ a52_decode_kernel(const DecodeParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     Tables& T = *reinterpret_cast<Tables*>(smem);
+    // Frame gate: the pairs of a CTA that are inside a frame loop start every frame together.  The kernel is bound by
+    // instruction fetch - its pairs are all at different places of a program several times the size of the
+    // instruction cache - and the per-frame work (header, block 0's side information, exponents, bit allocation,
+    // locate passes) is the largest part of that program that a pair runs only once per frame: started together,
+    // one pair's fetches serve the others.  One word: [7:0] arrived, [15:8] members, [31:16] generation.
+    // Streams whose blocks are mostly of the expensive kind (new exponents / allocation in most blocks: what the last
+    // frame looked like decides) also start every BLOCK together, through a second gate of their own.
+    unsigned int* const gates = reinterpret_cast<unsigned int*>(smem + sizeof(Tables));  // (inside the tables' padding)
+    unsigned int& gate = gates[0];
+    unsigned int& bgate = gates[1];
     const int tid = threadIdx.x;
     const int wid = tid >> 5, lane = tid & 31, pair = wid >> 1, w = wid & 1;
     const int gt = w * 32 + lane;
@@ -1696,7 +1708,8 @@ a52_decode_kernel(const DecodeParams P)
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
         for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    const PairPtrs G = carve_pair<NPL>(smem + align128((int)sizeof(Tables)) + pair * P.warp_bytes);
+    if (tid == 0) { gates[0] = 0; gates[1] = 0; }
+    const PairPtrs G = carve_pair<NPL>(smem + kTablesBytes + pair * P.warp_bytes);
     GroupCtl* c = G.ctl;
     uint32_t* const W = G.fbuf;
     const PairSync sync{pair + 1};
@@ -1765,9 +1778,46 @@ a52_decode_kernel(const DecodeParams P)
             dither_index = __ldg(P.slice_dither + (size_t)s * P.nslices + slice) % kDitherPeriod;
         }
         if (gt == 0 && fl < f1) issue_frame_load(P, G, fl);
+        const bool gated = P.lockstep && fl < f1;
+        if (gated && gt == 0) atomicAdd(&gate, 1u << 8);         // a member from here to the end of the unit's frames
         sync();
 
+        // arrive at a gate (thread 0 of the pair), optionally wait for the round to complete; leave a gate
+        auto gate_arrive = [&](unsigned int& g, bool wait) {
+            if (gt == 0) {
+                unsigned int old = *(volatile unsigned int*)&g, seen;
+                bool released;
+                do {
+                    seen = old;
+                    const unsigned int cnt = (seen & 255u) + 1u, act = (seen >> 8) & 255u;
+                    released = cnt >= act;
+                    const unsigned int nw = released ? ((((seen >> 16) + 1u) & 0xffffu) << 16) | (act << 8) : seen + 1u;
+                    old = atomicCAS(&g, seen, nw);
+                } while (old != seen);
+                if (!released && wait)
+                    while ((*(volatile unsigned int*)&g >> 16) == (seen >> 16)) __nanosleep(100);
+            }
+            if (wait) sync();
+        };
+        auto gate_leave = [&](unsigned int& g) {
+            if (gt == 0) {
+                // if everyone who stays has already arrived, let them go
+                unsigned int old = *(volatile unsigned int*)&g, seen;
+                do {
+                    seen = old;
+                    const unsigned int cnt = seen & 255u, act = ((seen >> 8) & 255u) - 1u;
+                    const unsigned int nw = (cnt && cnt >= act) ? ((((seen >> 16) + 1u) & 0xffffu) << 16) | (act << 8)
+                                                                : (seen & ~0xff00u) | (act << 8);
+                    old = atomicCAS(&g, seen, nw);
+                } while (old != seen);
+            }
+        };
+        int cold_prev = 0;                        // expensive blocks among blocks 1..5 of the unit's previous frame
         for (uint32_t f = fl; f < f1; f++) {
+            if (gated) gate_arrive(gate, true);
+            const bool bgated = gated && cold_prev >= 3;      // this frame's blocks go through the block gate
+            if (bgated && gt == 0) atomicAdd(&bgate, 1u << 8);
+            int cold_now = 0, gates_passed = 0;
             const bool shadow = lookback && f == fl;          // decoded for its state only
             uint32_t frame_draws = 0;
             const uint64_t off = P.frame_off[f];
@@ -1817,6 +1867,7 @@ a52_decode_kernel(const DecodeParams P)
             if (frame_ok)
             for (;; blk++) {
                 const bool more = blk < 6;
+                if (bgated && blk > 0 && more) { gate_arrive(bgate, true); gates_passed++; }
                 // ================= P (block blk) | T (block blk - 1) =================
                 if (more && gt == 0) {
                     c->cur_blk = f * 6u + (uint32_t)blk;
@@ -1973,6 +2024,7 @@ a52_decode_kernel(const DecodeParams P)
                 // and allocation reused: the rule, not the exception) skips the passes altogether and lets the
                 // unpack stage add the shift.
                 const bool rep = c->repeat != 0;
+                if (!rep && blk > 0) cold_now++;
                 const uint32_t bitpos = c->bitpos;
                 uint32_t ta, tb, tz, mant_bits, pos_delta = 0;
                 for (int i = gt; i < NPL * 256 / 4; i += NT)
@@ -2348,6 +2400,11 @@ a52_decode_kernel(const DecodeParams P)
                 sync();
             }   // blocks
 
+            if (bgated) {
+                for (; gates_passed < 5; gates_passed++) gate_arrive(bgate, false);    // a frame cut short still counts
+                gate_leave(bgate);
+            }
+            cold_prev = cold_now;
             if (frame_ok && blk < 6) frame_status = 16 + blk;
             if (P.scan_only) {
                 if (gt == 0) {
@@ -2374,6 +2431,7 @@ a52_decode_kernel(const DecodeParams P)
             if (!next_issued && f + 1 < f1 && gt == 0) issue_frame_load(P, G, f + 1);
             sync();
         }   // frames
+        if (gated) gate_leave(gate);
 
         // the state after the unit's last frame: for the next slice of the chain, or (frame-independent slices: from
         // the slice that holds the stream's last frame) for the caller

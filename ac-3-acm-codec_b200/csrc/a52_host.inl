@@ -444,6 +444,7 @@ struct a52_batch_s {
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
     int slice_mode = 0;            // 0 = choose, 1 = slices of a stream chained by the carry record, 2 = frame-independent
+    int lockstep = 1;              // the pairs of a CTA start every frame together (A52_B200_LOCKSTEP=0 turns it off)
     int zero_copy = 1;             // host-pointer calls: the kernel stores PCM straight into a pinned, mapped caller
                                    // buffer (A52_B200_ZERO_COPY=0: always stage in device memory and copy)
     const float* drc_table = nullptr;   // a52_batch_set_drc_table: ranges for the next A52_DRC_TABLE call
@@ -509,6 +510,8 @@ a52_batch_t* a52_batch_create(int device)
     if (g) ctx->warps_per_cta = atoi(g);
     const char* sf = getenv("A52_B200_SLICE_FRAMES");
     if (sf && atoi(sf) > 0) ctx->slice_frames = atoi(sf);
+    const char* lk = getenv("A52_B200_LOCKSTEP");
+    if (lk) ctx->lockstep = atoi(lk);
     const char* zc = getenv("A52_B200_ZERO_COPY");
     if (zc) ctx->zero_copy = atoi(zc);
     const char* sm = getenv("A52_B200_SLICE_MODE");
@@ -669,6 +672,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.nslices = 1;
     P.carry_init = P.carry != nullptr;
     P.slice_done = nullptr;
+    P.lockstep = ctx->lockstep;
     P.scan_only = run_mode == RUN_SCAN;
     P.indep = run_mode == RUN_INDEP;
     if (run_mode != RUN_CHAINED) {
@@ -700,7 +704,7 @@ static int launch_decode(a52_batch_t* ctx, a52::DecodeParams& P, int nframes, in
     P.warp_bytes = pair_smem_bytes(P.fbuf_bytes, P.nplanes);
     P.dither_seq = ctx->d_dither;
     P.work_counter = ctx->d_counter + counter_slot;
-    const int tables = align128((int)sizeof(Tables));
+    const int tables = kTablesBytes;
     int fit = (227 * 1024 - tables) / P.warp_bytes;
     const int fit_max = kMaxPairsPerCta;
     if (fit > fit_max) fit = fit_max;

@@ -121,6 +121,23 @@ a52_ab_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int nplane
     }
 }
 
+// FP32 peak of the device, measured (SURVEY.md section 8d asks for it instead of the nominal figure): eight independent
+// FMA chains per thread, nothing else in the loop.
+__global__ void __launch_bounds__(256) a52_ab_fma_kernel(float* out, int iters, float a, float b)
+{
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (float)(threadIdx.x + k);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = fmaf(v[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += v[k];
+    if (s == 12345.678f) out[0] = s;             // keeps the chains alive
+}
+
 }  // namespace a52
 
 #pragma GCC visibility push(default)
@@ -143,6 +160,29 @@ int a52_ab_imdct(a52_batch_t* ctx, int variant, const float* x, float* y, int np
         a52_ab_mma_kernel<<<ctx->num_sms, 256, smem, st>>>(x, y, nplanes, (const uint4*)afrag);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// Measured FP32 FMA throughput of the device in TFLOP/s (2 flops per FMA), CUDA events around 10 launches.
+double a52_ab_fp32_peak(a52_batch_t* ctx)
+{
+    using namespace a52;
+    if (!ctx) return -1.0;
+    float* d = nullptr;
+    if (cudaMalloc(&d, 256) != cudaSuccess) return -1.0;
+    const int iters = 20000, blocks = ctx->num_sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    a52_ab_fma_kernel<<<blocks, 256>>>(d, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e0);
+    for (int r = 0; r < 10; r++) a52_ab_fma_kernel<<<blocks, 256>>>(d, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    if (ms <= 0) return -1.0;
+    return 10.0 * (double)blocks * 256 * 8 * (double)iters * 2.0 / (ms * 1e-3) / 1e12;
 }
 
 }  // extern "C"

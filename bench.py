@@ -448,6 +448,8 @@ def run_gpu(args):
         peak = float(peaks["hbm_gbs"]) if peaks and peaks.get("hbm_gbs") else 6650.0
         if peaks and peaks.get("hbm_gbs"):
             peak_src = "measured"
+        # the other roofline of SURVEY.md 8(d): 79.5 kFLOP per frame against the MEASURED FP32 FMA peak of this GPU
+        fp32_peak = float(eng.load_library().a52_ab_fp32_peak(dec.ctx))
         algo = FRAME_BYTES + (PCM_BYTES // 2 if s16 else PCM_BYTES)
         achieved = nframes * algo / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         traffic = None
@@ -463,7 +465,11 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "a52_decode_kernel", "kernel_ms": kms, "kernel_launches_timed": kn,
-                         "algorithmic_bytes_per_launch": nframes * algo},
+                         "algorithmic_bytes_per_launch": nframes * algo,
+                         "fp32": {"peak_tflops_measured": fp32_peak, "algorithmic_flop_per_frame": 79500,
+                                  "achieved_tflops": nframes * 79500 / (kms / 1e3) / 1e12 if kms > 0 else 0.0,
+                                  "frac": (nframes * 79500 / (kms / 1e3) / 1e12 / fp32_peak) if (kms > 0 and fp32_peak > 0) else None,
+                                  "note": "HBM is the slower roofline of the two: frac above is against it"}},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "extra": extra,
             "shards": {"partition": "shard.partition_streams: contiguous ranges of global stream ids (equal costs)",

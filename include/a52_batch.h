@@ -178,6 +178,9 @@ int a52_batch_violations (void);
 int a52_ab_imdct (a52_batch_t * ctx, int variant, const float * x, float * y, int nplanes, const void * afrag,
 		  void * cuda_stream);
 
+/* Measured FP32 FMA peak of the context's device in TFLOP/s (a register-only FMA loop; for bench.py's FP32 roofline). */
+double a52_ab_fp32_peak (a52_batch_t * ctx);
+
 /* number of kernel launches issued by this context so far (bench bookkeeping) */
 long a52_batch_launch_count (a52_batch_t * ctx);
 /* average device time (ms) of the decode kernel over the launches since the
