@@ -1709,7 +1709,11 @@ a52_decode_kernel(const DecodeParams P)
         for (int i = tid; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     }
     if (tid == 0) { gates[0] = 0; gates[1] = 0; }
-    const PairPtrs G = carve_pair<NPL>(smem + kTablesBytes + pair * P.warp_bytes);
+    // (the pair's offset is pinned in a register: left to itself the compiler re-derives it - a constant-bank load
+    // and a multiply - in front of most shared-memory accesses)
+    uint32_t pair_off;
+    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(pair_off) : "r"((uint32_t)pair), "r"((uint32_t)P.warp_bytes));
+    const PairPtrs G = carve_pair<NPL>(smem + kTablesBytes + pair_off);
     GroupCtl* c = G.ctl;
     uint32_t* const W = G.fbuf;
     const PairSync sync{pair + 1};
@@ -1795,7 +1799,7 @@ a52_decode_kernel(const DecodeParams P)
                     old = atomicCAS(&g, seen, nw);
                 } while (old != seen);
                 if (!released && wait)
-                    while ((*(volatile unsigned int*)&g >> 16) == (seen >> 16)) __nanosleep(100);
+                    while ((*(volatile unsigned int*)&g >> 16) == (seen >> 16)) __nanosleep(400);
             }
             if (wait) sync();
         };
