@@ -1492,19 +1492,25 @@ struct PairPtrs : WarpPtrs {
     uint32_t* xch;     // [2][8] scan totals of the two warps
 };
 
+// The pair's pointers are built from ONE pinned 32-bit shared address (an opaque register): the compiler then addresses
+// every field as that register plus an immediate.  Built from the generic `smem + offset` it re-derives the shared
+// window base (S2UR CgaCtaId, UMOV, ULEA) in front of most accesses - 500 warp instructions per frame.
+template <class T>
+__device__ __forceinline__ T* shared_ptr_at(uint32_t sa) { return reinterpret_cast<T*>(__cvta_shared_to_generic((size_t)sa)); }
+
 template <int NPL>
-__device__ __forceinline__ PairPtrs carve_pair(uint8_t* base)
+__device__ __forceinline__ PairPtrs carve_pair(uint32_t base_sa)
 {
     using Lay = PairLayout<NPL>;
     PairPtrs g;
-    g.plane = reinterpret_cast<float*>(base + Lay::plane);
-    g.delay = reinterpret_cast<float*>(base + Lay::delay);
-    g.ctl = reinterpret_cast<GroupCtl*>(base + Lay::ctl);
-    g.exp = base + Lay::exp;
-    g.bap = base + Lay::bap;
-    g.xch = reinterpret_cast<uint32_t*>(base + Lay::xch);
-    g.mbar = reinterpret_cast<uint64_t*>(base + Lay::mbar);
-    g.fbuf = reinterpret_cast<uint32_t*>(base + Lay::fbuf);
+    g.plane = shared_ptr_at<float>(base_sa + Lay::plane);
+    g.delay = shared_ptr_at<float>(base_sa + Lay::delay);
+    g.ctl = shared_ptr_at<GroupCtl>(base_sa + Lay::ctl);
+    g.exp = shared_ptr_at<uint8_t>(base_sa + Lay::exp);
+    g.bap = shared_ptr_at<uint8_t>(base_sa + Lay::bap);
+    g.xch = shared_ptr_at<uint32_t>(base_sa + Lay::xch);
+    g.mbar = shared_ptr_at<uint64_t>(base_sa + Lay::mbar);
+    g.fbuf = shared_ptr_at<uint32_t>(base_sa + Lay::fbuf);
     return g;
 }
 
@@ -1711,9 +1717,10 @@ a52_decode_kernel(const DecodeParams P)
     if (tid == 0) { gates[0] = 0; gates[1] = 0; }
     // (the pair's offset is pinned in a register: left to itself the compiler re-derives it - a constant-bank load
     // and a multiply - in front of most shared-memory accesses)
-    uint32_t pair_off;
-    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(pair_off) : "r"((uint32_t)pair), "r"((uint32_t)P.warp_bytes));
-    const PairPtrs G = carve_pair<NPL>(smem + kTablesBytes + pair_off);
+    uint32_t pair_sa;
+    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(pair_sa)
+                 : "r"((uint32_t)pair), "r"((uint32_t)P.warp_bytes), "r"(smem_u32(smem) + (uint32_t)kTablesBytes));
+    const PairPtrs G = carve_pair<NPL>(pair_sa);
     GroupCtl* c = G.ctl;
     uint32_t* const W = G.fbuf;
     const PairSync sync{pair + 1};
@@ -1726,7 +1733,7 @@ a52_decode_kernel(const DecodeParams P)
     __syncthreads();
     uint32_t tab_base, plane_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(tab_base) : "r"(smem_u32(&T)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(plane_sa) : "r"(smem_u32(G.plane)));
+    plane_sa = pair_sa + (uint32_t)PairLayout<NPL>::plane;
     constexpr uint32_t kDumpWord = (uint32_t)(PairLayout<NPL>::dump - PairLayout<NPL>::plane);   // scale bits 0: stores 0.0f
     uint32_t phase = 0;
     constexpr int ndelay = NPL;              // tails: planes 0..4 main, 5 LFE
@@ -2247,7 +2254,7 @@ a52_decode_kernel(const DecodeParams P)
                     }
                     dither_index = (dither_index + tz) % kDitherPeriod;
 
-                    const uint32_t w_sa = smem_u32(W);
+                    const uint32_t w_sa = pair_sa + (uint32_t)PairLayout<NPL>::fbuf;
                     auto window = [&](uint32_t pw) {          // the 32 bits at the entry's (shifted, clamped) position
                         const uint32_t pos = min((pw & 0x7fffu) + pos_delta, limit);
                         const uint32_t a = w_sa + ((pos >> 5) << 2);
