@@ -1684,6 +1684,38 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
         }
 }
 
+// The gates of a CTA (see the kernel): one shared-memory word each, [7:0] arrived, [15:8] members, [31:16] generation.
+__device__ __forceinline__ void gate_arrive_fn(unsigned int* g, bool wait, int gt, int bar_id)
+{
+    if (gt == 0) {
+        unsigned int old = *(volatile unsigned int*)g, seen;
+        bool released;
+        do {
+            seen = old;
+            const unsigned int cnt = (seen & 255u) + 1u, act = (seen >> 8) & 255u;
+            released = cnt >= act;
+            const unsigned int nw = released ? ((((seen >> 16) + 1u) & 0xffffu) << 16) | (act << 8) : seen + 1u;
+            old = atomicCAS(g, seen, nw);
+        } while (old != seen);
+        if (!released && wait)
+            while ((*(volatile unsigned int*)g >> 16) == (seen >> 16)) __nanosleep(400);
+    }
+    if (wait) asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+}
+
+__device__ __forceinline__ void gate_leave_fn(unsigned int* g)
+{
+    // if everyone who stays has already arrived, let them go
+    unsigned int old = *(volatile unsigned int*)g, seen;
+    do {
+        seen = old;
+        const unsigned int cnt = seen & 255u, act = ((seen >> 8) & 255u) - 1u;
+        const unsigned int nw = (cnt && cnt >= act) ? ((((seen >> 16) + 1u) & 0xffffu) << 16) | (act << 8)
+                                                    : (seen & ~0xff00u) | (act << 8);
+        old = atomicCAS(g, seen, nw);
+    } while (old != seen);
+}
+
 #ifndef A52_PAIRS_PER_CTA
 #define A52_PAIRS_PER_CTA 14
 #endif
@@ -1794,40 +1826,17 @@ a52_decode_kernel(const DecodeParams P)
         sync();
 
         // arrive at a gate (thread 0 of the pair), optionally wait for the round to complete; leave a gate
-        auto gate_arrive = [&](unsigned int& g, bool wait) {
-            if (gt == 0) {
-                unsigned int old = *(volatile unsigned int*)&g, seen;
-                bool released;
-                do {
-                    seen = old;
-                    const unsigned int cnt = (seen & 255u) + 1u, act = (seen >> 8) & 255u;
-                    released = cnt >= act;
-                    const unsigned int nw = released ? ((((seen >> 16) + 1u) & 0xffffu) << 16) | (act << 8) : seen + 1u;
-                    old = atomicCAS(&g, seen, nw);
-                } while (old != seen);
-                if (!released && wait)
-                    while ((*(volatile unsigned int*)&g >> 16) == (seen >> 16)) __nanosleep(400);
-            }
-            if (wait) sync();
-        };
-        auto gate_leave = [&](unsigned int& g) {
-            if (gt == 0) {
-                // if everyone who stays has already arrived, let them go
-                unsigned int old = *(volatile unsigned int*)&g, seen;
-                do {
-                    seen = old;
-                    const unsigned int cnt = seen & 255u, act = ((seen >> 8) & 255u) - 1u;
-                    const unsigned int nw = (cnt && cnt >= act) ? ((((seen >> 16) + 1u) & 0xffffu) << 16) | (act << 8)
-                                                                : (seen & ~0xff00u) | (act << 8);
-                    old = atomicCAS(&g, seen, nw);
-                } while (old != seen);
-            }
-        };
+        auto gate_arrive = [&](unsigned int& g, bool wait) { gate_arrive_fn(&g, wait, gt, pair + 1); };
+        auto gate_leave = [&](unsigned int& g) { if (gt == 0) gate_leave_fn(&g); };
         int cold_prev = 0;                        // expensive blocks among blocks 1..5 of the unit's previous frame
         for (uint32_t f = fl; f < f1; f++) {
             if (gated) gate_arrive(gate, true);
             const bool bgated = gated && cold_prev >= 3;      // this frame's blocks go through the block gate
             if (bgated && gt == 0) atomicAdd(&bgate, 1u << 8);
+            // (P.lockstep >= 2: such streams also meet in front of every stage of a block - their blocks are long, and
+            // the instruction cache holds about one stage's code of it)
+            const bool sgated = bgated && P.lockstep >= 2;
+            const int gates_due = sgated ? 5 + 6 * 5 : 5;
             int cold_now = 0, gates_passed = 0;
             const bool shadow = lookback && f == fl;          // decoded for its state only
             uint32_t frame_draws = 0;
@@ -1995,6 +2004,9 @@ a52_decode_kernel(const DecodeParams P)
                 const uint32_t chincpl = c->chincpl;
                 const uint32_t limit = c->limit_bit;
 
+#ifndef A52_NO_STAGE_GATES
+                if (sgated) { gate_arrive(bgate, true); gates_passed++; }
+#endif
                 // ================= E =================
                 // (a block that repeats the last allocation has no exponents to decode and nothing to allocate)
                 if (!c->repeat) {
@@ -2013,6 +2025,9 @@ a52_decode_kernel(const DecodeParams P)
                     if (c->err) break;
                 }
 
+#ifndef A52_NO_STAGE_GATES
+                if (sgated) { gate_arrive(bgate, true); gates_passed++; }
+#endif
                 // ================= B =================
                 if (c->do_alloc) {
                     if (c->zero_alloc) {
@@ -2025,6 +2040,9 @@ a52_decode_kernel(const DecodeParams P)
                     sync();
                 }
 
+#ifndef A52_NO_STAGE_GATES
+                if (sgated) { gate_arrive(bgate, true); gates_passed++; }
+#endif
                 // ================= L =================
                 // What the locate passes produce is a PLAN of the block's mantissas: for every class (3-, 5- and
                 // 11-level groups, plain fields, dithered zeros) the list of its members in coded order, each with
@@ -2216,6 +2234,9 @@ a52_decode_kernel(const DecodeParams P)
                 if (P.scan_only) continue;        // a scan stops here: the counts are all it wants of the block
                 const uint32_t t1 = ta & 0xffff, t2 = ta >> 16, t4 = tb & 0xffff, tp = tb >> 16;
 
+#ifndef A52_NO_STAGE_GATES
+                if (sgated) { gate_arrive(bgate, true); gates_passed++; }
+#endif
                 // ================= U =================
                 // Every class reads its part of the plan back in coalesced 16-byte (groups, pairs of plain fields) or
                 // 4-byte (zeros: one row of 32 per load, eight rows in flight) loads; a member word is
@@ -2375,6 +2396,9 @@ a52_decode_kernel(const DecodeParams P)
                     o[15] = c->csnroffst;
                 }
 
+#ifndef A52_NO_STAGE_GATES
+                if (sgated) { gate_arrive(bgate, true); gates_passed++; }
+#endif
                 // ================= M =================
                 const int nmain = c->nout;
                 const bool uniform = c->uniform_path;
@@ -2412,7 +2436,7 @@ a52_decode_kernel(const DecodeParams P)
             }   // blocks
 
             if (bgated) {
-                for (; gates_passed < 5; gates_passed++) gate_arrive(bgate, false);    // a frame cut short still counts
+                for (; gates_passed < gates_due; gates_passed++) gate_arrive(bgate, false);    // a frame cut short still counts
                 gate_leave(bgate);
             }
             cold_prev = cold_now;

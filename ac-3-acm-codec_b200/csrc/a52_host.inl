@@ -444,7 +444,7 @@ struct a52_batch_s {
     int max_stream_hint = 0;       // frames of the longest stream of the next batches (0 = derive)
     int slice_frames = 32;         // pair kernel: frames per work unit
     int slice_mode = 0;            // 0 = choose, 1 = slices of a stream chained by the carry record, 2 = frame-independent
-    int lockstep = 1;              // the pairs of a CTA start every frame together (A52_B200_LOCKSTEP=0 turns it off)
+    int lockstep = 2;              // frame gate; block and stage gates for streams of expensive blocks (A52_B200_LOCKSTEP=0 / 1: none / no stage gates)
     int zero_copy = 1;             // host-pointer calls: the kernel stores PCM straight into a pinned, mapped caller
                                    // buffer (A52_B200_ZERO_COPY=0: always stage in device memory and copy)
     const float* drc_table = nullptr;   // a52_batch_set_drc_table: ranges for the next A52_DRC_TABLE call
