@@ -40,6 +40,7 @@ struct __align__(16) Tables {
     int16_t  q4[2][128];       // grouped 11-level values by (digit, 7-bit code)
     int16_t  q35[24];          // 7-level at [0..7], 15-level at [8..23]
     uint16_t dither_lut[256];  // CRC-16/0xA011 byte step (tables.h:213-246)
+    uint16_t exp_lut[128];     // 7-bit exponent group code -> the three deltas + 2 as nibbles, bit 15: not a code (>= 125)
     uint32_t cnt_lut32[20];    // per bap: 5-bit counters n1 | n2 << 5 | n4 << 10 | zero << 15, plain field bits << 20
     uint4    emit_lut[32];     // per bap (+16: bap-0 mantissas of this run are dithered), see build_tables()
     uint4    emit_lut2[32];    // same index: where a mantissa's plan entry goes and what its position word holds

@@ -86,6 +86,7 @@ struct __align__(16) GroupCtl {
     int      err;              // error raised inside the current block
     int      tr_ticket;        // transform jobs of the pending block handed out so far
     float    wg2[12];          // wt[o][ch] * gain[ch] of outputs 0 and 1 ([0..4] and [5..9]): the stereo mix fast path
+    uint32_t arange[8];        // per array 0..6: start | end << 8 | first band << 16 | end band << 24 of the coded range
     uint32_t cur_blk;          // 6 * frame + block being parsed (index into the per-block tables of the launch)
     int16_t  dynw[2];          // the block's dynrng words as coded (-1: none)
     uint32_t pad1;
@@ -439,7 +440,7 @@ __device__ void compute_gains(GroupCtl* c)
 // ---------------------------------------------------------------------------
 // audio block side information (parse.c:570-804), one thread
 // ---------------------------------------------------------------------------
-__device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P)
+__device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P, const Tables& T)
 {
     BitReader br{w, c->bitpos, c->limit_bit};
     const int nfchans = c->nfchans;
@@ -702,6 +703,12 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     }
     c->nseg = ns;
     c->total_bins = flat;
+    // the coded range of every exponent / bap array and the bands of the masking curve it covers
+    for (int a = 0; a < 7; a++) {
+        const int st = (a == 6) ? c->cplstrtmant : 0, en = (a == 5) ? 7 : (a == 6) ? c->cplendmant : c->endmant[a];
+        c->arange[a] = (uint32_t)st | ((uint32_t)en << 8) | ((uint32_t)T.masktab[st & 255] << 16) |
+                       ((uint32_t)(T.masktab[(en - 1) & 255] + 1) << 24);
+    }
     // Lanes of the locate passes: every lane walks a run of at most K mantissas of ONE segment,
     // lanes in coded order (so that one warp scan orders the whole block).  K = smallest run
     // length for which the segments need no more than 32 lanes; recomputed only when the
@@ -750,7 +757,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
 // ---------------------------------------------------------------------------
 // exponent decode for one array, executed by one warp (parse.c:218-270)
 // ---------------------------------------------------------------------------
-__device__ int decode_exponents(const uint32_t* w, uint32_t limit, uint8_t* dst, int strategy,
+__device__ int decode_exponents(const Tables& T, const uint32_t* w, uint32_t limit, uint8_t* dst, int strategy,
                                 int ngrp, uint32_t pos0, int start, int lane)
 {
     const int rep = 1 << (strategy - 1);
@@ -762,8 +769,9 @@ __device__ int decode_exponents(const uint32_t* w, uint32_t limit, uint8_t* dst,
         if (g < ngrp) {
             uint32_t p = pos0 + 7 * g;
             uint32_t code = (p + 7 <= limit) ? peek_bits(w, p, 7) : 0;
-            if (code >= 125) bad = 1;
-            d0 = code / 25; d1 = (code / 5) % 5; d2 = code % 5;
+            const uint32_t L = T.exp_lut[code];
+            bad |= (int)(L >> 15);
+            d0 = L & 15; d1 = (L >> 4) & 15; d2 = (L >> 8) & 15;
         }
         int s = d0 + d1 + d2 - 6;
         int incl = s;
@@ -810,10 +818,9 @@ __device__ __forceinline__ int lowcomp_step(int a, int b0, int b1, int band)
 
 __device__ __forceinline__ void alloc_range(const GroupCtl* c, int a, int& start, int& end)
 {
-    start = 0;
-    if (a == 6) { start = c->cplstrtmant; end = c->cplendmant; }
-    else if (a == 5) end = 7;
-    else end = c->endmant[a];
+    const uint32_t r = c->arange[a];          // kept by parse_block whenever a coded range changes
+    start = r & 255;
+    end = (r >> 8) & 255;
 }
 
 // Bit allocation of every array flagged in `todo` (bit a: 0..4 fbw, 5 lfe, 6 coupling), one warp.
@@ -896,8 +903,8 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
         const int fdecay = (0x3f + 0x14 * ((bai >> 7) & 3)) >> half;
         const int sgain = c_sgain[(bai >> 5) & 3];
         const int fgain = 0x80 * ((chbai & 7) + 1);
-        const int bndstrt = T.masktab[start];
-        const int bndend = T.masktab[end - 1] + 1;
+        const int bndstrt = (c->arange[a] >> 16) & 255;
+        const int bndend = c->arange[a] >> 24;
         int band, begin, lowcomp = 0;
         if (bndstrt == 0) {
             lowcomp = lowcomp_step(lowcomp, bndpsd[0], bndpsd[1], 0);
@@ -945,8 +952,8 @@ __device__ void bit_allocate_block(const Tables& T, const GroupCtl* c, uint32_t 
             const int a = (act >> (3 * j)) & 7;
             int start, end;
             alloc_range(c, a, start, end);
-            const int bndstrt = T.masktab[start];
-            const int bndend = T.masktab[end - 1] + 1;
+            const int bndstrt = (c->arange[a] >> 16) & 255;
+            const int bndend = c->arange[a] >> 24;
             if (band < bndstrt || band >= bndend) continue;
             const int snroffset = (((csnr - 15) << 4) + (c->chbai[a] >> 3)) << 2;
             const int deltbae = c->deltbae[a];
@@ -1480,7 +1487,7 @@ __device__ __forceinline__ void issue_frame_load(const DecodeParams& P, const Wa
     tma_load_1d(G.fbuf, P.es + a0, nb, G.mbar);
 }
 
-static_assert(sizeof(GroupCtl) <= 1264, "GroupCtl grew: check the shared-memory budget per stream");
+static_assert(sizeof(GroupCtl) <= 1296, "GroupCtl grew: check the shared-memory budget per stream");
 
 // ===========================================================================
 // The decode kernel: TWO warps (64 threads, a "pair") walk one stream.  The two warps split every
@@ -1891,7 +1898,7 @@ a52_decode_kernel(const DecodeParams P)
                 // ================= P (block blk) | T (block blk - 1) =================
                 if (more && gt == 0) {
                     c->cur_blk = f * 6u + (uint32_t)blk;
-                    c->err = parse_block(c, W, P);
+                    c->err = parse_block(c, W, P, T);
                     if (P.scan_only && !c->err) {
                         P.scan[f].dynrng[blk][0] = c->dynw[0];
                         P.scan[f].dynrng[blk][1] = c->dynw[1];
@@ -2017,7 +2024,7 @@ a52_decode_kernel(const DecodeParams P)
                         uint8_t* e = G.exp + a * 256;
                         int dst = (a == 6) ? c->cplstrtmant : 1;
                         if (a != 6 && lane == 0) e[0] = c->exp_abs[a];
-                        bad |= decode_exponents(W, limit, e + dst, c->expstr[a], c->exp_ngrp[a],
+                        bad |= decode_exponents(T, W, limit, e + dst, c->expstr[a], c->exp_ngrp[a],
                                                 c->exp_pos[a], c->exp_abs[a], lane);
                     }
                     if (bad && lane == 0) c->err = 1;

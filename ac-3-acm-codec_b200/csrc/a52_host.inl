@@ -243,6 +243,8 @@ static void build_tables(Tables* T)
         for (int d = 0; d < 3; d++) T->q2[d][c] = c < 125 ? ac3_q5[d5[d]] : 0;
         for (int d = 0; d < 2; d++) T->q4[d][c] = c < 121 ? ac3_q11[d11[d]] : 0;
     }
+    for (int c = 0; c < 128; c++)
+        T->exp_lut[c] = (uint16_t)(c < 125 ? (c / 25) | (((c / 5) % 5) << 4) | ((c % 5) << 8) : 0x8000 | 2 | (2 << 4) | (2 << 8));
     for (int i = 0; i < 8; i++) T->q35[i] = ac3_q7[i];
     for (int i = 0; i < 16; i++) T->q35[8 + i] = ac3_q15[i];
     for (int i = 0; i < 256; i++) {
