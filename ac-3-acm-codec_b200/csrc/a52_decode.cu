@@ -1691,6 +1691,9 @@ __device__ __noinline__ void ola_store_generic(const Tables& T, const DecodePara
         }
 }
 
+#ifndef A52_GATE_SLEEP_NS
+#define A52_GATE_SLEEP_NS 400          // (100 .. 400 ns measure the same; 1.5 us and more lose)
+#endif
 // The gates of a CTA (see the kernel): one shared-memory word each, [7:0] arrived, [15:8] members, [31:16] generation.
 __device__ __forceinline__ void gate_arrive_fn(unsigned int* g, bool wait, int gt, int bar_id)
 {
@@ -1705,7 +1708,7 @@ __device__ __forceinline__ void gate_arrive_fn(unsigned int* g, bool wait, int g
             old = atomicCAS(g, seen, nw);
         } while (old != seen);
         if (!released && wait)
-            while ((*(volatile unsigned int*)g >> 16) == (seen >> 16)) __nanosleep(400);
+            while ((*(volatile unsigned int*)g >> 16) == (seen >> 16)) __nanosleep(A52_GATE_SLEEP_NS);
     }
     if (wait) asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
 }

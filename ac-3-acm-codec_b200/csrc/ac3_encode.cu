@@ -231,42 +231,74 @@ __device__ __forceinline__ void e1_transform(EncShared& S, const EncTables& T, i
         z[T.rev[i]] = pack16(xr, xi);
     }
     __syncwarp();
-    // 128-point FFT (:485-568), 7 halving radix-2 passes, two butterflies per lane and pass
-#pragma unroll 1
-    for (int st = 0; st < 7; st++) {
-        const int half = 1 << st;
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int b = lane + 32 * r;
-            const int t = b & (half - 1);
-            const int i0 = ((b >> st) << (st + 1)) + t, i1 = i0 + half;
-            const uint32_t p = z[i0], q = z[i1];
-            const int bx = (int16_t)(p & 0xffff), by = (int16_t)(p >> 16);
-            const int qre = (int16_t)(q & 0xffff), qim = (int16_t)(q >> 16);
-            int ax, ay;
-            if (t == 0) { ax = qre; ay = qim; }
-            else if (st == 1) { ax = qim; ay = -qre; }
-            else {
-                const int l = t * (64 >> st);
-                const int c = T.costab[l], sn = -T.sintab[l];
-                ax = (c * qre - sn * qim) >> 15;
-                ay = (c * qim + qre * sn) >> 15;
-            }
-            z[i0] = pack16((bx + ax) >> 1, (by + ay) >> 1);
-            z[i1] = pack16((bx - ax) >> 1, (by - ay) >> 1);
+    // 128-point FFT (:485-568): the reference's seven halving radix-2 passes, butterfly for butterfly (same products,
+    // same shifts, results cut to 16 bits as its IComplex stores cut them), but two passes at a time in registers:
+    // a lane holds the four points of a 4-point group, so the scratch is crossed four times instead of seven.
+    struct CI { int re, im; };
+    auto ld = [&](int i) { const uint32_t p = z[i]; return CI{(int)(int16_t)(p & 0xffff), (int)(int16_t)(p >> 16)}; };
+    auto stz = [&](int i, const CI& v) { z[i] = pack16(v.re, v.im); };
+    // one butterfly; t == 0: no product (the reference's first butterfly of a group), quarter: multiply by -j
+    auto bf = [&](CI& pp, CI& q, int l, bool plain, bool quarter) {
+        int ax, ay;
+        if (quarter) { ax = q.im; ay = -q.re; }
+        else {
+            const int c = T.costab[l], sn = -T.sintab[l];
+            ax = (c * q.re - sn * q.im) >> 15;
+            ay = (c * q.im + q.re * sn) >> 15;
+            if (plain) { ax = q.re; ay = q.im; }
         }
-        __syncwarp();
+        const int r0 = (pp.re + ax) >> 1, i0 = (pp.im + ay) >> 1, r1 = (pp.re - ax) >> 1, i1 = (pp.im - ay) >> 1;
+        pp.re = (int16_t)r0; pp.im = (int16_t)i0; q.re = (int16_t)r1; q.im = (int16_t)i1;
+    };
+    auto bf_plain = [&](CI& pp, CI& q) {
+        const int r0 = (pp.re + q.re) >> 1, i0 = (pp.im + q.im) >> 1, r1 = (pp.re - q.re) >> 1, i1 = (pp.im - q.im) >> 1;
+        pp.re = (int16_t)r0; pp.im = (int16_t)i0; q.re = (int16_t)r1; q.im = (int16_t)i1;
+    };
+    CI y0, y1, y2, y3;
+    {   // passes 0, 1: points 4 lane .. 4 lane + 3
+        const uint4 v = reinterpret_cast<const uint4*>(z)[lane];
+        y0 = CI{(int)(int16_t)(v.x & 0xffff), (int)(int16_t)(v.x >> 16)};
+        y1 = CI{(int)(int16_t)(v.y & 0xffff), (int)(int16_t)(v.y >> 16)};
+        y2 = CI{(int)(int16_t)(v.z & 0xffff), (int)(int16_t)(v.z >> 16)};
+        y3 = CI{(int)(int16_t)(v.w & 0xffff), (int)(int16_t)(v.w >> 16)};
+        bf_plain(y0, y1); bf_plain(y2, y3);
+        bf_plain(y0, y2); bf(y1, y3, 0, false, true);
+        reinterpret_cast<uint4*>(z)[lane] = make_uint4(pack16(y0.re, y0.im), pack16(y1.re, y1.im), pack16(y2.re, y2.im), pack16(y3.re, y3.im));
+    }
+    __syncwarp();
+    {   // passes 2, 3: points base + 4 j
+        const int t = lane & 3, base = (lane >> 2) * 16 + t;
+        y0 = ld(base); y1 = ld(base + 4); y2 = ld(base + 8); y3 = ld(base + 12);
+        bf(y0, y1, 16 * t, t == 0, false); bf(y2, y3, 16 * t, t == 0, false);
+        bf(y0, y2, 8 * t, t == 0, false);  bf(y1, y3, 8 * (t + 4), false, false);
+        stz(base, y0); stz(base + 4, y1); stz(base + 8, y2); stz(base + 12, y3);
+    }
+    __syncwarp();
+    {   // passes 4, 5: points base + 16 j
+        const int t = lane & 15, base = (lane >> 4) * 64 + t;
+        y0 = ld(base); y1 = ld(base + 16); y2 = ld(base + 32); y3 = ld(base + 48);
+        bf(y0, y1, 4 * t, t == 0, false); bf(y2, y3, 4 * t, t == 0, false);
+        bf(y0, y2, 2 * t, t == 0, false); bf(y1, y3, 2 * (t + 16), false, false);
+        stz(base, y0); stz(base + 16, y1); stz(base + 32, y2); stz(base + 48, y3);
+    }
+    __syncwarp();
+    {   // pass 6: (lane, lane + 64) and (lane + 32, lane + 96); the results stay in registers for the post-rotation
+        y0 = ld(lane); y2 = ld(lane + 64); y1 = ld(lane + 32); y3 = ld(lane + 96);
+        bf(y0, y2, lane, lane == 0, false);
+        bf(y1, y3, lane + 32, false, false);
     }
     // post-rotation (:594-602) into the coefficient slot (the samples are no longer needed)
     int32_t* out = S.coef[blk][ch];
     int o0[4], o1[4];
+    {
+        const CI* yy[4] = {&y0, &y1, &y2, &y3};
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int i = lane + 32 * r;
-        const uint32_t p = z[i];
-        const int re = (int16_t)(p & 0xffff), im = (int16_t)(p >> 16);
-        o1[r] = (re * T.xsin1[i] - im * T.xcos1[i]) >> 15;               // re1 -> out[255 - 2i]
-        o0[r] = (re * T.xcos1[i] + T.xsin1[i] * im) >> 15;               // im1 -> out[2i]
+        for (int r = 0; r < 4; r++) {
+            const int i = lane + 32 * r;
+            const int re = yy[r]->re, im = yy[r]->im;
+            o1[r] = (re * T.xsin1[i] - im * T.xcos1[i]) >> 15;               // re1 -> out[255 - 2i]
+            o0[r] = (re * T.xcos1[i] + T.xsin1[i] * im) >> 15;               // im1 -> out[2i]
+        }
     }
     __syncwarp();
 #pragma unroll
