@@ -262,6 +262,47 @@ struct BitReader {
     __device__ __forceinline__ void skip(uint32_t n) { pos += n; }
 };
 
+// The same reader for the audio blocks' side information, where a hundred fields are read one after the other on one
+// thread: a 64-bit window in registers, refilled where the parser says so (need()), so that a field costs a shift and
+// two funnel shifts instead of two dependent shared-memory loads.  The staged frame is zero from its last bit to the
+// end of the buffer, so fields past the end read as zero without a check (a field that straddles the end keeps its
+// leading bits; BitReader returns the whole field as zero: damaged frames only).
+struct BitWin {
+    const uint32_t* w;
+    uint32_t pos;            // bit position of the window's first bit
+    uint32_t maxw;           // last word index a refill may start at
+    uint32_t hi, lo;
+    int      left;           // valid bits in the window
+    __device__ __forceinline__ BitWin(const uint32_t* w_, uint32_t pos_, uint32_t fbuf_bytes)
+        : w(w_), pos(pos_), maxw(fbuf_bytes / 4 - 3), hi(0), lo(0), left(0) {}
+    __device__ __forceinline__ void need(int n)
+    {
+        if (left < n) {
+            const uint32_t i = min(pos >> 5, maxw), s = pos & 31;
+            const uint32_t w0 = w[i], w1 = w[i + 1], w2 = w[i + 2];
+            hi = __funnelshift_l(w1, w0, s);
+            lo = __funnelshift_l(w2, w1, s);
+            left = 64;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n)       // n in 1..31, after a need() that covers it
+    {
+        A52_CHECK(left >= (int)n && n >= 1 && n < 32, 402);
+        const uint32_t v = hi >> (32 - n);
+        hi = __funnelshift_l(lo, hi, n);
+        lo <<= n;
+        pos += n;
+        left -= (int)n;
+        return v;
+    }
+    __device__ __forceinline__ int32_t get_signed(uint32_t n)
+    {
+        const uint32_t v = get(n);
+        return ((int32_t)(v << (32 - n))) >> (32 - n);
+    }
+    __device__ __forceinline__ void skip(uint32_t n) { pos += n; left = 0; }
+};
+
 // bytes to stage for frame f: from the 16-byte aligned address at or below its
 // offset up to the start of the next frame (or the end of the buffer), capped
 // end of frame f's bytes: the start of the next frame of the table, or the end of the buffer (for the last frame of
@@ -442,7 +483,7 @@ __device__ void compute_gains(GroupCtl* c)
 // ---------------------------------------------------------------------------
 __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P, const Tables& T)
 {
-    BitReader br{w, c->bitpos, c->limit_bit};
+    BitWin br(w, c->bitpos, (uint32_t)P.fbuf_bytes);
     const int nfchans = c->nfchans;
     const int acmod = c->acmod;
     const uint32_t chmask = (1u << nfchans) - 1;
@@ -480,6 +521,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     c->dynw[0] = -1;
     c->dynw[1] = -1;
     if (!fast) {
+    br.need(64);                               // up to 44 bits: blksw / dithflag, dynrng, the coupling strategy header
     uint32_t v = br.get(2 * nfchans);          // blksw[nfchans], dithflag[nfchans]
     // the fields are sent channel 0 first (msb): bit-reverse them so that bit i = channel i
     blksw = __brev(v >> nfchans) >> (32 - nfchans);
@@ -518,6 +560,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             c->cplstrtmant = begf * 12 + 37;
             c->cplendmant = endf * 12 + 73;
             uint32_t strc = 0;
+            br.need(32);
             for (int i = 0; i < nsub - 1; i++)
                 if (br.get(1)) { strc |= 1u << i; nbnd--; }
             c->cplbndstrc = strc;
@@ -529,21 +572,27 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     if (chincpl) {                             // coupling coordinates (parse.c:636-667)
         int any = 0;
         for (int i = 0; i < nfchans; i++)
-            if ((chincpl >> i) & 1)
+            if ((chincpl >> i) & 1) {
+                br.need(8);
                 if (br.get(1)) {
                     any = 1;
                     int mstr = 3 * br.get(2);
                     for (int j = 0; j < c->ncplbnd; j++) {
+                        br.need(8);
                         int e = br.get(4), m = br.get(4);
                         m = (e == 15) ? m << 14 : (m | 0x10) << 13;
                         c->cplco[i][j] = (float)m * pow2neg(15 + e + mstr);
                     }
                 }
-        if (acmod == 2 && c->phsflginu && any)
+            }
+        if (acmod == 2 && c->phsflginu && any) {
+            br.need(32);
             for (int j = 0; j < c->ncplbnd; j++)
                 if (br.get(1)) c->cplco[1][j] = -c->cplco[1][j];
+        }
     }
 
+    br.need(64);                               // rematrix flags, exponent strategies, channel bandwidth codes: <= 48 bits
     if (acmod == 2 && br.get(1)) {             // rematrix flags (parse.c:669-678)
         int stop = chincpl ? c->cplstrtmant : 253;
         uint32_t f = br.get(1);
@@ -576,6 +625,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     if (expstr[6]) {
         int ngrp = (c->cplendmant - c->cplstrtmant) / (3 << (expstr[6] - 1));
         do_alloc |= 64;
+        br.need(4);
         c->exp_abs[6] = br.get(4) << 1;
         c->exp_pos[6] = br.pos;
         c->exp_ngrp[6] = ngrp;
@@ -586,6 +636,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             int gsz = 3 << (expstr[i] - 1);
             int ngrp = (c->endmant[i] + gsz - 4) / gsz;
             do_alloc |= 1u << i;
+            br.need(4);
             c->exp_abs[i] = br.get(4);
             c->exp_pos[i] = br.pos;
             c->exp_ngrp[i] = ngrp;
@@ -593,6 +644,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         }
     if (expstr[5]) {
         do_alloc |= 32;
+        br.need(4);
         c->exp_abs[5] = br.get(4);
         c->exp_pos[5] = br.pos;
         c->exp_ngrp[5] = 2;
@@ -601,14 +653,17 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     for (int i = 0; i < 7; i++) c->expstr[i] = expstr[i];
 
     // bit allocation side info (parse.c:738-772)
+    br.need(64);                               // baie .. the coupling channel's offsets: <= 26 bits
     if (br.get(1)) { do_alloc = 127; c->bai = br.get(11); }
     if (br.get(1)) {
         do_alloc = 127;
         c->csnroffst = br.get(6);
         if (chincpl) c->chbai[6] = br.get(7);
+        br.need(64);                           // five channels and the lfe: 42 bits
         for (int i = 0; i < nfchans; i++) c->chbai[i] = br.get(7);
         if (c->lfeon) c->chbai[5] = br.get(7);
     }
+    br.need(32);                               // leak terms, deltbaie, deltbae: <= 20 bits
     if (chincpl && br.get(1)) {
         do_alloc |= 64;
         c->cplfleak = br.get(3);               // kept as coded; standard form uses (x<<8)+768
@@ -624,8 +679,10 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             if (c->deltbae[a] != 1) continue;
             int8_t* dst = c->deltba[a];        // parse_deltba (parse.c:272-294)
             for (int j = 0; j < 50; j++) dst[j] = 0;
+            br.need(8);
             int nseg = br.get(3) + 1, band = 0;
             while (nseg--) {
+                br.need(16);
                 band += br.get(5);
                 int len = br.get(4), code = br.get(3);
                 int delta = (code >= 4) ? code - 3 : code - 4;
@@ -656,6 +713,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
         do_alloc = m;
     }
 
+    br.need(16);
     if (br.get(1)) {                           // skip field (parse.c:800-804)
         uint32_t n = br.get(9);
         br.skip(8 * n);
