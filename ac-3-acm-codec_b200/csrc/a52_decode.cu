@@ -623,7 +623,8 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
 
     // exponent fields: remember where they are, decode later in parallel
     if (expstr[6]) {
-        int ngrp = (c->cplendmant - c->cplstrtmant) / (3 << (expstr[6] - 1));
+        // (x / (3 << k) == (x / 3) >> k for non-negative x, and x / 3 == (x * 43691) >> 17 below 2^16: no divider)
+        int ngrp = (int)((((uint32_t)(c->cplendmant - c->cplstrtmant) * 43691u) >> 17) >> (expstr[6] - 1));
         do_alloc |= 64;
         br.need(4);
         c->exp_abs[6] = br.get(4) << 1;
@@ -634,7 +635,7 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
     for (int i = 0; i < nfchans; i++)
         if (expstr[i]) {
             int gsz = 3 << (expstr[i] - 1);
-            int ngrp = (c->endmant[i] + gsz - 4) / gsz;
+            int ngrp = (int)((((uint32_t)(c->endmant[i] + gsz - 4) * 43691u) >> 17) >> (expstr[i] - 1));
             do_alloc |= 1u << i;
             br.need(4);
             c->exp_abs[i] = br.get(4);
@@ -780,16 +781,20 @@ __device__ int parse_block(GroupCtl* c, const uint32_t* w, const DecodeParams& P
             // the 7 LFE bins stay in one lane: when the LFE channel is not requested its lane takes part in
             // the bit count but not in the list cursors, which only works for the last lane of the block
             if (c->lfeon && K < 7) K = 7;
+            // ceil(count / K) through one reciprocal per candidate K: (x * r) >> 16 with r = 65536 / K + 1 is exact
+            // for count < 300, K < 100 (checked exhaustively; a segment has at most 253 bins, K stays below 50)
+            uint32_t r;
             for (;; K += 2) {
+                r = 65536u / K + 1u;
                 uint32_t lanes = 0;
-                for (int k = 0; k < ns; k++) lanes += (c->seg[k].count + K - 1) / K;
+                for (int k = 0; k < ns; k++) lanes += ((c->seg[k].count + K - 1) * r) >> 16;
                 if (lanes <= (uint32_t)P.group_threads) break;
             }
             uint32_t l0 = 0;
             for (int k = 0; k < ns; k++) {
                 c->plan_lane0[k] = (uint8_t)l0;
                 c->plan_count[k] = c->seg[k].count;
-                l0 += (c->seg[k].count + K - 1) / K;
+                l0 += ((c->seg[k].count + K - 1) * r) >> 16;
             }
             c->plan_lane0[ns] = (uint8_t)l0;
             c->plan_nseg = ns;
