@@ -39,15 +39,17 @@ namespace ac3e {
 constexpr int kWarps = 6;
 constexpr int kThreads = kWarps * 32;
 constexpr int kFrameWords = 968;         // staged output frame, 32-bit words (3840 bytes max + slack)
-constexpr int kCodes = 1320;             // group codes per block: 3- and 5-level <= 375 each, 11-level <= 562
 
 struct EncTables {
+    uint32_t taba[16];                   // per bap: plain field bits | 3-level << 8 | 5-level << 16 | 11-level << 24 (counters)
+    uint32_t tabb[16];                   // per bap: levels (0 = asymmetric) | quantiser bits << 8 | field width << 16 | class << 24
+    uint32_t tabc[64];                   // taba[baptab[address]]: a search probe counts without looking at the bap
+    uint8_t  masktab[256];               // (8-byte aligned: read eight bins at a time)
     int16_t  window[256];
     int16_t  costab[64], sintab[64], xcos1[128], xsin1[128];
     uint16_t crc_table[256];
     uint16_t hth[150];
     uint8_t  rev[128];
-    uint8_t  masktab[256];
     uint8_t  latab[256];
     uint8_t  baptab[64];
     uint8_t  bndtab[52];
@@ -76,6 +78,7 @@ struct EncParams {
     int nstreams, nframes;
     int nch_all, nch, lfe, acmod, fscod, halfrate, bsid, frmsizecod, frame_words;
     uint32_t crc_inv;                    // x^-(16 fs58 - 16) mod poly (ac3enc.cpp:1627)
+    uint16_t crc_fold[2][5];             // x^(8 L 2^k) mod poly, L = chunk bytes per lane of the two CRC ranges
     uint8_t chmap[8];
     // optional dumps
     int32_t* dbg_coef;
@@ -86,6 +89,8 @@ struct EncParams {
     int32_t* dbg_snr;
 };
 
+static_assert(offsetof(EncTables, masktab) % 8 == 0, "masktab is read as uint2");
+
 struct EncShared {
     int32_t  coef[6][6][256];            // MDCT coefficients; a (block, channel) slot first holds its 512 input samples
     uint8_t  expo[6][6][256];            // raw exponents, later the baps
@@ -93,12 +98,14 @@ struct EncShared {
     int16_t  last[6][256];               // previous 256 samples per coded channel
     union {
         // E1..E3: FFT scratch, masking curves before the snr offset (run heads)
-        struct { uint32_t z[6][128]; int16_t mask[6][6][50]; } e1;
-        // E4: the frame being packed, group-code accumulators and their bit positions
-        struct { uint32_t frame[kFrameWords]; uint32_t codes[kCodes]; uint16_t gpos[kCodes]; } e4;
+        // (pcnt: the class counts of the search probes, two buffers used in turn)
+        struct { uint32_t z[6][128]; int16_t mask[6][6][50]; int pcnt[2][6][6][4]; } e1;
+        // E4: the frame being packed; per block (= warp) the quantised members of the 3- / 5- / 11-level groups by
+        // occurrence number and the bit positions of the group codes, as rings (a channel adds at most 223 members
+        // and 112 groups to a class, and at most one group of a class stays open across a channel boundary)
+        struct { uint32_t frame[kFrameWords]; uint8_t ring_v[6][3][256]; uint16_t ring_p[6][3][128]; } e4;
     } u;
     int      cnt[6][6][4];               // per exponent set: 3-, 5-, 11-level mantissas, bits of plain fields
-    int      pcnt[2][6][6][4];           // the same for the search probes, two buffers used in turn
     uint8_t  strategy[6][6];
     uint8_t  head[6][6];                 // block holding the exponent set a (block, channel) uses
     int8_t   exp_shift[6][6];
@@ -126,10 +133,16 @@ __device__ __forceinline__ void put_bits_atomic(uint32_t* frame, uint32_t pos, u
     if (lo) atomicOr(&frame[wi + 1], lo);
 }
 
+// the same out of line for the side information (some fifty fields written once per frame by a few lanes)
+__device__ __noinline__ void put_bits_call(uint32_t* frame, uint32_t pos, uint32_t n, uint32_t v)
+{
+    put_bits_atomic(frame, pos, n, v);
+}
+
 struct SerialBits {                      // single-thread bit cursor for the side information
     uint32_t* frame;
     uint32_t pos;
-    __device__ __forceinline__ void put(uint32_t n, uint32_t v) { put_bits_atomic(frame, pos, n, v); pos += n; }
+    __device__ __forceinline__ void put(uint32_t n, uint32_t v) { put_bits_call(frame, pos, n, v); pos += n; }
 };
 
 __device__ __forceinline__ int sym_quant(int c, int e, int levels)      // ac3enc.cpp:1150-1166
@@ -150,10 +163,11 @@ __device__ __forceinline__ int asym_quant(int c, int e, int qbits)       // ac3e
     return v & ((1 << qbits) - 1);
 }
 
-__device__ __forceinline__ uint32_t mul_poly(uint32_t a, uint32_t b)      // ac3enc.cpp:1513-1524, poly 0x18005
+__device__ __noinline__ uint32_t mul_poly(uint32_t a, uint32_t b)      // ac3enc.cpp:1513-1524, poly 0x18005
 {
+    // (a loop on purpose, and out of line: it runs a dozen times per frame and must not cost instruction-cache space)
     uint32_t c = 0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 16; i++) {
         if (a & 1) c ^= b;
         a >>= 1;
@@ -165,26 +179,27 @@ __device__ __forceinline__ uint32_t mul_poly(uint32_t a, uint32_t b)      // ac3
 
 // CRC-16 (poly 0x8005, init 0) of frame bytes [b0, b1) by one warp: every lane runs the table CRC over
 // an equal chunk (chunks are aligned to the END of the range: leading zero bytes do not change a
-// zero-initialised CRC), then the chunks are folded pairwise: crc(A|B) = crc(A) * x^(8 len B) ^ crc(B).
-__device__ uint32_t warp_crc(const EncTables& T, const uint32_t* frame, int b0, int b1, int lane)
+// zero-initialised CRC), then the chunks are folded pairwise: crc(A|B) = crc(A) * x^(8 len B) ^ crc(B);
+// fold[k] = x^(8 L 2^k) mod poly comes from the host (the ranges are the same for every frame of a call).
+__device__ __forceinline__ uint32_t warp_crc(const EncTables& T, const uint32_t* frame, int b0, int b1, int lane,
+                                             const uint16_t (&fold)[5])
 {
     const int n = b1 - b0;
     const int L = (n + 31) >> 5;
     const int start = b1 - (32 - lane) * L;
     uint32_t crc = 0;
+#pragma unroll 1
     for (int k = 0; k < L; k++) {
         int idx = start + k;
         uint32_t byte = (idx >= b0) ? ((frame[idx >> 2] >> (24 - 8 * (idx & 3))) & 0xff) : 0u;
         crc = (T.crc_table[byte ^ (crc >> 8)] ^ (crc << 8)) & 0xffff;
     }
-    // m = x^(8 L) mod poly: the register after shifting a one through L zero bytes
-    uint32_t m = 1;
-    for (int k = 0; k < L; k++) m = (T.crc_table[m >> 8] ^ (m << 8)) & 0xffff;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) {
+        const int o = 1 << k;
         uint32_t right = __shfl_down_sync(0xffffffffu, crc, o);
-        if ((lane & (2 * o - 1)) == 0) crc = mul_poly(crc, m) ^ right;
-        m = mul_poly(m, m);
+        const uint32_t folded = mul_poly(crc, fold[k]) ^ right;
+        if ((lane & (2 * o - 1)) == 0) crc = folded;
     }
     return __shfl_sync(0xffffffffu, crc, 0);
 }
@@ -504,39 +519,52 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
     __syncwarp();
 }
 
-// E3b: baps of one exponent set for an snr offset (:393-420) + class counts.  One warp.
-__device__ void e3_probe(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane,
-                         int snroffset, bool store, int (*cnt)[6][4])
+// E3b: baps of one exponent set for an snr offset (:393-420) + class counts.  One warp, in two steps.
+// With mask' = (max(mask - snroffset - 0x1f0, 0) & 0x1fe0) + 0x1f0 = 32 k + 496 and psd = 3072 - 128 exp, the bap
+// address (psd - mask') >> 5 is 80 - 4 exp - k: step 1 (lanes = bands) leaves k per band in `kb`, step 2 (a lane owns
+// eight consecutive bins) looks the class counters up by address and sums them in one packed word.
+__device__ __forceinline__ void e3_bands(const EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch,
+                                         int lane, int snroffset, uint8_t* kb)
 {
-    const bool is_lfe = P.lfe && ch == 5;
-    const int end = is_lfe ? 7 : 223;
-    const uint8_t* ex = S.enc[blk][ch];
+    const int end = (P.lfe && ch == 5) ? 7 : 223;
+    const int bndend = T.masktab[end - 1] + 1;
     const int16_t* mk = S.u.e1.mask[blk][ch];
-    uint8_t* bap = S.expo[blk][ch];                                      // raw exponents are dead: baps live there
-    int n1 = 0, n2 = 0, n4 = 0, fixed = 0;
-    for (int i0 = 0; i0 < end; i0 += 32) {
-        const int i = i0 + lane;
-        int b = 0;
-        if (i < end) {
-            int v = mk[T.masktab[i]] - snroffset - 0x1f0;
-            v = (max(v, 0) & 0x1fe0) + 0x1f0;
-            int a = ((3072 - (ex[i] << 7)) - v) >> 5;
-            a = min(max(a, 0), 63);
-            b = T.baptab[a];
-            if (store) bap[i] = (uint8_t)b;
-        }
-        n1 += __popc(__ballot_sync(0xffffffffu, b == 1));
-        n2 += __popc(__ballot_sync(0xffffffffu, b == 2));
-        n4 += __popc(__ballot_sync(0xffffffffu, b == 4));
-        fixed += T.plain_bits[b];
-    }
+    for (int band = lane; band < bndend; band += 32)
+        kb[band] = (uint8_t)((max(mk[band] - snroffset - 0x1f0, 0) >> 5) & 0xff);
+}
+
+__device__ __forceinline__ void e3_probe(EncShared& S, const EncTables& T, const EncParams& P, int blk, int ch, int lane,
+                                         const uint8_t* kb, bool store, int (*cnt)[6][4])
+{
+    const int end = (P.lfe && ch == 5) ? 7 : 223;
+    const int i0 = 8 * lane;
+    const int nvalid = min(max(end - i0, 0), 8);
+    const uint2 e8 = *reinterpret_cast<const uint2*>(S.enc[blk][ch] + i0);
+    const uint2 m8 = *reinterpret_cast<const uint2*>(T.masktab + i0);
+    uint32_t acc = 0;
+    uint2 b8 = make_uint2(0u, 0u);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) fixed += __shfl_xor_sync(0xffffffffu, fixed, o);
+    for (int k = 0; k < 8; k++) {
+        if (k < nvalid) {
+            const int sh = 8 * (k & 3);
+            const int ex = (int)(((k < 4 ? e8.x : e8.y) >> sh) & 0xff);
+            const int band = (int)(((k < 4 ? m8.x : m8.y) >> sh) & 0xff);
+            const int a = min(max(80 - 4 * ex - (int)kb[band], 0), 63);
+            acc += T.tabc[a];
+            if (store) {
+                const uint32_t b = T.baptab[a];
+                if (k < 4) b8.x |= b << sh; else b8.y |= b << sh;
+            }
+        }
+    }
+    if (store && nvalid) *reinterpret_cast<uint2*>(S.expo[blk][ch] + i0) = b8;   // raw exponents are dead: baps live there
+    const uint32_t n = __reduce_add_sync(0xffffffffu, acc >> 8);
+    const uint32_t fixed = __reduce_add_sync(0xffffffffu, acc & 0xff);
     if (lane == 0) {
-        cnt[blk][ch][0] = n1;
-        cnt[blk][ch][1] = n2;
-        cnt[blk][ch][2] = n4;
-        cnt[blk][ch][3] = fixed;
+        cnt[blk][ch][0] = (int)(n & 0xff);
+        cnt[blk][ch][1] = (int)((n >> 8) & 0xff);
+        cnt[blk][ch][2] = (int)(n >> 16);
+        cnt[blk][ch][3] = (int)fixed;
     }
 }
 
@@ -711,27 +739,39 @@ ac3_encode_kernel(const EncParams P)
             q.probe_fs = q.fs = q.phase = q.done = q.failed = 0;
             for (int par = 0;; par ^= 1) {
                 const int snro = (((q.probe_cs - 15) << 4) + q.probe_fs) << 2;
-                if (active)
+                if (active) {
+                    uint8_t* kb = reinterpret_cast<uint8_t*>(S.u.e1.z[warp]);   // scratch: 6 sets x 64 bands
                     for (int blk = 0; blk < 6; blk++)
-                        if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, snro, false, S.pcnt[par]);
+                        if (S.head[blk][warp] == blk) e3_bands(S, T, P, blk, warp, lane, snro, kb + 64 * blk);
+                    __syncwarp();
+                    for (int blk = 0; blk < 6; blk++)
+                        if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, kb + 64 * blk, false, S.u.e1.pcnt[par]);
+                }
                 __syncthreads();
-                search_step(q, bits_left(S, P, lane, S.pcnt[par]));
+                search_step(q, bits_left(S, P, lane, S.u.e1.pcnt[par]));
                 if (q.done) break;
             }
             {
                 // the accepted allocation (or, after a failed search, all-zero baps)
                 const int snro = (((q.cs - 15) << 4) + q.fs) << 2;
                 if (tid == 0) { S.cs = q.cs; S.fs = q.fs; S.failed = q.failed; }
-                if (active)
+                if (active) {
+                    uint8_t* kb = reinterpret_cast<uint8_t*>(S.u.e1.z[warp]);
+                    if (!q.failed) {
+                        for (int blk = 0; blk < 6; blk++)
+                            if (S.head[blk][warp] == blk) e3_bands(S, T, P, blk, warp, lane, snro, kb + 64 * blk);
+                    }
+                    __syncwarp();
                     for (int blk = 0; blk < 6; blk++)
                         if (S.head[blk][warp] == blk) {
                             if (q.failed) {
                                 for (int i = lane; i < 256; i += 32) S.expo[blk][warp][i] = 0;
                                 if (lane < 4) S.cnt[blk][warp][lane] = 0;
                             } else {
-                                e3_probe(S, T, P, blk, warp, lane, snro, true, S.cnt);
+                                e3_probe(S, T, P, blk, warp, lane, kb + 64 * blk, true, S.cnt);
                             }
                         }
+                }
             }
             __syncthreads();
             if (P.dbg_bap) {
@@ -748,7 +788,6 @@ ac3_encode_kernel(const EncParams P)
             // ================= E4 =================
             uint32_t* frame = S.u.e4.frame;
             for (int i = tid; i < kFrameWords; i += kThreads) frame[i] = 0;
-            for (int i = tid; i < kCodes; i += kThreads) S.u.e4.codes[i] = 0;
             __syncthreads();
             if (warp == 0) {
                 // side information (:1113-1147, 1210-1259, 1316-1337): lane 0 writes the BSI, lanes 0..5 then
@@ -833,14 +872,24 @@ ac3_encode_kernel(const EncParams P)
                 }
             }
             __syncthreads();
-            for (int blk = 0; blk < 6; blk++) {
-                if (active) {
-                    const int ch = warp;
+            {
+                // exponents and mantissas (:1261-1314, 1346-1501): warp = audio block, walking the block's channels in
+                // coded order (the occurrence numbers of the grouped classes run across channels); a lane owns eight
+                // consecutive bins.  No barrier and no accumulator shared between warps: group members go to the
+                // block's rings, the lanes then emit the codes of the groups the channel closed.
+                const int blk = warp;
+                uint8_t* rv = &S.u.e4.ring_v[warp][0][0];
+                uint16_t* rp = &S.u.e4.ring_p[warp][0][0];
+                int N1 = 0, N2 = 0, N4 = 0;
+                uint32_t pos0 = S.mant_pos[blk];
+                auto g3 = [](int x) { return (int)(((uint32_t)(x + 2) * 43691u) >> 17); };   // members x' < x with x' % 3 == 0
+                auto d3 = [](int x) { return (int)(((uint32_t)x * 43691u) >> 17); };         // x / 3 below 2^15
+                for (int ch = 0; ch < P.nch_all; ch++) {
                     const bool is_lfe = P.lfe && ch == 5;
                     const int ncoef = is_lfe ? 7 : 223;
                     const int h = S.head[blk][ch];
                     const uint8_t* en = S.enc[h][ch];
-                    // grouped exponents (:1261-1314): lanes = groups
+                    // grouped exponents: lanes = groups
                     const int st = S.strategy[blk][ch];
                     if (st) {
                         const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
@@ -854,79 +903,123 @@ ac3_encode_kernel(const EncParams P)
                             put_bits_atomic(frame, p0 + 4 + 7 * g, 7, (uint32_t)((d0 * 5 + d1) * 5 + d2));
                         }
                     }
-                    // mantissas (:1346-1501): occurrence numbers of the grouped classes run across channels
-                    int N1 = 0, N2 = 0, N4 = 0, fixed_before = 0;
-                    for (int c = 0; c < ch; c++) {
-                        const int* q = S.cnt[S.head[blk][c]][c];
-                        N1 += q[0]; N2 += q[1]; N4 += q[2]; fixed_before += q[3];
+                    // mantissas
+                    const int i0 = 8 * lane;
+                    const int nvalid = min(max(ncoef - i0, 0), 8);
+                    uint2 b8 = *reinterpret_cast<const uint2*>(S.expo[h][ch] + i0);
+                    const uint2 e8 = *reinterpret_cast<const uint2*>(en + i0);
+                    {
+                        // bins past the coded range hold no bap
+                        const uint64_t keep = nvalid >= 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+                        b8.x &= (uint32_t)keep;
+                        b8.y &= (uint32_t)(keep >> 32);
                     }
-                    uint32_t pos0 = S.mant_pos[blk] + fixed_before + 5 * ((N1 + 2) / 3) + 7 * ((N2 + 2) / 3) + 7 * ((N4 + 1) / 2);
-                    const uint8_t* bap = S.expo[h][ch];
-                    const int gexp = S.exp_shift[blk][ch];
-                    for (int i0 = 0; i0 < ncoef; i0 += 32) {
-                        const int i = i0 + lane;
-                        int b = 0, c = 0, e = 0;
-                        if (i < ncoef) { b = bap[i]; c = S.coef[blk][ch][i]; e = en[i] - gexp; }
-                        const uint32_t m1 = __ballot_sync(0xffffffffu, b == 1);
-                        const uint32_t m2 = __ballot_sync(0xffffffffu, b == 2);
-                        const uint32_t m4 = __ballot_sync(0xffffffffu, b == 4);
-                        const uint32_t lt = (1u << lane) - 1;
-                        // occurrence number x of my mantissa in its class -> group g, digit (x < 1500: the
-                        // division by 3 is a multiply-shift)
-                        int x = 0, cls = -1, g = 0, digit = 0;
-                        if (b == 1) { x = N1 + __popc(m1 & lt); cls = 0; }
-                        else if (b == 2) { x = N2 + __popc(m2 & lt); cls = 1; }
-                        else if (b == 4) { x = N4 + __popc(m4 & lt); cls = 2; }
-                        if (cls == 2) { g = x >> 1; digit = x & 1; }
-                        else if (cls >= 0) { g = (x * 43691) >> 17; digit = x - 3 * g; }
-                        int width = (cls >= 0 && digit) ? 0 : T.width[b];
-                        // inclusive scan of the widths
-                        int incl = width;
+                    uint32_t acc = 0;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            int t = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += t;
-                        }
-                        const uint32_t pos = pos0 + incl - width;
-                        pos0 += __shfl_sync(0xffffffffu, incl, 31);
-                        N1 += __popc(m1); N2 += __popc(m2); N4 += __popc(m4);
+                    for (int k = 0; k < 8; k++) acc += T.taba[((k < 4 ? b8.x : b8.y) >> (8 * (k & 3))) & 15];
+                    const uint32_t cnt = acc >> 8, pl = acc & 0xff;
+                    uint32_t icnt = cnt, ipl = pl;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, icnt, o), u = __shfl_up_sync(0xffffffffu, ipl, o);
+                        if (lane >= o) { icnt += t; ipl += u; }
+                    }
+                    const uint32_t tcnt = __shfl_sync(0xffffffffu, icnt, 31), tpl = __shfl_sync(0xffffffffu, ipl, 31);
+                    const uint32_t ec = icnt - cnt;
+                    int X1 = N1 + (int)(ec & 0xff), X2 = N2 + (int)((ec >> 8) & 0xff), X4 = N4 + (int)(ec >> 16);
+                    uint32_t pos = pos0 + (ipl - pl) + 5 * (g3(X1) - g3(N1)) + 7 * (g3(X2) - g3(N2)) + 7 * (((X4 + 1) >> 1) - ((N4 + 1) >> 1));
+                    const int gexp = S.exp_shift[blk][ch];
+                    int cf[8];
+                    {
+                        const int4 c0 = *reinterpret_cast<const int4*>(&S.coef[blk][ch][i0]);
+                        const int4 c1 = *reinterpret_cast<const int4*>(&S.coef[blk][ch][i0 + 4]);
+                        cf[0] = c0.x; cf[1] = c0.y; cf[2] = c0.z; cf[3] = c0.w;
+                        cf[4] = c1.x; cf[5] = c1.y; cf[6] = c1.z; cf[7] = c1.w;
+                    }
+                    // (a real loop: unrolled, the eight copies of the quantisers miss the instruction cache)
+                    uint2 e8r = e8;
+#pragma unroll 1
+                    for (int k = 0; k < 8; k++) {
+                        const int b = (int)(b8.x & 15);
+                        const int c = cf[0];
+                        const int e = (int)(e8r.x & 0xff) - gexp;
+                        b8.x = __funnelshift_r(b8.x, b8.y, 8); b8.y >>= 8;
+                        e8r.x = __funnelshift_r(e8r.x, e8r.y, 8); e8r.y >>= 8;
+#pragma unroll
+                        for (int j = 0; j < 7; j++) cf[j] = cf[j + 1];
                         if (b == 0) continue;
-                        if (cls >= 0) {
-                            const int levels = cls == 0 ? 3 : cls == 1 ? 5 : 11;
-                            const int v = sym_quant(c, e, levels);
-                            const int wgt = cls == 2 ? (digit ? 1 : 11)
-                                                     : (digit == 0 ? levels * levels : digit == 1 ? levels : 1);
-                            const int gi = (cls == 0 ? 0 : cls == 1 ? 376 : 752) + g;
-                            atomicAdd(&S.u.e4.codes[gi], (uint32_t)(wgt * v));
-                            if (digit == 0) S.u.e4.gpos[gi] = (uint16_t)min(pos, 65535u);
+                        const uint32_t tb = T.tabb[b];
+                        const int lv = (int)(tb & 0xff), qb = (int)((tb >> 8) & 0xff), cl = (int)(tb >> 24);
+                        const uint32_t wd = (tb >> 16) & 0xff;
+                        int v;
+                        {
+                            // symmetric (:1150-1166) and asymmetric (:1169-1190) quantiser side by side
+                            const int a = abs(c);
+                            int vs = (lv * (a << e)) >> 24;
+                            vs = (vs + 1) >> 1;
+                            vs = (lv >> 1) + (c >= 0 ? vs : -vs);
+                            const int lshift = e + qb - 24;
+                            int va = lshift >= 0 ? c << lshift : c >> (-lshift);
+                            va = (va + 1) >> 1;
+                            const int m = 1 << (qb - 1);
+                            if (va >= m) va = m - 1;
+                            va &= (1 << qb) - 1;
+                            v = lv ? vs : va;
+                        }
+                        if (cl) {
+                            int x;
+                            if (cl == 1) x = X1++; else if (cl == 2) x = X2++; else x = X4++;
+                            int g, digit;
+                            if (cl == 3) { g = x >> 1; digit = x & 1; }
+                            else { g = d3(x); digit = x - 3 * g; }
+                            rv[(cl - 1) * 256 + (x & 255)] = (uint8_t)v;
+                            if (digit == 0) {
+                                rp[(cl - 1) * 128 + (g & 127)] = (uint16_t)min(pos, 65535u);
+                                pos += wd;
+                            }
                         } else {
-                            int v;
-                            if (b == 3) v = sym_quant(c, e, 7);
-                            else if (b == 5) v = sym_quant(c, e, 15);
-                            else if (b == 14) v = asym_quant(c, e, 14);
-                            else if (b == 15) v = asym_quant(c, e, 16);
-                            else v = asym_quant(c, e, b - 1);
-                            put_bits_atomic(frame, pos, T.width[b], (uint32_t)v);
+                            put_bits_atomic(frame, pos, wd, (uint32_t)v);
+                            pos += wd;
                         }
                     }
-                }
-                __syncthreads();
-                {
-                    // group codes of the block
-                    int n1 = 0, n2 = 0, n4 = 0;
-                    for (int c = 0; c < P.nch_all; c++) {
-                        const int* q = S.cnt[S.head[blk][c]][c];
-                        n1 += q[0]; n2 += q[1]; n4 += q[2];
+                    __syncwarp();
+                    // the groups this channel closed: lanes = groups
+                    const int t1 = (int)(tcnt & 0xff), t2 = (int)((tcnt >> 8) & 0xff), t4 = (int)(tcnt >> 16);
+                    {
+                        const int d1a = d3(N1), d2a = d3(N2), d4a = N4 >> 1;
+                        const int n1g = d3(N1 + t1) - d1a, n2g = d3(N2 + t2) - d2a, n4g = ((N4 + t4) >> 1) - d4a;
+                        for (int i = lane; i < n1g + n2g + n4g; i += 32) {
+                            int g, cls, m0, m1;
+                            if (i < n1g) { g = d1a + i; cls = 0; m0 = 9; m1 = 3; }
+                            else if (i < n1g + n2g) { g = d2a + i - n1g; cls = 1; m0 = 25; m1 = 5; }
+                            else { g = d4a + i - n1g - n2g; cls = 2; m0 = 11; m1 = 1; }
+                            const uint8_t* r = rv + cls * 256;
+                            const int x0 = cls == 2 ? 2 * g : 3 * g;
+                            int code = m0 * r[x0 & 255] + m1 * r[(x0 + 1) & 255];
+                            if (cls != 2) code += r[(x0 + 2) & 255];
+                            put_bits_atomic(frame, rp[cls * 128 + (g & 127)], cls == 0 ? 5 : 7, (uint32_t)code);
+                        }
                     }
-                    const int g1 = (n1 + 2) / 3, g2 = (n2 + 2) / 3, g4 = (n4 + 1) / 2;
-                    for (int i = tid; i < g1 + g2 + g4; i += kThreads) {
-                        const int gi = i < g1 ? i : i < g1 + g2 ? 376 + (i - g1) : 752 + (i - g1 - g2);
-                        put_bits_atomic(frame, S.u.e4.gpos[gi], i < g1 ? 5 : 7, S.u.e4.codes[gi]);
-                        S.u.e4.codes[gi] = 0;
+                    pos0 += tpl + 5 * (g3(N1 + t1) - g3(N1)) + 7 * (g3(N2 + t2) - g3(N2)) + 7 * (((N4 + t4 + 1) >> 1) - ((N4 + 1) >> 1));
+                    N1 += t1; N2 += t2; N4 += t4;
+                    __syncwarp();
+                }
+                // groups still open at the end of the block carry what they have (:1375-1421)
+                if (lane < 3) {
+                    const int n = lane == 0 ? N1 : lane == 1 ? N2 : N4;
+                    const int g = lane == 2 ? n >> 1 : d3(n);
+                    const int rem = n - (lane == 2 ? 2 : 3) * g;
+                    if (rem) {
+                        const uint8_t* r = rv + lane * 256;
+                        const int x0 = (lane == 2 ? 2 : 3) * g;
+                        const int m0 = lane == 0 ? 9 : lane == 1 ? 25 : 11, m1 = lane == 0 ? 3 : 5;
+                        int code = m0 * r[x0 & 255];
+                        if (rem == 2) code += m1 * r[(x0 + 1) & 255];
+                        put_bits_atomic(frame, rp[lane * 128 + (g & 127)], lane == 0 ? 5 : 7, (uint32_t)code);
                     }
                 }
-                __syncthreads();
             }
+            __syncthreads();
             // frame end (:1599-1638): crc1 over the first 5/8 through the inverse polynomial trick,
             // crc2 over the rest, stored over the last two bytes whatever spilled into them
             {
@@ -939,10 +1032,10 @@ ac3_encode_kernel(const EncParams P)
                 }
                 __syncthreads();
                 if (warp == 0) {
-                    uint32_t c1 = warp_crc(T, frame, 4, 2 * fs58, lane);
+                    uint32_t c1 = warp_crc(T, frame, 4, 2 * fs58, lane, P.crc_fold[0]);
                     if (lane == 0) S.crc[0] = mul_poly(P.crc_inv, c1);
                 } else if (warp == 1) {
-                    uint32_t c2 = warp_crc(T, frame, 2 * fs58, nbytes - 2, lane);
+                    uint32_t c2 = warp_crc(T, frame, 2 * fs58, nbytes - 2, lane, P.crc_fold[1]);
                     if (lane == 0) S.crc[1] = c2;
                 }
                 __syncthreads();

@@ -59,7 +59,15 @@ static void build_enc_tables(EncTables* T)
     for (int b = 0; b < 16; b++) {
         T->width[b] = ac3_bap_bits[b];
         T->plain_bits[b] = (b == 0 || b == 1 || b == 2 || b == 4) ? 0 : ac3_bap_bits[b];
+        // counters of the packer and the search: bits of an ungrouped field, one count per grouped class
+        T->taba[b] = T->plain_bits[b] | (uint32_t)(b == 1) << 8 | (uint32_t)(b == 2) << 16 | (uint32_t)(b == 4) << 24;
+        // quantiser per bap (ac3enc.cpp:1363-1460): 3 / 5 / 7 / 11 / 15 levels symmetric, the rest asymmetric
+        static const uint8_t levels[16] = {0, 3, 5, 7, 11, 15, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t qbits = b < 6 ? 1 : b == 14 ? 14 : b == 15 ? 16 : b - 1;
+        const uint32_t cls = b == 1 ? 1 : b == 2 ? 2 : b == 4 ? 3 : 0;
+        T->tabb[b] = levels[b] | qbits << 8 | (uint32_t)ac3_bap_bits[b] << 16 | cls << 24;
     }
+    for (int a = 0; a < 64; a++) T->tabc[a] = T->taba[ac3_baptab[a]];
 }
 
 struct EncConfig {
@@ -239,6 +247,15 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
     P.halfrate = c.halfrate; P.bsid = c.bsid; P.frmsizecod = c.frmsizecod; P.frame_words = c.frame_words;
     const int fs58 = (c.frame_words >> 1) + (c.frame_words >> 3);
     P.crc_inv = h_pow_poly(0x18005 >> 1, (unsigned)(16 * fs58 - 16), 0x18005);
+    {
+        // fold multipliers of the warp-parallel CRCs: range 1 = bytes [4, 2 fs58), range 2 = [2 fs58, frame - 2)
+        const int nbytes = c.frame_words * 2;
+        const int n[2] = {2 * fs58 - 4, nbytes - 2 - 2 * fs58};
+        for (int r = 0; r < 2; r++) {
+            const unsigned L = (unsigned)((n[r] + 31) >> 5);
+            for (int k = 0; k < 5; k++) P.crc_fold[r][k] = (uint16_t)h_pow_poly(2, (8 * L) << k, 0x18005);
+        }
+    }
     for (int i = 0; i < 6; i++) P.chmap[i] = chmap ? chmap[i < channels ? i : 0] : (uint8_t)i;
     for (int i = 0; i < channels; i++)
         if (P.chmap[i] >= channels) {
