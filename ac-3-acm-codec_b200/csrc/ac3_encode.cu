@@ -42,7 +42,8 @@ constexpr int kFrameWords = 968;         // staged output frame, 32-bit words (3
 
 struct EncTables {
     uint32_t taba[16];                   // per bap: plain field bits | 3-level << 8 | 5-level << 16 | 11-level << 24 (counters)
-    uint32_t tabb[16];                   // per bap: levels (0 = asymmetric) | quantiser bits << 8 | field width << 16 | class << 24
+    uint2    tabq[16];                   // per bap: x = levels (0 = asymmetric) | quantiser bits << 8 | field width << 16 | class << 24,
+                                         //          y = taba >> 8 (what the bap adds to the class counters) | its class's counter shift << 24
     uint32_t tabc[64];                   // taba[baptab[address]]: a search probe counts without looking at the bap
     uint8_t  masktab[256];               // (8-byte aligned: read eight bins at a time)
     int16_t  window[256];
@@ -329,19 +330,17 @@ __device__ __forceinline__ void e1_transform(EncShared& S, const EncTables& T, i
     for (int r = 0; r < 8; r++) {
         const int j = lane + 32 * r;
         const int a = abs(out[j]);
-        int e = 24;
-        if (a) {
-            e = 23 - ilog2((uint32_t)a) + es;
-            if (e >= 24) { e = 24; out[j] = 0; }
-        }
-        S.expo[blk][ch][j] = (uint8_t)e;
+        // 23 - ilog2(a) + es = clz(a) - 8 + es; zero and everything at or past 24 read 24, and the latter is zeroed
+        int e = a ? __clz(a) - 8 + es : 24;
+        if (a && e >= 24) out[j] = 0;
+        S.expo[blk][ch][j] = (uint8_t)min(e, 24);
     }
 }
 
 // ---------------------------------------------------------------------------
 // E2: strategies + exponent sets of one channel.  One warp.  Returns the exponent bits.
 // ---------------------------------------------------------------------------
-__device__ int e2_exponents(EncShared& S, const EncParams& P, int ch, int lane)
+__device__ int e2_exponents(EncShared& S, const EncParams& P, int ch, int lane, uint32_t& sets)
 {
     const bool is_lfe = P.lfe && ch == 5;
     const int ncoef = is_lfe ? 7 : 223;
@@ -358,6 +357,7 @@ __device__ int e2_exponents(EncShared& S, const EncParams& P, int ch, int lane)
         for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         if (d > 1000) newmask |= 1u << blk;
     }
+    sets = newmask;                                                      // the blocks that start an exponent set
     int bits = 0;
     for (int i = 0; i < 6;) {
         int j = i + 1;
@@ -703,9 +703,10 @@ ac3_encode_kernel(const EncParams P)
                 if (tid < 36) P.dbg_shift[fidx * 36 + tid] = (tid % 6) < P.nch_all ? (&S.exp_shift[0][0])[tid] : 0;
             }
             // ================= E2 =================
+            uint32_t sets = 0;                                           // this channel's exponent sets, one bit per block
             if (active) {
                 __syncwarp();
-                const int bits = e2_exponents(S, P, warp, lane);
+                const int bits = e2_exponents(S, P, warp, lane, sets);
                 if (lane == 0) S.exp_bits[warp] = bits;
             }
             __syncthreads();
@@ -729,8 +730,7 @@ ac3_encode_kernel(const EncParams P)
             // ================= E3 =================
             if (active) {
                 int16_t* psd = reinterpret_cast<int16_t*>(S.u.e1.z[warp]);      // scratch: 50 band values
-                for (int blk = 0; blk < 6; blk++)
-                    if (S.head[blk][warp] == blk) e3_mask(S, T, P, blk, warp, lane, psd);
+                for (uint32_t m = sets; m; m &= m - 1) e3_mask(S, T, P, __ffs(m) - 1, warp, lane, psd);
             }
             __syncthreads();
             Search q;
@@ -741,11 +741,15 @@ ac3_encode_kernel(const EncParams P)
                 const int snro = (((q.probe_cs - 15) << 4) + q.probe_fs) << 2;
                 if (active) {
                     uint8_t* kb = reinterpret_cast<uint8_t*>(S.u.e1.z[warp]);   // scratch: 6 sets x 64 bands
-                    for (int blk = 0; blk < 6; blk++)
-                        if (S.head[blk][warp] == blk) e3_bands(S, T, P, blk, warp, lane, snro, kb + 64 * blk);
+                    for (uint32_t m = sets; m; m &= m - 1) {
+                        const int blk = __ffs(m) - 1;
+                        e3_bands(S, T, P, blk, warp, lane, snro, kb + 64 * blk);
+                    }
                     __syncwarp();
-                    for (int blk = 0; blk < 6; blk++)
-                        if (S.head[blk][warp] == blk) e3_probe(S, T, P, blk, warp, lane, kb + 64 * blk, false, S.u.e1.pcnt[par]);
+                    for (uint32_t m = sets; m; m &= m - 1) {
+                        const int blk = __ffs(m) - 1;
+                        e3_probe(S, T, P, blk, warp, lane, kb + 64 * blk, false, S.u.e1.pcnt[par]);
+                    }
                 }
                 __syncthreads();
                 search_step(q, bits_left(S, P, lane, S.u.e1.pcnt[par]));
@@ -758,19 +762,21 @@ ac3_encode_kernel(const EncParams P)
                 if (active) {
                     uint8_t* kb = reinterpret_cast<uint8_t*>(S.u.e1.z[warp]);
                     if (!q.failed) {
-                        for (int blk = 0; blk < 6; blk++)
-                            if (S.head[blk][warp] == blk) e3_bands(S, T, P, blk, warp, lane, snro, kb + 64 * blk);
+                        for (uint32_t m = sets; m; m &= m - 1) {
+                            const int blk = __ffs(m) - 1;
+                            e3_bands(S, T, P, blk, warp, lane, snro, kb + 64 * blk);
+                        }
                     }
                     __syncwarp();
-                    for (int blk = 0; blk < 6; blk++)
-                        if (S.head[blk][warp] == blk) {
-                            if (q.failed) {
-                                for (int i = lane; i < 256; i += 32) S.expo[blk][warp][i] = 0;
-                                if (lane < 4) S.cnt[blk][warp][lane] = 0;
-                            } else {
-                                e3_probe(S, T, P, blk, warp, lane, kb + 64 * blk, true, S.cnt);
-                            }
+                    for (uint32_t m = sets; m; m &= m - 1) {
+                        const int blk = __ffs(m) - 1;
+                        if (q.failed) {
+                            for (int i = lane; i < 256; i += 32) S.expo[blk][warp][i] = 0;
+                            if (lane < 4) S.cnt[blk][warp][lane] = 0;
+                        } else {
+                            e3_probe(S, T, P, blk, warp, lane, kb + 64 * blk, true, S.cnt);
                         }
+                    }
                 }
             }
             __syncthreads();
@@ -936,51 +942,54 @@ ac3_encode_kernel(const EncParams P)
                         cf[0] = c0.x; cf[1] = c0.y; cf[2] = c0.z; cf[3] = c0.w;
                         cf[4] = c1.x; cf[5] = c1.y; cf[6] = c1.z; cf[7] = c1.w;
                     }
-                    // (a real loop: unrolled, the eight copies of the quantisers miss the instruction cache)
+                    // (a real loop, two mantissas per trip: unrolled eight times the quantisers miss the instruction
+                    // cache; no branch on the bap - lanes hold different classes, so every path is predicated work)
                     uint2 e8r = e8;
+                    uint32_t Xr = ec;                                    // the classes' counters since the channel start
 #pragma unroll 1
-                    for (int k = 0; k < 8; k++) {
-                        const int b = (int)(b8.x & 15);
-                        const int c = cf[0];
-                        const int e = (int)(e8r.x & 0xff) - gexp;
-                        b8.x = __funnelshift_r(b8.x, b8.y, 8); b8.y >>= 8;
-                        e8r.x = __funnelshift_r(e8r.x, e8r.y, 8); e8r.y >>= 8;
+                    for (int it = 0; it < 4; it++) {
 #pragma unroll
-                        for (int j = 0; j < 7; j++) cf[j] = cf[j + 1];
-                        if (b == 0) continue;
-                        const uint32_t tb = T.tabb[b];
-                        const int lv = (int)(tb & 0xff), qb = (int)((tb >> 8) & 0xff), cl = (int)(tb >> 24);
-                        const uint32_t wd = (tb >> 16) & 0xff;
-                        int v;
-                        {
-                            // symmetric (:1150-1166) and asymmetric (:1169-1190) quantiser side by side
-                            const int a = abs(c);
-                            int vs = (lv * (a << e)) >> 24;
-                            vs = (vs + 1) >> 1;
-                            vs = (lv >> 1) + (c >= 0 ? vs : -vs);
-                            const int lshift = e + qb - 24;
-                            int va = lshift >= 0 ? c << lshift : c >> (-lshift);
-                            va = (va + 1) >> 1;
-                            const int m = 1 << (qb - 1);
-                            if (va >= m) va = m - 1;
-                            va &= (1 << qb) - 1;
-                            v = lv ? vs : va;
-                        }
-                        if (cl) {
-                            int x;
-                            if (cl == 1) x = X1++; else if (cl == 2) x = X2++; else x = X4++;
-                            int g, digit;
-                            if (cl == 3) { g = x >> 1; digit = x & 1; }
-                            else { g = d3(x); digit = x - 3 * g; }
-                            rv[(cl - 1) * 256 + (x & 255)] = (uint8_t)v;
-                            if (digit == 0) {
-                                rp[(cl - 1) * 128 + (g & 127)] = (uint16_t)min(pos, 65535u);
-                                pos += wd;
+                        for (int j = 0; j < 2; j++) {
+                            const uint32_t b = (b8.x >> (8 * j)) & 15;
+                            const int c = cf[j];
+                            const int e = (int)((e8r.x >> (8 * j)) & 0xff) - gexp;
+                            const uint2 tq = T.tabq[b];
+                            const int lv = (int)(tq.x & 0xff), qb = (int)((tq.x >> 8) & 0xff), cl = (int)(tq.x >> 24);
+                            const uint32_t wd = (tq.x >> 16) & 0xff;
+                            int v;
+                            {
+                                // symmetric (:1150-1166) and asymmetric (:1169-1190) quantiser side by side
+                                const int a = abs(c);
+                                int vs = (lv * (a << e)) >> 24;
+                                vs = (vs + 1) >> 1;
+                                vs = (lv >> 1) + (c >= 0 ? vs : -vs);
+                                const int lshift = e + qb - 24;
+                                int va = lshift >= 0 ? c << lshift : c >> (-lshift);
+                                va = (va + 1) >> 1;
+                                const int m = 1 << (qb - 1);
+                                va = min(va, m - 1);
+                                va &= 2 * m - 1;
+                                v = lv ? vs : va;
                             }
-                        } else {
-                            put_bits_atomic(frame, pos, wd, (uint32_t)v);
-                            pos += wd;
+                            // grouped classes: occurrence number x; x % 3 == 0 <=> x * 0xAAAAAAAB <= 0x55555555 (mod 2^32),
+                            // x even <=> x * 2^31 == 0: the member that opens a group reserves the code's place
+                            const uint32_t xr = (Xr >> (tq.y >> 24)) & 0xff;       // (the shift rides in the increment's idle top byte)
+                            Xr += tq.y;
+                            const uint32_t x = (uint32_t)(cl == 1 ? N1 : cl == 2 ? N2 : N4) + xr;
+                            const bool pairs = cl == 3;
+                            const bool opens = x * (pairs ? 0x80000000u : 0xAAAAAAABu) <= (pairs ? 0u : 0x55555555u);
+                            if (cl) {
+                                rv[(cl - 1) * 256 + (x & 255)] = (uint8_t)v;
+                                if (opens) rp[(cl - 1) * 128 + ((x >> 1) & 127)] = (uint16_t)min(pos, 65535u);
+                            } else if (b) {
+                                put_bits_atomic(frame, pos, wd, (uint32_t)v);
+                            }
+                            if (!cl || opens) pos += wd;
                         }
+                        b8.x = __funnelshift_r(b8.x, b8.y, 16); b8.y >>= 16;
+                        e8r.x = __funnelshift_r(e8r.x, e8r.y, 16); e8r.y >>= 16;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) cf[j] = cf[j + 2];
                     }
                     __syncwarp();
                     // the groups this channel closed: lanes = groups
@@ -997,7 +1006,7 @@ ac3_encode_kernel(const EncParams P)
                             const int x0 = cls == 2 ? 2 * g : 3 * g;
                             int code = m0 * r[x0 & 255] + m1 * r[(x0 + 1) & 255];
                             if (cls != 2) code += r[(x0 + 2) & 255];
-                            put_bits_atomic(frame, rp[cls * 128 + (g & 127)], cls == 0 ? 5 : 7, (uint32_t)code);
+                            put_bits_atomic(frame, rp[cls * 128 + ((x0 >> 1) & 127)], cls == 0 ? 5 : 7, (uint32_t)code);
                         }
                     }
                     pos0 += tpl + 5 * (g3(N1 + t1) - g3(N1)) + 7 * (g3(N2 + t2) - g3(N2)) + 7 * (((N4 + t4 + 1) >> 1) - ((N4 + 1) >> 1));
@@ -1015,7 +1024,7 @@ ac3_encode_kernel(const EncParams P)
                         const int m0 = lane == 0 ? 9 : lane == 1 ? 25 : 11, m1 = lane == 0 ? 3 : 5;
                         int code = m0 * r[x0 & 255];
                         if (rem == 2) code += m1 * r[(x0 + 1) & 255];
-                        put_bits_atomic(frame, rp[lane * 128 + (g & 127)], lane == 0 ? 5 : 7, (uint32_t)code);
+                        put_bits_atomic(frame, rp[lane * 128 + ((x0 >> 1) & 127)], lane == 0 ? 5 : 7, (uint32_t)code);
                     }
                 }
             }

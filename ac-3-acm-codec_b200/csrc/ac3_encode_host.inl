@@ -65,7 +65,8 @@ static void build_enc_tables(EncTables* T)
         static const uint8_t levels[16] = {0, 3, 5, 7, 11, 15, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const uint32_t qbits = b < 6 ? 1 : b == 14 ? 14 : b == 15 ? 16 : b - 1;
         const uint32_t cls = b == 1 ? 1 : b == 2 ? 2 : b == 4 ? 3 : 0;
-        T->tabb[b] = levels[b] | qbits << 8 | (uint32_t)ac3_bap_bits[b] << 16 | cls << 24;
+        T->tabq[b].x = b ? (levels[b] | qbits << 8 | (uint32_t)ac3_bap_bits[b] << 16 | cls << 24) : 0u;
+        T->tabq[b].y = (T->taba[b] >> 8) | (cls ? 8 * (cls - 1) : 0) << 24;
     }
     for (int a = 0; a < 64; a++) T->tabc[a] = T->taba[ac3_baptab[a]];
 }

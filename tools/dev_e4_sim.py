@@ -90,6 +90,7 @@ def pack_block(fr, blk, nch_all, lfe, coef, enc, bap, exp_shift, mant_pos):
         for lane in range(32):
             ec, ep = icnt[lane] - cnt[lane], ipl[lane] - pl[lane]
             X1, X2, X4 = N1 + (ec & 0xff), N2 + ((ec >> 8) & 0xff), N4 + (ec >> 16)
+            Xr = ec
             pos = pos0 + ep + 5 * (G3(X1) - G3(N1)) + 7 * (G3(X2) - G3(N2)) + 7 * (G2(X4) - G2(N4))
             for k in range(8):
                 b = bb[lane][k]
@@ -101,20 +102,17 @@ def pack_block(fr, blk, nch_all, lfe, coef, enc, bap, exp_shift, mant_pos):
                 v = quant(b, c, e)
                 cl = CLS[b]
                 if cl:
-                    if cl == 1:
-                        x = X1; X1 += 1
-                    elif cl == 2:
-                        x = X2; X2 += 1
-                    else:
-                        x = X4; X4 += 1
-                    if cl == 3:
-                        g, digit = x >> 1, x & 1
-                    else:
-                        g = (x * 43691) >> 17
-                        digit = x - 3 * g
+                    # packed per-class counters relative to the channel start; the carrier test is a multiply
+                    # (x % 3 == 0 <=> x * 0xAAAAAAAB mod 2^32 <= 0x55555555; x even <=> x * 2^31 mod 2^32 == 0)
+                    xr = (Xr >> (8 * cl - 8)) & 0xff
+                    Xr += TABA[b] >> 8
+                    x = (N1, N2, N4)[cl - 1] + xr
+                    M, Tt = (0x80000000, 0) if cl == 3 else (0xAAAAAAAB, 0x55555555)
+                    carrier = ((x * M) & 0xffffffff) <= Tt
+                    assert carrier == ((x & 1) == 0 if cl == 3 else x % 3 == 0)
                     writes_v.append((cl - 1, x & 255, v))
-                    if digit == 0:
-                        writes_p.append((cl - 1, g & 127, pos))
+                    if carrier:
+                        writes_p.append((cl - 1, (x >> 1) & 127, pos))
                         pos += WIDTH[b]
                 else:
                     fr.put(pos, WIDTH[b], v)
@@ -133,15 +131,15 @@ def pack_block(fr, blk, nch_all, lfe, coef, enc, bap, exp_shift, mant_pos):
             if i < n1g:
                 g = d1a + i; x0 = 3 * g
                 code = 9 * ring_v[0, x0 & 255] + 3 * ring_v[0, (x0 + 1) & 255] + ring_v[0, (x0 + 2) & 255]
-                fr.put(int(ring_p[0, g & 127]), 5, int(code))
+                fr.put(int(ring_p[0, (x0 >> 1) & 127]), 5, int(code))
             elif i < n1g + n2g:
                 g = d2a + i - n1g; x0 = 3 * g
                 code = 25 * ring_v[1, x0 & 255] + 5 * ring_v[1, (x0 + 1) & 255] + ring_v[1, (x0 + 2) & 255]
-                fr.put(int(ring_p[1, g & 127]), 7, int(code))
+                fr.put(int(ring_p[1, (x0 >> 1) & 127]), 7, int(code))
             else:
                 g = d4a + i - n1g - n2g; x0 = 2 * g
                 code = 11 * ring_v[2, x0 & 255] + ring_v[2, (x0 + 1) & 255]
-                fr.put(int(ring_p[2, g & 127]), 7, int(code))
+                fr.put(int(ring_p[2, (x0 >> 1) & 127]), 7, int(code))
         pos0 += tpl + 5 * (G3(N1 + t1) - G3(N1)) + 7 * (G3(N2 + t2) - G3(N2)) + 7 * (G2(N4 + t4) - G2(N4))
         N1 += t1; N2 += t2; N4 += t4
     # the block's open groups
@@ -149,12 +147,12 @@ def pack_block(fr, blk, nch_all, lfe, coef, enc, bap, exp_shift, mant_pos):
     if r:
         g = (N1 * 43691) >> 17; x0 = 3 * g
         code = 9 * ring_v[0, x0 & 255] + (3 * ring_v[0, (x0 + 1) & 255] if r == 2 else 0)
-        fr.put(int(ring_p[0, g & 127]), 5, int(code))
+        fr.put(int(ring_p[0, (x0 >> 1) & 127]), 5, int(code))
     r = N2 - 3 * ((N2 * 43691) >> 17)
     if r:
         g = (N2 * 43691) >> 17; x0 = 3 * g
         code = 25 * ring_v[1, x0 & 255] + (5 * ring_v[1, (x0 + 1) & 255] if r == 2 else 0)
-        fr.put(int(ring_p[1, g & 127]), 7, int(code))
+        fr.put(int(ring_p[1, (x0 >> 1) & 127]), 7, int(code))
     if N4 & 1:
         g = N4 >> 1
         fr.put(int(ring_p[2, g & 127]), 7, int(11 * ring_v[2, (2 * g) & 255]))
