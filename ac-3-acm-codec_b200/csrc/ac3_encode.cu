@@ -79,7 +79,6 @@ struct EncParams {
     int nstreams, nframes;
     int nch_all, nch, lfe, acmod, fscod, halfrate, bsid, frmsizecod, frame_words;
     uint32_t crc_inv;                    // x^-(16 fs58 - 16) mod poly (ac3enc.cpp:1627)
-    uint16_t crc_fold[2][5];             // x^(8 L 2^k) mod poly, L = chunk bytes per lane of the two CRC ranges
     uint8_t chmap[8];
     // optional dumps
     int32_t* dbg_coef;
@@ -115,7 +114,7 @@ struct EncShared {
     int      exp_bits[6];                // per channel: bits of its exponent sections (ac3enc.cpp:760)
     int      frame_bits;                 // everything but mantissas
     int      cs, fs, failed;             // result of the search (and the warm start of the next frame's)
-    uint32_t crc[2];
+    uint32_t crcp[6];                    // the warps' parts of the two CRCs
 };
 
 __device__ __forceinline__ int ilog2(uint32_t v) { return v ? 31 - __clz(v) : 0; }
@@ -134,16 +133,23 @@ __device__ __forceinline__ void put_bits_atomic(uint32_t* frame, uint32_t pos, u
     if (lo) atomicOr(&frame[wi + 1], lo);
 }
 
-// the same out of line for the side information (some fifty fields written once per frame by a few lanes)
-__device__ __noinline__ void put_bits_call(uint32_t* frame, uint32_t pos, uint32_t n, uint32_t v)
-{
-    put_bits_atomic(frame, pos, n, v);
-}
-
-struct SerialBits {                      // single-thread bit cursor for the side information
-    uint32_t* frame;
-    uint32_t pos;
-    __device__ __forceinline__ void put(uint32_t n, uint32_t v) { put_bits_call(frame, pos, n, v); pos += n; }
+// A run of at most 64 bits of side information collected in a register and written in one go.
+struct BitRun {
+    uint64_t acc;
+    uint32_t n;
+    __device__ __forceinline__ void put(uint32_t k, uint32_t v) { acc = (acc << k) | v; n += k; }
+    // writes the run at bit `pos` of the frame (big-endian bit order) and returns the position after it
+    __device__ __forceinline__ uint32_t flush(uint32_t* frame, uint32_t pos) const
+    {
+        if (n == 0 || pos + n > kFrameWords * 32) return pos + n;
+        const uint64_t x = acc << (64 - n);
+        const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x, wi = pos >> 5, sh = pos & 31;
+        const uint32_t w0 = hi >> sh, w1 = __funnelshift_r(lo, hi, sh), w2 = __funnelshift_r(0u, lo, sh);
+        if (w0) atomicOr(&frame[wi], w0);
+        if (w1) atomicOr(&frame[wi + 1], w1);
+        if (w2) atomicOr(&frame[wi + 2], w2);
+        return pos + n;
+    }
 };
 
 __device__ __forceinline__ int sym_quant(int c, int e, int levels)      // ac3enc.cpp:1150-1166
@@ -178,31 +184,20 @@ __device__ __noinline__ uint32_t mul_poly(uint32_t a, uint32_t b)      // ac3enc
     return c;
 }
 
-// CRC-16 (poly 0x8005, init 0) of frame bytes [b0, b1) by one warp: every lane runs the table CRC over
-// an equal chunk (chunks are aligned to the END of the range: leading zero bytes do not change a
-// zero-initialised CRC), then the chunks are folded pairwise: crc(A|B) = crc(A) * x^(8 len B) ^ crc(B);
-// fold[k] = x^(8 L 2^k) mod poly comes from the host (the ranges are the same for every frame of a call).
-__device__ __forceinline__ uint32_t warp_crc(const EncTables& T, const uint32_t* frame, int b0, int b1, int lane,
-                                             const uint16_t (&fold)[5])
+// CRC-16 (poly 0x8005, init 0) over a byte range of the frame by 96 threads: every thread runs the table CRC over
+// an equal chunk (chunks are aligned to the END of the range: leading zero bytes do not change a zero-initialised
+// CRC) and multiplies it by x^(8 * bytes after its chunk) - a constant of the thread, worked out once per launch -
+// so that the range's CRC is the XOR of the threads' values (the CRC is linear over GF(2)).
+__device__ __forceinline__ uint32_t crc_chunk(const EncTables& T, const uint32_t* frame, int b0, int start, int L)
 {
-    const int n = b1 - b0;
-    const int L = (n + 31) >> 5;
-    const int start = b1 - (32 - lane) * L;
     uint32_t crc = 0;
 #pragma unroll 1
     for (int k = 0; k < L; k++) {
-        int idx = start + k;
-        uint32_t byte = (idx >= b0) ? ((frame[idx >> 2] >> (24 - 8 * (idx & 3))) & 0xff) : 0u;
+        const int idx = start + k;
+        const uint32_t byte = (idx >= b0) ? ((frame[idx >> 2] >> (24 - 8 * (idx & 3))) & 0xff) : 0u;
         crc = (T.crc_table[byte ^ (crc >> 8)] ^ (crc << 8)) & 0xffff;
     }
-#pragma unroll 1
-    for (int k = 0; k < 5; k++) {
-        const int o = 1 << k;
-        uint32_t right = __shfl_down_sync(0xffffffffu, crc, o);
-        const uint32_t folded = mul_poly(crc, fold[k]) ^ right;
-        if ((lane & (2 * o - 1)) == 0) crc = folded;
-    }
-    return __shfl_sync(0xffffffffu, crc, 0);
+    return crc;
 }
 
 // ---------------------------------------------------------------------------
@@ -641,6 +636,19 @@ ac3_encode_kernel(const EncParams P)
     __syncthreads();
     const int nbytes = P.frame_words * 2;
     const bool active = warp < P.nch_all;                              // warp = coded channel
+    // CRC constants of this thread (frame end, :1599-1638): warps 0..2 share crc1's range, bytes [4, 5/8 of the frame),
+    // warps 3..5 crc2's, [5/8, end - 2); crc1's multipliers also carry the inverse-polynomial factor (:1627)
+    const int fs58 = (P.frame_words >> 1) + (P.frame_words >> 3);
+    const int crc_b0 = warp < 3 ? 4 : 2 * fs58, crc_b1 = warp < 3 ? 2 * fs58 : nbytes - 2;
+    const int crc_L = (crc_b1 - crc_b0 + 95) / 96;
+    const int crc_start = crc_b1 - (96 - (tid - (warp < 3 ? 0 : 96))) * crc_L;
+    uint32_t crc_mult = 1;
+    {
+        const int after = crc_b1 - (crc_start + crc_L);
+#pragma unroll 1
+        for (int k = 0; k < after; k++) crc_mult = (T.crc_table[crc_mult >> 8] ^ (crc_mult << 8)) & 0xffff;
+        if (warp < 3) crc_mult = mul_poly(crc_mult, P.crc_inv);
+    }
 
     // Work units are slices of streams (P.slice_frames frames), handed out slice-major from one ticket counter;
     // a slice starts from the carry record its predecessor left in global memory.  The predecessor holds a
@@ -796,13 +804,13 @@ ac3_encode_kernel(const EncParams P)
             for (int i = tid; i < kFrameWords; i += kThreads) frame[i] = 0;
             __syncthreads();
             if (warp == 0) {
-                // side information (:1113-1147, 1210-1259, 1316-1337): lane 0 writes the BSI, lanes 0..5 then
-                // size one block each, a prefix sum places the blocks, and every lane writes its block's
-                // fields; sections written later by the channel warps are skipped over, positions recorded
-                SerialBits w{frame, 0};
+                // side information (:1113-1147, 1210-1259, 1316-1337): lane 0 writes the BSI, lanes 0..5 then size one
+                // block each and a prefix sum places the blocks.  A block's fields are two runs of at most 64 bits -
+                // up to the exponents, and from the bit allocation flag to the skip flag - which a lane collects in
+                // a register and writes with three atomic ORs each; the exponent and mantissa sections between and
+                // after them are written later by the block's warp, their positions recorded here.
                 if (lane == 0) {
-                    w.put(16, 0x0b77);
-                    w.put(16, 0);
+                    BitRun w{0, 0};
                     w.put(2, P.fscod);
                     w.put(6, P.frmsizecod);
                     w.put(5, P.bsid);
@@ -816,8 +824,11 @@ ac3_encode_kernel(const EncParams P)
                     w.put(4, 0);
                     w.put(1, 1);
                     w.put(3, 0);
+                    atomicOr(&frame[0], 0x0b770000u);                    // sync word; crc1 comes at the frame end
+                    w.flush(frame, 32);
                 }
-                const uint32_t bsi_bits = __shfl_sync(0xffffffffu, w.pos, 0);
+                const uint32_t bsi_bits = 16 + 16 + 2 + 6 + 5 + 3 + 3 + (((P.acmod & 1) && P.acmod != 1) ? 2 : 0)
+                                        + ((P.acmod & 4) ? 2 : 0) + (P.acmod == 2 ? 2 : 0) + 1 + 5 + 4 + 1 + 3;
                 const int blk = lane < 6 ? lane : 5;
                 uint32_t exp_len[6], len = 0, mant = 0;
                 {
@@ -850,7 +861,8 @@ ac3_encode_kernel(const EncParams P)
                     if (lane >= o) incl += t;
                 }
                 if (lane < 6) {
-                    w.pos = bsi_bits + incl - len;
+                    uint32_t pos = bsi_bits + incl - len;
+                    BitRun w{0, 0};
                     w.put(P.nch, 0);                                     // blksw
                     w.put(P.nch, (1u << P.nch) - 1);                     // dithflag
                     w.put(1, 0);                                         // dynrnge
@@ -860,21 +872,23 @@ ac3_encode_kernel(const EncParams P)
                     if (P.lfe) w.put(1, S.strategy[blk][5]);
                     for (int ch = 0; ch < P.nch; ch++)
                         if (S.strategy[blk][ch]) w.put(6, 50);
+                    pos = w.flush(frame, pos);                           // at most 11 + 2 + 5 + 10 + 1 + 30 = 59 bits
 #pragma unroll
                     for (int ch = 0; ch < 6; ch++) {
                         if (ch >= P.nch_all || !exp_len[ch]) continue;
-                        S.exp_pos[blk][ch] = w.pos;
-                        w.pos += exp_len[ch];
+                        S.exp_pos[blk][ch] = pos;
+                        pos += exp_len[ch];
                     }
+                    w = BitRun{0, 0};
                     w.put(1, blk == 0);
                     if (blk == 0) w.put(11, (2u << 9) | (1u << 7) | (1u << 5) | (2u << 3) | 4u);
                     w.put(1, blk == 0);
                     if (blk == 0) {
                         w.put(6, S.cs);
-                        for (int ch = 0; ch < P.nch_all; ch++) { w.put(4, S.fs); w.put(3, 4); }
+                        for (int ch = 0; ch < P.nch_all; ch++) w.put(7, ((uint32_t)S.fs << 3) | 4u);
                     }
                     w.put(2, 0);
-                    S.mant_pos[blk] = w.pos;
+                    S.mant_pos[blk] = w.flush(frame, pos);               // at most 1 + 11 + 1 + 6 + 42 + 2 = 63 bits
                 }
             }
             __syncthreads();
@@ -1029,38 +1043,24 @@ ac3_encode_kernel(const EncParams P)
                 }
             }
             __syncthreads();
-            // frame end (:1599-1638): crc1 over the first 5/8 through the inverse polynomial trick,
-            // crc2 over the rest, stored over the last two bytes whatever spilled into them
+            // frame end (:1599-1638): crc1 over the first 5/8 through the inverse polynomial trick, crc2 over the
+            // rest, stored over the last two bytes whatever spilled into them (the stereo bit-accounting slip, :889)
             {
-                const int fs58 = (P.frame_words >> 1) + (P.frame_words >> 3);
-                if (tid == 0) {
-                    // bytes past the payload that belong to the crc2 field are excluded below; clear the
-                    // field first so that payload overflow (stereo bit-accounting slip, :889) is dropped
-                    const int k = nbytes - 2;
-                    frame[k >> 2] &= ~(0xffffu << (16 - 8 * (k & 3)));
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    uint32_t c1 = warp_crc(T, frame, 4, 2 * fs58, lane, P.crc_fold[0]);
-                    if (lane == 0) S.crc[0] = mul_poly(P.crc_inv, c1);
-                } else if (warp == 1) {
-                    uint32_t c2 = warp_crc(T, frame, 2 * fs58, nbytes - 2, lane, P.crc_fold[1]);
-                    if (lane == 0) S.crc[1] = c2;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    frame[0] |= S.crc[0] & 0xffff;                           // bytes 2, 3
-                    const int k = nbytes - 2;
-                    frame[k >> 2] |= (S.crc[1] & 0xffff) << (16 - 8 * (k & 3));
-                }
+                uint32_t crc = mul_poly(crc_chunk(T, frame, crc_b0, crc_start, crc_L), crc_mult);
+                crc = __reduce_xor_sync(0xffffffffu, crc);
+                if (lane == 0) S.crcp[warp] = crc;
                 __syncthreads();
             }
-            // store (big-endian bytes): frames start at even offsets, so 16-bit stores
+            // store (big-endian bytes): frames start at even offsets, so 16-bit stores; the threads that hold the
+            // CRC fields (bytes 2, 3 and the last two) put the sums of the warps' parts there
             {
+                const uint32_t c1 = (S.crcp[0] ^ S.crcp[1] ^ S.crcp[2]) & 0xffff, c2 = (S.crcp[3] ^ S.crcp[4] ^ S.crcp[5]) & 0xffff;
                 uint16_t* dst = reinterpret_cast<uint16_t*>(P.out + fidx * nbytes);
                 for (int i = tid; i < P.frame_words; i += kThreads) {
                     const uint32_t wv = frame[i >> 1];
-                    const uint32_t h = (i & 1) ? (wv & 0xffff) : (wv >> 16);
+                    uint32_t h = (i & 1) ? (wv & 0xffff) : (wv >> 16);
+                    if (i == 1) h = c1;
+                    if (i == P.frame_words - 1) h = c2;
                     dst[i] = (uint16_t)(((h & 0xff) << 8) | (h >> 8));
                 }
                 if (tid == 0 && P.status) P.status[fidx] = S.failed ? AC3_ST_NO_FIT : AC3_ST_OK;

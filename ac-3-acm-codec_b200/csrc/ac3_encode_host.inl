@@ -248,15 +248,6 @@ int ac3_batch_encode(ac3_batch_t* ctx, const int16_t* pcm, int nstreams, int nfr
     P.halfrate = c.halfrate; P.bsid = c.bsid; P.frmsizecod = c.frmsizecod; P.frame_words = c.frame_words;
     const int fs58 = (c.frame_words >> 1) + (c.frame_words >> 3);
     P.crc_inv = h_pow_poly(0x18005 >> 1, (unsigned)(16 * fs58 - 16), 0x18005);
-    {
-        // fold multipliers of the warp-parallel CRCs: range 1 = bytes [4, 2 fs58), range 2 = [2 fs58, frame - 2)
-        const int nbytes = c.frame_words * 2;
-        const int n[2] = {2 * fs58 - 4, nbytes - 2 - 2 * fs58};
-        for (int r = 0; r < 2; r++) {
-            const unsigned L = (unsigned)((n[r] + 31) >> 5);
-            for (int k = 0; k < 5; k++) P.crc_fold[r][k] = (uint16_t)h_pow_poly(2, (8 * L) << k, 0x18005);
-        }
-    }
     for (int i = 0; i < 6; i++) P.chmap[i] = chmap ? chmap[i < channels ? i : 0] : (uint8_t)i;
     for (int i = 0; i < channels; i++)
         if (P.chmap[i] >= channels) {
