@@ -43,7 +43,7 @@ constexpr int kFrameWords = 968;         // staged output frame, 32-bit words (3
 struct EncTables {
     uint32_t taba[16];                   // per bap: plain field bits | 3-level << 8 | 5-level << 16 | 11-level << 24 (counters)
     uint2    tabq[16];                   // per bap: x = levels (0 = asymmetric) | quantiser bits << 8 | field width << 16 | class << 24,
-                                         //          y = taba >> 8 (what the bap adds to the class counters) | its class's counter shift << 24
+                                         //          y = what the bap adds to the packed class counters (1 << 10 (class - 1), or 0)
     uint32_t tabc[64];                   // taba[baptab[address]]: a search probe counts without looking at the bap
     uint8_t  masktab[256];               // (8-byte aligned: read eight bins at a time)
     int16_t  window[256];
@@ -471,6 +471,7 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
     }
     __syncwarp();
     int16_t* mk = S.u.e1.mask[blk][ch];
+    int fast21 = 0, slow21 = 0;                                          // the recurrences' state after band 21
     if (lane == 0) {
         auto lc1 = [](int a, int b0, int b1) { return (b0 + 256 == b1) ? 384 : (b0 > b1) ? max(a - 64, 0) : a; };
         int lowcomp = 0, fast = 0, slow = 0, begin = 7, bin;
@@ -498,11 +499,26 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
             slow = max(slow - sdecay, psd[bin] - sgain);
             mk[bin] = (int16_t)max(fast - lowcomp, slow);
         }
-        for (bin = 22; bin < bndend; bin++) {
-            fast = max(fast - fdecay, psd[bin] - fgain);
-            slow = max(slow - sdecay, psd[bin] - sgain);
-            mk[bin] = (int16_t)max(fast, slow);
+        fast21 = fast;
+        slow21 = slow;
+    }
+    // bands 22 and up: fast = max(fast - fdecay, psd - fgain) and the same for slow are max-plus recurrences without
+    // side conditions, i.e. prefix maxima of psd + j * decay: lane j takes band 22 + j
+    if (bndend > 22) {
+        fast21 = __shfl_sync(0xffffffffu, fast21, 0);
+        slow21 = __shfl_sync(0xffffffffu, slow21, 0);
+        const int bin = 22 + lane;
+        const bool on = bin < bndend;
+        const int p = on ? psd[bin] : -(1 << 20);
+        int pf = p - fgain + lane * fdecay, ps = p - sgain + lane * sdecay;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tf = __shfl_up_sync(0xffffffffu, pf, o), ts = __shfl_up_sync(0xffffffffu, ps, o);
+            if (lane >= o) { pf = max(pf, tf); ps = max(ps, ts); }
         }
+        const int f = max(fast21 - (lane + 1) * fdecay, pf - lane * fdecay);
+        const int sl = max(slow21 - (lane + 1) * sdecay, ps - lane * sdecay);
+        if (on) mk[bin] = (int16_t)max(f, sl);
     }
     __syncwarp();
     for (int band = lane; band < bndend; band += 32) {
@@ -892,8 +908,29 @@ ac3_encode_kernel(const EncParams P)
                 }
             }
             __syncthreads();
+            if (active) {
+                // grouped exponents (:1261-1314): warp = channel (the sets are spread evenly over the channels, not
+                // over the blocks), lanes = groups
+                const int ch = warp;
+                const int ncoef = (P.lfe && ch == 5) ? 7 : 223;
+                for (int blk = 0; blk < 6; blk++) {
+                    const int st = S.strategy[blk][ch];
+                    if (!st) continue;
+                    const uint8_t* en = S.enc[blk][ch];
+                    const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
+                    const int ng = (ncoef + gs * 3 - 4) / (3 * gs);
+                    const uint32_t p0 = S.exp_pos[blk][ch];
+                    if (lane == 0) put_bits_atomic(frame, p0, 4, en[0]);
+                    for (int g = lane; g < ng; g += 32) {
+                        const int k = 1 + 3 * g * gs;
+                        const int ea = g ? en[k - gs] : en[0];
+                        const int d0 = en[k] - ea + 2, d1 = en[k + gs] - en[k] + 2, d2 = en[k + 2 * gs] - en[k + gs] + 2;
+                        put_bits_atomic(frame, p0 + 4 + 7 * g, 7, (uint32_t)((d0 * 5 + d1) * 5 + d2));
+                    }
+                }
+            }
             {
-                // exponents and mantissas (:1261-1314, 1346-1501): warp = audio block, walking the block's channels in
+                // mantissas (:1346-1501): warp = audio block, walking the block's channels in
                 // coded order (the occurrence numbers of the grouped classes run across channels); a lane owns eight
                 // consecutive bins.  No barrier and no accumulator shared between warps: group members go to the
                 // block's rings, the lanes then emit the codes of the groups the channel closed.
@@ -909,20 +946,6 @@ ac3_encode_kernel(const EncParams P)
                     const int ncoef = is_lfe ? 7 : 223;
                     const int h = S.head[blk][ch];
                     const uint8_t* en = S.enc[h][ch];
-                    // grouped exponents: lanes = groups
-                    const int st = S.strategy[blk][ch];
-                    if (st) {
-                        const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
-                        const int ng = (ncoef + gs * 3 - 4) / (3 * gs);
-                        const uint32_t p0 = S.exp_pos[blk][ch];
-                        if (lane == 0) put_bits_atomic(frame, p0, 4, en[0]);
-                        for (int g = lane; g < ng; g += 32) {
-                            const int k = 1 + 3 * g * gs;
-                            const int ea = g ? en[k - gs] : en[0];
-                            const int d0 = en[k] - ea + 2, d1 = en[k + gs] - en[k] + 2, d2 = en[k + 2 * gs] - en[k + gs] + 2;
-                            put_bits_atomic(frame, p0 + 4 + 7 * g, 7, (uint32_t)((d0 * 5 + d1) * 5 + d2));
-                        }
-                    }
                     // mantissas
                     const int i0 = 8 * lane;
                     const int nvalid = min(max(ncoef - i0, 0), 8);
@@ -959,7 +982,11 @@ ac3_encode_kernel(const EncParams P)
                     // (a real loop, two mantissas per trip: unrolled eight times the quantisers miss the instruction
                     // cache; no branch on the bap - lanes hold different classes, so every path is predicated work)
                     uint2 e8r = e8;
-                    uint32_t Xr = ec;                                    // the classes' counters since the channel start
+                    uint32_t Xm;                                         // the classes' occurrence counters at this lane
+                    {
+                        const uint32_t m1 = N1 >= 768 ? N1 - 768 : N1, m2 = N2 >= 768 ? N2 - 768 : N2, m4 = N4 >= 768 ? N4 - 768 : N4;
+                        Xm = (m1 + (ec & 0xff)) | (m2 + ((ec >> 8) & 0xff)) << 10 | (m4 + (ec >> 16)) << 20;
+                    }
 #pragma unroll 1
                     for (int it = 0; it < 4; it++) {
 #pragma unroll
@@ -987,9 +1014,10 @@ ac3_encode_kernel(const EncParams P)
                             }
                             // grouped classes: occurrence number x; x % 3 == 0 <=> x * 0xAAAAAAAB <= 0x55555555 (mod 2^32),
                             // x even <=> x * 2^31 == 0: the member that opens a group reserves the code's place
-                            const uint32_t xr = (Xr >> (tq.y >> 24)) & 0xff;       // (the shift rides in the increment's idle top byte)
-                            Xr += tq.y;
-                            const uint32_t x = (uint32_t)(cl == 1 ? N1 : cl == 2 ? N2 : N4) + xr;
+                            // (counters modulo 768 = 3 * 256 in ten-bit fields: x is only used modulo 256, 3 and 2)
+                            const uint32_t xsh = (uint32_t)(10 * cl + 22) & 31;
+                            const uint32_t x = (Xm >> xsh) & 0x3ff;
+                            Xm += tq.y;                                  // 1 << xsh for a grouped bap, else 0
                             const bool pairs = cl == 3;
                             const bool opens = x * (pairs ? 0x80000000u : 0xAAAAAAABu) <= (pairs ? 0u : 0x55555555u);
                             if (cl) {

@@ -66,7 +66,7 @@ static void build_enc_tables(EncTables* T)
         const uint32_t qbits = b < 6 ? 1 : b == 14 ? 14 : b == 15 ? 16 : b - 1;
         const uint32_t cls = b == 1 ? 1 : b == 2 ? 2 : b == 4 ? 3 : 0;
         T->tabq[b].x = b ? (levels[b] | qbits << 8 | (uint32_t)ac3_bap_bits[b] << 16 | cls << 24) : 0u;
-        T->tabq[b].y = (T->taba[b] >> 8) | (cls ? 8 * (cls - 1) : 0) << 24;
+        T->tabq[b].y = cls ? 1u << (10 * (cls - 1)) : 0u;
     }
     for (int a = 0; a < 64; a++) T->tabc[a] = T->taba[ac3_baptab[a]];
 }

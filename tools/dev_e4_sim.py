@@ -90,7 +90,7 @@ def pack_block(fr, blk, nch_all, lfe, coef, enc, bap, exp_shift, mant_pos):
         for lane in range(32):
             ec, ep = icnt[lane] - cnt[lane], ipl[lane] - pl[lane]
             X1, X2, X4 = N1 + (ec & 0xff), N2 + ((ec >> 8) & 0xff), N4 + (ec >> 16)
-            Xr = ec
+            Xm = (N1 % 768 + (ec & 0xff)) | (N2 % 768 + ((ec >> 8) & 0xff)) << 10 | (N4 % 768 + (ec >> 16)) << 20
             pos = pos0 + ep + 5 * (G3(X1) - G3(N1)) + 7 * (G3(X2) - G3(N2)) + 7 * (G2(X4) - G2(N4))
             for k in range(8):
                 b = bb[lane][k]
@@ -104,12 +104,14 @@ def pack_block(fr, blk, nch_all, lfe, coef, enc, bap, exp_shift, mant_pos):
                 if cl:
                     # packed per-class counters relative to the channel start; the carrier test is a multiply
                     # (x % 3 == 0 <=> x * 0xAAAAAAAB mod 2^32 <= 0x55555555; x even <=> x * 2^31 mod 2^32 == 0)
-                    xr = (Xr >> (8 * cl - 8)) & 0xff
-                    Xr += TABA[b] >> 8
-                    x = (N1, N2, N4)[cl - 1] + xr
+                    # (absolute counters modulo 768 = 3 * 256, ten bits each: all uses of x are modulo 256, 3 or 2)
+                    sh = (10 * cl + 22) & 31
+                    x = (Xm >> sh) & 0x3ff
+                    Xm += 1 << sh
                     M, Tt = (0x80000000, 0) if cl == 3 else (0xAAAAAAAB, 0x55555555)
                     carrier = ((x * M) & 0xffffffff) <= Tt
                     assert carrier == ((x & 1) == 0 if cl == 3 else x % 3 == 0)
+                    assert x < 1024
                     writes_v.append((cl - 1, x & 255, v))
                     if carrier:
                         writes_p.append((cl - 1, (x >> 1) & 127, pos))
