@@ -987,6 +987,8 @@ ac3_encode_kernel(const EncParams P)
                         const uint32_t m1 = N1 >= 768 ? N1 - 768 : N1, m2 = N2 >= 768 ? N2 - 768 : N2, m4 = N4 >= 768 ? N4 - 768 : N4;
                         Xm = (m1 + (ec & 0xff)) | (m2 + ((ec >> 8) & 0xff)) << 10 | (m4 + (ec >> 16)) << 20;
                     }
+                    BitRun run{0, 0};
+                    uint32_t run_pos = pos;
 #pragma unroll 1
                     for (int it = 0; it < 4; it++) {
 #pragma unroll
@@ -1023,10 +1025,18 @@ ac3_encode_kernel(const EncParams P)
                             if (cl) {
                                 rv[(cl - 1) * 256 + (x & 255)] = (uint8_t)v;
                                 if (opens) rp[(cl - 1) * 128 + ((x >> 1) & 127)] = (uint16_t)min(pos, 65535u);
-                            } else if (b) {
-                                put_bits_atomic(frame, pos, wd, (uint32_t)v);
                             }
-                            if (!cl || opens) pos += wd;
+                            // the lane's mantissas are consecutive in the stream: ungrouped fields (and zeros where a
+                            // group code will go) collect in a run that is written every four mantissas (<= 64 bits)
+                            const uint32_t adv = (!cl || opens) ? wd : 0u;
+                            run.acc = (run.acc << adv) | ((b && !cl) ? (uint32_t)v : 0u);
+                            run.n += adv;
+                            pos += adv;
+                        }
+                        if (it & 1) {
+                            run.flush(frame, run_pos);
+                            run_pos = pos;
+                            run = BitRun{0, 0};
                         }
                         b8.x = __funnelshift_r(b8.x, b8.y, 16); b8.y >>= 16;
                         e8r.x = __funnelshift_r(e8r.x, e8r.y, 16); e8r.y >>= 16;
