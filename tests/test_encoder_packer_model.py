@@ -1,16 +1,13 @@
-"""Developer tool (CPU): lane-level model of the encoder's block-warp mantissa packer (ac3_encode.cu, stage E4)
-checked against the encoder oracle's frames.  A warp owns one audio block and walks its channels in coded order; a
-lane owns eight consecutive bins.  Test infrastructure only (imports oracle/ through tests/refbind.py).
-Usage: python tools/dev_e4_sim.py"""
-import os
-import sys
-
+"""CPU test: lane-level model of the encoder kernel's block-warp mantissa packer (csrc/ac3_encode.cu, stage E4;
+reference src/ac3enc/ac3enc.cpp:1346-1501) checked bit for bit against the encoder oracle's frames.  A warp owns one
+audio block and walks its channels in coded order; a lane owns eight consecutive bins; class counters, the multiply
+test for the member that opens a group and the rings are written exactly as the kernel writes them, so the algorithm is
+pinned here without a GPU (the kernel itself is compared byte for byte in tests/test_encoder_gpu.py)."""
 import numpy as np
+import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from refbind import OracleEnc  # noqa: E402
-from synth import synth_pcm  # noqa: E402
+from refbind import OracleEnc
+from synth import synth_pcm
 
 PLAIN = [0, 0, 0, 3, 0, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16]
 WIDTH = [0, 5, 7, 3, 7, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16]
@@ -192,37 +189,32 @@ def side_lengths(nch_all, lfe, acmod, strategy, bap):
     return out
 
 
-def main():
+CONFIGS = [(6, 448000, 48000), (6, 384000, 44100), (5, 320000, 48000), (4, 192000, 44100), (3, 128000, 48000),
+           (2, 192000, 48000), (2, 96000, 48000), (1, 64000, 32000), (2, 128000, 22050), (6, 640000, 48000),
+           (6, 32000, 48000)]
+
+
+@pytest.mark.parametrize("nch,br,rate", CONFIGS)
+def test_packer_model_reproduces_the_oracle_mantissa_bits(nch, br, rate):
     ora = OracleEnc()
     acmod_of = {1: 1, 2: 2, 3: 3, 4: 6, 5: 7, 6: 7}
+    lfe = nch == 6
     total = 0
-    for nch, br, rate in [(6, 448000, 48000), (6, 384000, 44100), (5, 320000, 48000), (4, 192000, 44100),
-                          (3, 128000, 48000), (2, 192000, 48000), (2, 96000, 48000), (1, 64000, 32000),
-                          (2, 128000, 22050), (6, 640000, 48000), (6, 32000, 48000)]:
-        lfe = nch == 6
-        for s in range(3):
-            nfr = 4
-            pcm = synth_pcm(7, 10 * nch + s, nch, 1536 * nfr, rate, noise=[0.02, 0.2, 0.001][s], bursts=(s == 1))
-            fb = ora.init(rate, br, nch)
-            for f in range(nfr):
-                want = ora.frame(pcm[f * 1536:(f + 1) * 1536])
-                wbits = np.unpackbits(want)
-                coef, strategy, enc, bap, shift = ora.get(0), ora.get(2), ora.get(3), ora.get(4), ora.get(5)
-                if ora.get(6)[3]:
-                    bap = np.zeros_like(bap)
-                fr = Frame(fb * 8)
-                for blk, (mp, mant) in enumerate(side_lengths(nch, lfe, acmod_of[nch], strategy, bap)):
-                    end = pack_block(fr, blk, nch, lfe, coef, enc, bap, shift, mp)
-                    assert end == mp + mant, (blk, end, mp, mant)
-                    lim = min(mp + mant, fb * 8 - 16)
-                    if not (fr.bits[mp:lim] == wbits[mp:lim]).all():
-                        bad = np.nonzero(fr.bits[mp:lim] != wbits[mp:lim])[0]
-                        raise SystemExit("mismatch cfg %s stream %d frame %d block %d at +%d of %d" %
-                                         ((nch, br, rate), s, f, blk, bad[0], mant))
-                    total += mant
-        print("ok", nch, br, rate)
-    print("all mantissa bits equal:", total)
-
-
-if __name__ == "__main__":
-    main()
+    for s in range(3):
+        nfr = 3
+        pcm = synth_pcm(7, 10 * nch + s, nch, 1536 * nfr, rate, noise=[0.02, 0.2, 0.001][s], bursts=(s == 1))
+        fb = ora.init(rate, br, nch)
+        for f in range(nfr):
+            want = ora.frame(pcm[f * 1536:(f + 1) * 1536])
+            wbits = np.unpackbits(want)
+            coef, strategy, enc, bap, shift = ora.get(0), ora.get(2), ora.get(3), ora.get(4), ora.get(5)
+            if ora.get(6)[3]:
+                bap = np.zeros_like(bap)                              # a failed search packs no mantissas
+            fr = Frame(fb * 8)
+            for blk, (mp, mant) in enumerate(side_lengths(nch, lfe, acmod_of[nch], strategy, bap)):
+                end = pack_block(fr, blk, nch, lfe, coef, enc, bap, shift, mp)
+                assert end == mp + mant, (blk, end, mp, mant)
+                lim = min(mp + mant, fb * 8 - 16)
+                assert (fr.bits[mp:lim] == wbits[mp:lim]).all(), (s, f, blk)
+                total += mant
+    assert total > 0 or br == 32000
