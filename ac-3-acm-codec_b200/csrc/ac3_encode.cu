@@ -773,25 +773,9 @@ ac3_encode_kernel(const EncParams P)
             if (active) {
                 __syncwarp();
                 const int bits = e2_exponents(S, P, warp, lane, sets);
-                if (lane == 0) S.exp_bits[warp] = bits;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                // everything but mantissas (:880-916)
-                static const int inc[8] = {0, 0, 2, 2, 2, 4, 2, 4};
-                int fb = 65 + inc[P.acmod];
-                for (int ch = 0; ch < P.nch_all; ch++) fb += S.exp_bits[ch];
-                for (int blk = 0; blk < 6; blk++) {
-                    fb += P.nch * 2 + 2;
-                    if (P.acmod == 2) fb++;
-                    fb += 2 * P.nch;
-                    if (P.lfe) fb++;
-                    for (int ch = 0; ch < P.nch; ch++)
-                        if (S.strategy[blk][ch]) fb += 6 + 2;
-                    fb += 4;
-                }
-                fb += 1 + 2 * 4 + 3 + 6 + P.nch_all * (4 + 3) + 2 + 16;
-                S.frame_bits = fb;
+                // this channel's share of everything but mantissas (:880-916): its exponent sections and, per set of a
+                // full-bandwidth channel, chbwcod and the gain range field
+                if (lane == 0) S.exp_bits[warp] = bits + (warp < P.nch ? 8 * __popc(sets) : 0);
             }
             // ================= E3 =================
             if (active) {
@@ -799,6 +783,14 @@ ac3_encode_kernel(const EncParams P)
                 for (uint32_t m = sets; m; m &= m - 1) e3_mask(S, T, P, __ffs(m) - 1, warp, lane, psd);
             }
             __syncthreads();
+            {
+                // the rest of it is the same for every frame of the call
+                static const int inc[8] = {0, 0, 2, 2, 2, 4, 2, 4};
+                int fb = 65 + inc[P.acmod] + 6 * (P.nch * 2 + 2 + (P.acmod == 2 ? 1 : 0) + 2 * P.nch + (P.lfe ? 1 : 0) + 4)
+                       + 1 + 2 * 4 + 3 + 6 + P.nch_all * (4 + 3) + 2 + 16;
+                for (int ch = 0; ch < P.nch_all; ch++) fb += S.exp_bits[ch];
+                if (tid == 0) S.frame_bits = fb;                         // (read after the first pass's barrier)
+            }
             Search q;
             q.cs = S.cs;
             q.probe_cs = q.cs;                                           // warm start (:921)
