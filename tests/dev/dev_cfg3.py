@@ -1,8 +1,8 @@
 """Developer check: throughput on config-3-like streams (5.1 640 kb/s, block switching, coupling, dynrng, deltba
 from tests/bitstream_writer.py) next to the stationary config-2 corpus, device-resident, stereo float out."""
 import os, sys, time
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import numpy as np, torch
 import __graft_entry__ as g
 from refbind import Oracle

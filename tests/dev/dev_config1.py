@@ -6,7 +6,7 @@
   a52dec_b200      this repository's batch CLI: the whole file in one a52_batch_decode     (ac-3-acm-codec_b200/a52dec_b200)
 for a 60 s stream (the config) and a 2 h one (a film's worth: 225 000 frames)."""
 import json, os, subprocess, sys, time
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from refbind import RefAc3Enc

@@ -1,7 +1,7 @@
 """Developer check: statuses of one synthetic stream through the batch API for several requests/formats."""
 import sys, os, time
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import numpy as np
 import __graft_entry__ as g
 from refbind import Oracle

@@ -6,7 +6,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 spec = importlib.util.spec_from_file_location("ac3_b200", os.path.join(ROOT, "ac-3-acm-codec_b200", "__init__.py"))
 eng = importlib.util.module_from_spec(spec)
