@@ -472,7 +472,45 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
     __syncwarp();
     int16_t* mk = S.u.e1.mask[blk][ch];
     int fast21 = 0, slow21 = 0;                                          // the recurrences' state after band 21
-    if (lane == 0) {
+    if (bndend > 22) {
+        // Bands 0..21 of a full-bandwidth channel, lane = band (:262-330 of the reference, which walks them one by one).
+        // The low-frequency compensation is a chain of steps x -> max(x - a, c) - "reset to 384 / 320" (a = inf), "down by
+        // 64 / 128, not below 0", "hold" (a = 0, c = -inf) - chosen by the band's psd and the next; such steps compose
+        // ((a1, c1) then (a2, c2) = (a1 + a2, max(c1 - a2, c2))), so the chain is a warp scan.  fast and slow restart at
+        // band begin - 1 (the first band in 2..6 whose psd does not fall, else 6) and decay from there: prefix maxima of
+        // psd + band * decay, as for the bands above 21.
+        constexpr int kInf = 1 << 20;
+        const int b = lane;
+        const bool on = b < 22;
+        const int p0 = psd[on ? b : 0], p1 = psd[on ? b + 1 : 0];
+        int a, c;
+        if (b < 20) {
+            if (p0 + 256 == p1) { a = kInf; c = b < 7 ? 384 : 320; }
+            else if (p0 > p1) { a = 64; c = 0; }
+            else { a = 0; c = -kInf; }
+        } else { a = 128; c = 0; }
+        const uint32_t rise = __ballot_sync(0xffffffffu, b >= 2 && b <= 6 && p0 <= p1);
+        const int begin = rise ? __ffs(rise) : 7;                        // (lowest such band) + 1
+        const bool live = on && b >= begin - 1;
+        int pf = live ? p0 - fgain + b * fdecay : -kInf, ps = live ? p0 - sgain + b * sdecay : -kInf;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a1 = __shfl_up_sync(0xffffffffu, a, o), c1 = __shfl_up_sync(0xffffffffu, c, o);
+            const int tf = __shfl_up_sync(0xffffffffu, pf, o), ts = __shfl_up_sync(0xffffffffu, ps, o);
+            if (lane >= o) {
+                c = max(c1 - a, c);
+                a = min(a1 + a, kInf);
+                pf = max(pf, tf);
+                ps = max(ps, ts);
+            }
+        }
+        const int lowcomp = max(-a, c);
+        const int f = pf - b * fdecay, sl = ps - b * sdecay;
+        if (on) mk[b] = (int16_t)(b < begin ? p0 - fgain - lowcomp : max(f - lowcomp, sl));
+        fast21 = __shfl_sync(0xffffffffu, f, 21);
+        slow21 = __shfl_sync(0xffffffffu, sl, 21);
+    } else if (lane == 0) {
+        // the LFE channel's seven bands, one by one
         auto lc1 = [](int a, int b0, int b1) { return (b0 + 256 == b1) ? 384 : (b0 > b1) ? max(a - 64, 0) : a; };
         int lowcomp = 0, fast = 0, slow = 0, begin = 7, bin;
         lowcomp = lc1(lowcomp, psd[0], psd[1]);
@@ -487,8 +525,7 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
             mk[bin] = (int16_t)(fast - lowcomp);
             if (!last_lfe && psd[bin] <= psd[bin + 1]) { begin = bin + 1; break; }
         }
-        const int stop = min(bndend, 22);
-        for (bin = begin; bin < stop; bin++) {
+        for (bin = begin; bin < bndend; bin++) {
             if (!(is_lfe && bin == 6)) {
                 const int b0 = psd[bin], b1 = psd[bin + 1];
                 if (bin < 7) lowcomp = lc1(lowcomp, b0, b1);
@@ -499,14 +536,10 @@ __device__ void e3_mask(EncShared& S, const EncTables& T, const EncParams& P, in
             slow = max(slow - sdecay, psd[bin] - sgain);
             mk[bin] = (int16_t)max(fast - lowcomp, slow);
         }
-        fast21 = fast;
-        slow21 = slow;
     }
     // bands 22 and up: fast = max(fast - fdecay, psd - fgain) and the same for slow are max-plus recurrences without
     // side conditions, i.e. prefix maxima of psd + j * decay: lane j takes band 22 + j
     if (bndend > 22) {
-        fast21 = __shfl_sync(0xffffffffu, fast21, 0);
-        slow21 = __shfl_sync(0xffffffffu, slow21, 0);
         const int bin = 22 + lane;
         const bool on = bin < bndend;
         const int p = on ? psd[bin] : -(1 << 20);
