@@ -117,6 +117,13 @@ struct EncShared {
     uint32_t crcp[6];                    // the warps' parts of the two CRCs
 };
 
+// exponent groups of a coded range for strategy 1 / 2 / 3 (one, two or four bins per exponent; :684-700):
+// (ncoef + 3 gs - 4) / (3 gs) for the two ranges there are - 223 bins (74, 37, 19) and the LFE's 7 (2, 1, 1)
+__device__ __forceinline__ int exp_groups(int strategy, bool is_lfe)
+{
+    return is_lfe ? (strategy == 1 ? 2 : 1) : (strategy == 1 ? 74 : strategy == 2 ? 37 : 19);
+}
+
 __device__ __forceinline__ int ilog2(uint32_t v) { return v ? 31 - __clz(v) : 0; }
 
 // two 16-bit halves -> one word (low halves of re and im), one PRMT
@@ -341,16 +348,15 @@ __device__ int e2_exponents(EncShared& S, const EncParams& P, int ch, int lane, 
     const int ncoef = is_lfe ? 7 : 223;
     // new exponents when the L1 distance to the previous block exceeds 1000 over all 256 bins (:617-640)
     uint32_t newmask = 1;
-    for (int blk = 1; blk < 6; blk++) {
-        int d = 0;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int j = lane + 32 * r;
-            d += abs((int)S.expo[blk][ch][j] - (int)S.expo[blk - 1][ch][j]);
+    {
+        // (a lane takes eight consecutive bins: sums of absolute byte differences, four bytes per instruction)
+        uint2 prev = *reinterpret_cast<const uint2*>(S.expo[0][ch] + 8 * lane);
+        for (int blk = 1; blk < 6; blk++) {
+            const uint2 cur = *reinterpret_cast<const uint2*>(S.expo[blk][ch] + 8 * lane);
+            const uint32_t d = __reduce_add_sync(0xffffffffu, __vsadu4(cur.x, prev.x) + __vsadu4(cur.y, prev.y));
+            if (d > 1000) newmask |= 1u << blk;
+            prev = cur;
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (d > 1000) newmask |= 1u << blk;
     }
     sets = newmask;                                                      // the blocks that start an exponent set
     int bits = 0;
@@ -375,7 +381,7 @@ __device__ int e2_exponents(EncShared& S, const EncParams& P, int ch, int lane, 
         __syncwarp();
         // group minima, dc <= 15 (:684-726); lane owns values 7 lane .. 7 lane + 6 of e1[0 .. ng]
         const int gs = strat == 1 ? 1 : strat == 2 ? 2 : 4;
-        const int ng = ((ncoef + gs * 3 - 4) / (3 * gs)) * 3;
+        const int ng = 3 * exp_groups(strat, is_lfe);
         const uint8_t* ex = S.expo[i][ch];
         int e1[7];
 #pragma unroll
@@ -944,8 +950,7 @@ ac3_encode_kernel(const EncParams P)
                         if (ch >= P.nch_all) continue;
                         const int st = S.strategy[blk][ch];
                         if (st) {
-                            const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
-                            const int ng = (((P.lfe && ch == 5) ? 7 : 223) + gs * 3 - 4) / (3 * gs);
+                            const int ng = exp_groups(st, P.lfe && ch == 5);
                             exp_len[ch] = 4 + 7 * ng + ((P.lfe && ch == 5) ? 0 : 2);
                         }
                         const int* q = S.cnt[S.head[blk][ch]][ch];
@@ -1000,13 +1005,12 @@ ac3_encode_kernel(const EncParams P)
                 // grouped exponents (:1261-1314): warp = channel (the sets are spread evenly over the channels, not
                 // over the blocks), lanes = groups
                 const int ch = warp;
-                const int ncoef = (P.lfe && ch == 5) ? 7 : 223;
                 for (int blk = 0; blk < 6; blk++) {
                     const int st = S.strategy[blk][ch];
                     if (!st) continue;
                     const uint8_t* en = S.enc[blk][ch];
                     const int gs = st == 1 ? 1 : st == 2 ? 2 : 4;
-                    const int ng = (ncoef + gs * 3 - 4) / (3 * gs);
+                    const int ng = exp_groups(st, P.lfe && ch == 5);
                     const uint32_t p0 = S.exp_pos[blk][ch];
                     if (lane == 0) put_bits_atomic(frame, p0, 4, en[0]);
                     for (int g = lane; g < ng; g += 32) {
