@@ -12,12 +12,14 @@
 //       radix-2 FFT, 16-bit storage, halving butterflies), exponents   (:1673-1722, 485-603)
 //   E2  exponent strategy, run minima, group minima, +-2 delta constraint as two
 //       min-plus warp scans                                            (:617-761, 1725-1749)
-//   E3  masking curve once per exponent set, then the SNR-offset search on per-set
-//       class counts (a probe = bap lookup + ballots, no re-derivation of the curve)
-//                                                                      (:220-421, 764-975)
-//   E4  side information, grouped exponents, quantisation, group codes by shared-memory
-//       atomics, bit packing by absolute bit position, both CRCs by a warp-parallel
-//       chunked CRC                                                    (:1113-1638)
+//   E3  masking curve once per exponent set (warp scans: no serial lane), then the SNR-offset
+//       search on per-set class counts: a pass evaluates the next three likely probes by bap
+//       address (packed counters, no re-derivation of the curve) and every warp replays the
+//       reference's state machine on the results                      (:220-421, 764-975)
+//   E4  side information as 64-bit runs; grouped exponents by channel warps; mantissas by
+//       BLOCK warps (a lane owns eight consecutive bins, positions from one packed scan,
+//       group members in per-block rings, ungrouped fields in 64-bit runs); both CRCs over
+//       all six warps with per-thread multipliers                     (:1113-1638)
 //
 // Frames are byte-identical to the reference's (tests/test_encoder_gpu.py).
 #include <cuda_runtime.h>
