@@ -942,21 +942,27 @@ ac3_encode_kernel(const EncParams P)
                 const uint32_t bsi_bits = 16 + 16 + 2 + 6 + 5 + 3 + 3 + (((P.acmod & 1) && P.acmod != 1) ? 2 : 0)
                                         + ((P.acmod & 4) ? 2 : 0) + (P.acmod == 2 ? 2 : 0) + 1 + 5 + 4 + 1 + 3;
                 const int blk = lane < 6 ? lane : 5;
+                // (this is the one serial stretch the other five warps wait for: strategies are read once, runs of
+                // equal-width fields are put together in 32-bit arithmetic before they enter the 64-bit run)
                 uint32_t exp_len[6], len = 0, mant = 0;
+                uint32_t expstr = 0, bwcod = 0;                          // chexpstr of the full-bandwidth channels; chbwcod fields
+                int nnew = 0, lfe_st = 0;
                 {
-                    int nnew = 0, n1 = 0, n2 = 0, n4 = 0;
-                    for (int ch = 0; ch < P.nch; ch++) nnew += S.strategy[blk][ch] != 0;
+                    int n1 = 0, n2 = 0, n4 = 0;
 #pragma unroll
                     for (int ch = 0; ch < 6; ch++) {
                         exp_len[ch] = 0;
                         if (ch >= P.nch_all) continue;
                         const int st = S.strategy[blk][ch];
-                        if (st) {
-                            const int ng = exp_groups(st, P.lfe && ch == 5);
-                            exp_len[ch] = 4 + 7 * ng + ((P.lfe && ch == 5) ? 0 : 2);
+                        const bool ch_lfe = P.lfe && ch == 5;
+                        if (st) exp_len[ch] = 4 + 7 * exp_groups(st, ch_lfe) + (ch_lfe ? 0 : 2);
+                        if (ch_lfe) lfe_st = st;
+                        else {
+                            expstr = (expstr << 2) | (uint32_t)st;
+                            if (st) { bwcod = (bwcod << 6) | 50u; nnew++; }
                         }
-                        const int* q = S.cnt[S.head[blk][ch]][ch];
-                        n1 += q[0]; n2 += q[1]; n4 += q[2]; mant += q[3];
+                        const int4 q = *reinterpret_cast<const int4*>(S.cnt[S.head[blk][ch]][ch]);
+                        n1 += q.x; n2 += q.y; n4 += q.z; mant += q.w;
                         len += exp_len[ch];
                     }
                     mant += 5 * ((n1 + 2) / 3) + 7 * ((n2 + 2) / 3) + 7 * ((n4 + 1) / 2);
@@ -974,15 +980,12 @@ ac3_encode_kernel(const EncParams P)
                 if (lane < 6) {
                     uint32_t pos = bsi_bits + incl - len;
                     BitRun w{0, 0};
-                    w.put(P.nch, 0);                                     // blksw
-                    w.put(P.nch, (1u << P.nch) - 1);                     // dithflag
-                    w.put(1, 0);                                         // dynrnge
+                    w.put(2 * P.nch + 1, ((1u << P.nch) - 1) << 1);      // blksw (zeros), dithflag (ones), dynrnge (0)
                     if (blk == 0) w.put(2, 2); else w.put(1, 0);         // cplstre [cplinu]
                     if (P.acmod == 2) { if (blk == 0) w.put(5, 16); else w.put(1, 0); }
-                    for (int ch = 0; ch < P.nch; ch++) w.put(2, S.strategy[blk][ch]);
-                    if (P.lfe) w.put(1, S.strategy[blk][5]);
-                    for (int ch = 0; ch < P.nch; ch++)
-                        if (S.strategy[blk][ch]) w.put(6, 50);
+                    w.put(2 * P.nch, expstr);                            // chexpstr
+                    if (P.lfe) w.put(1, lfe_st);                         // lfeexpstr
+                    w.put(6 * nnew, bwcod);                              // chbwcod of the channels with new exponents
                     pos = w.flush(frame, pos);                           // at most 11 + 2 + 5 + 10 + 1 + 30 = 59 bits
 #pragma unroll
                     for (int ch = 0; ch < 6; ch++) {
@@ -991,14 +994,18 @@ ac3_encode_kernel(const EncParams P)
                         pos += exp_len[ch];
                     }
                     w = BitRun{0, 0};
-                    w.put(1, blk == 0);
-                    if (blk == 0) w.put(11, (2u << 9) | (1u << 7) | (1u << 5) | (2u << 3) | 4u);
-                    w.put(1, blk == 0);
                     if (blk == 0) {
-                        w.put(6, S.cs);
-                        for (int ch = 0; ch < P.nch_all; ch++) w.put(7, ((uint32_t)S.fs << 3) | 4u);
+                        // baie + the five allocation parameters, snroffste + csnroffst, then fsnroffst / fgaincod per channel
+                        w.put(12, (1u << 11) | (2u << 9) | (1u << 7) | (1u << 5) | (2u << 3) | 4u);
+                        w.put(7, (1u << 6) | (uint32_t)S.cs);
+                        const uint32_t f7 = ((uint32_t)S.fs << 3) | 4u, f21 = f7 | f7 << 7 | f7 << 14;
+                        int ch = 0;
+                        for (; ch + 3 <= P.nch_all; ch += 3) w.put(21, f21);
+                        for (; ch < P.nch_all; ch++) w.put(7, f7);
+                        w.put(2, 0);
+                    } else {
+                        w.put(4, 0);                                     // baie, snroffste, deltbaie, skiple: all off
                     }
-                    w.put(2, 0);
                     S.mant_pos[blk] = w.flush(frame, pos);               // at most 1 + 11 + 1 + 6 + 42 + 2 = 63 bits
                 }
             }
